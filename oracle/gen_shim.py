@@ -1,0 +1,242 @@
+"""ORACLE (test infrastructure) -- generator of the xobjects-side C API.
+
+The reference's element physics (`/root/reference/xtrack/**/*.h`) is written
+against an accessor API that the external `xobjects` package generates at JIT
+time and that therefore does not exist in the reference tree:
+
+  * `LocalParticle` struct + `LocalParticle_{get,set,add_to,scale}_<field>`,
+    `LocalParticle_exchange`, `Particles_to_LocalParticle`,
+    `LocalParticle_to_Particles`       (spec: xtrack/particles/particles.py:86-408)
+  * `ParticlesData_*` accessors        (call sites particles.py:143-181)
+  * `<Element>Data` structs/accessors  (call sites in elements_src/*.h)
+  * `ParticlesMonitorData_*`, `LastTurnsMonitorData_*`, `LastTurnsData_*`
+                                       (monitors/*.h)
+  * per-class `*_track_local_particle_with_transformations`
+                                       (base_element.py:83-127 -> the template
+                                        headers/track_local_particle_with_transformations.h)
+
+This script writes that API as plain C over plain structs into
+`oracle/_ref/gen/xt_generated.h`.  It is *our* restatement of generated glue;
+the physics headers it includes are compiled unmodified from /root/reference.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+from element_specs import SPECS, CLASS_ORDER, TYPE_ID, all_fields  # noqa: E402
+
+SIZE_VARS = [('int64_t', '_capacity'), ('int64_t', '_num_active_particles'),
+             ('int64_t', '_num_lost_particles'), ('int64_t', 'start_tracking_at_element')]
+SCALAR_VARS = [('double', 'q0'), ('double', 'mass0'), ('double', 't_sim')]
+PER_PARTICLE = (
+    [('double', nn) for nn in (
+        'p0c', 'gamma0', 'beta0', 's', 'zeta', 'x', 'y', 'px', 'py', 'ptau', 'delta',
+        'rpp', 'rvv', 'chi', 'charge_ratio', 'weight', 'ax', 'ay', 'spin_x',
+        'spin_y', 'spin_z', 'anomalous_magnetic_moment')]
+    + [('int64_t', nn) for nn in ('pdg_id', 'particle_id', 'at_element', 'at_turn',
+                                  'state', 'parent_particle_id')]
+    + [('uint32_t', nn) for nn in ('_rng_s1', '_rng_s2', '_rng_s3', '_rng_s4')])
+
+CTYPE = {'f64': 'double', 'i64': 'int64_t'}
+
+
+def gen_particles_api():
+    L = []
+    L.append('/* ---- ParticlesData: SoA of pointers (layout chosen by the oracle) ---- */')
+    L.append('typedef struct ParticlesData_s {')
+    for tt, vv in SIZE_VARS + SCALAR_VARS:
+        L.append(f'    {tt} {vv};')
+    for tt, vv in PER_PARTICLE:
+        L.append(f'    {tt}* {vv};')
+    L.append('} *ParticlesData;')
+    for tt, vv in SIZE_VARS + SCALAR_VARS:
+        L.append(f'GPUFUN {tt} ParticlesData_get_{vv}(ParticlesData p){{ return p->{vv}; }}')
+        L.append(f'GPUFUN void ParticlesData_set_{vv}(ParticlesData p, {tt} v){{ p->{vv} = v; }}')
+    for tt, vv in PER_PARTICLE:
+        L.append(f'GPUFUN {tt}* ParticlesData_getp1_{vv}(ParticlesData p, int64_t i){{ return p->{vv} + i; }}')
+        L.append(f'GPUFUN {tt} ParticlesData_get_{vv}(ParticlesData p, int64_t i){{ return p->{vv}[i]; }}')
+        L.append(f'GPUFUN void ParticlesData_set_{vv}(ParticlesData p, int64_t i, {tt} v){{ p->{vv}[i] = v; }}')
+
+    L.append('/* ---- LocalParticle (particles.py:96-109) ---- */')
+    L.append('typedef struct {')
+    for tt, vv in SIZE_VARS + SCALAR_VARS:
+        L.append(f'    {tt} {vv};')
+    for tt, vv in PER_PARTICLE:
+        L.append(f'    {tt}* {vv};')
+    L += ['    int64_t ipart;', '    int64_t endpart;', '    uint64_t track_flags;',
+          '    double line_length;', '    int8_t* io_buffer;', '} LocalParticle;']
+    L.append('GPUFUN int8_t* LocalParticle_get_io_buffer(LocalParticle* part){ return part->io_buffer; }')
+    L.append('GPUFUN uint64_t LocalParticle_check_track_flag(LocalParticle* part, uint8_t index){'
+             ' return (part->track_flags >> index) & 1; }')
+    for tt, vv in SIZE_VARS + SCALAR_VARS:
+        L.append(f'GPUFUN {tt} LocalParticle_get_{vv}(LocalParticle* part){{ return part->{vv}; }}')
+    for tt, vv in PER_PARTICLE:
+        L.append(f'GPUFUN {tt} LocalParticle_get_{vv}(LocalParticle* part){{ return part->{vv}[part->ipart]; }}')
+        for op, sym in (('set', '='), ('add_to', '+='), ('scale', '*=')):
+            L.append(f'GPUFUN void LocalParticle_{op}_{vv}(LocalParticle* part, {tt} value){{')
+            L.append(f'#ifndef FREEZE_VAR_{vv}')
+            L.append(f'    part->{vv}[part->ipart] {sym} value;')
+            L.append('#endif')
+            L.append('}')
+    L.append('GPUFUN void LocalParticle_exchange(LocalParticle* part, int64_t i1, int64_t i2){')
+    for tt, vv in PER_PARTICLE:
+        L.append(f'    {{ {tt} temp = part->{vv}[i2]; part->{vv}[i2] = part->{vv}[i1]; part->{vv}[i1] = temp; }}')
+    L.append('}')
+    L.append('GPUFUN void Particles_to_LocalParticle(ParticlesData source, LocalParticle* dest, int64_t id, int64_t eid){')
+    for tt, vv in SIZE_VARS + SCALAR_VARS:
+        L.append(f'    dest->{vv} = ParticlesData_get_{vv}(source);')
+    for tt, vv in PER_PARTICLE:
+        L.append(f'    dest->{vv} = ParticlesData_getp1_{vv}(source, 0);')
+    L += ['    dest->ipart = id;', '    dest->endpart = eid;', '}']
+    L.append('GPUFUN void LocalParticle_to_Particles(LocalParticle* source, ParticlesData dest, int64_t id, int64_t set_scalar){')
+    L.append('    if (set_scalar){')
+    for tt, vv in SIZE_VARS + SCALAR_VARS:
+        L.append(f'        ParticlesData_set_{vv}(dest, LocalParticle_get_{vv}(source));')
+    L.append('    }')
+    for tt, vv in PER_PARTICLE:
+        L.append(f'    ParticlesData_set_{vv}(dest, id, LocalParticle_get_{vv}(source));')
+    L.append('}')
+    return '\n'.join(L)
+
+
+def gen_element_struct(name):
+    L = [f'/* ---- {name}Data ---- */', f'typedef struct {name}Data_s {{']
+    ff = all_fields(name)
+    for fn, kind in ff:
+        if kind == 'arr':
+            L.append(f'    double* {fn}; int64_t {fn}__len;')
+        else:
+            L.append(f'    {CTYPE[kind]} {fn};')
+    L.append(f'}} *{name}Data;')
+    for fn, kind in ff:
+        if kind == 'arr':
+            L.append(f'GPUFUN double {name}Data_get_{fn}({name}Data el, int64_t i){{ return el->{fn}[i]; }}')
+            L.append(f'GPUFUN double* {name}Data_getp1_{fn}({name}Data el, int64_t i){{ return el->{fn} + i; }}')
+            L.append(f'GPUFUN int64_t {name}Data_len_{fn}({name}Data el){{ return el->{fn}__len; }}')
+        else:
+            L.append(f'GPUFUN {CTYPE[kind]} {name}Data_get_{fn}({name}Data el){{ return el->{fn}; }}')
+    if SPECS[name].get('internal_record'):
+        L.append(f'#define {name}Data_getp_internal_record(el, part) (NULL)')
+    return '\n'.join(L)
+
+
+def gen_with_transformations(name):
+    """Mirror of base_element.py:83-127."""
+    spec = SPECS[name]
+    opts = [('ELEMENT_NAME', name)]
+    if spec.get('rot_shift'):
+        opts.append(('ALLOW_ROT_AND_SHIFT', 1))
+    if spec.get('curved'):
+        opts.append(('CURVED', 1))
+    if spec.get('dyn_thick'):
+        opts.append(('IS_THICK_DYNAMIC', 1))
+    elif spec.get('isthick'):
+        opts.append(('IS_THICK', 1))
+    L = [f'#define {k} {v}' for k, v in opts]
+    L.append('#include "xtrack/headers/track_local_particle_with_transformations.h"')
+    L += [f'#undef {k}' for k, _ in opts]
+    return '\n'.join(L)
+
+
+MONITOR_API = r'''
+/* ---- ParticlesMonitorData (monitors/particles_monitor.py:180-192) ---- */
+typedef struct ParticlesMonitorData_s {
+    int64_t start_at_turn, stop_at_turn, part_id_start, part_id_end, ebe_mode,
+            n_records, n_repetitions, repetition_period, flag_auto_to_numpy;
+    ParticlesData data;
+} *ParticlesMonitorData;
+#define XTB_MON_GET(f) GPUFUN int64_t ParticlesMonitorData_get_##f(ParticlesMonitorData el){ return el->f; }
+XTB_MON_GET(start_at_turn) XTB_MON_GET(stop_at_turn) XTB_MON_GET(part_id_start)
+XTB_MON_GET(part_id_end) XTB_MON_GET(ebe_mode) XTB_MON_GET(n_repetitions)
+XTB_MON_GET(repetition_period)
+GPUFUN ParticlesData ParticlesMonitorData_getp_data(ParticlesMonitorData el){ return el->data; }
+
+/* ---- LastTurnsMonitorData (monitors/last_turns_monitor.py:18-44) ---- */
+typedef struct LastTurnsData_s {
+    uint32_t* lost_at_offset; uint32_t* particle_id; uint32_t* at_turn;
+    float *x, *px, *y, *py, *delta, *zeta;
+} *LastTurnsData;
+typedef struct LastTurnsMonitorData_s {
+    int64_t particle_id_start, num_particles, n_last_turns, every_n_turns;
+    LastTurnsData data;
+} *LastTurnsMonitorData;
+#define XTB_LTM_GET(f) GPUFUN int64_t LastTurnsMonitorData_get_##f(LastTurnsMonitorData el){ return el->f; }
+XTB_LTM_GET(particle_id_start) XTB_LTM_GET(num_particles) XTB_LTM_GET(n_last_turns)
+XTB_LTM_GET(every_n_turns)
+GPUFUN LastTurnsData LastTurnsMonitorData_getp_data(LastTurnsMonitorData el){ return el->data; }
+#define XTB_LTD_SET(f, T) GPUFUN void LastTurnsData_set_##f(LastTurnsData d, int64_t i, T v){ d->f[i] = v; }
+XTB_LTD_SET(lost_at_offset, uint32_t) XTB_LTD_SET(particle_id, uint32_t) XTB_LTD_SET(at_turn, uint32_t)
+XTB_LTD_SET(x, float) XTB_LTD_SET(px, float) XTB_LTD_SET(y, float) XTB_LTD_SET(py, float)
+XTB_LTD_SET(delta, float) XTB_LTD_SET(zeta, float)
+'''
+
+RECORD_STUBS = r'''
+/* In-kernel photon logging is outside the contract: the record handle is NULL
+   everywhere (synrad_spectrum.h:505 checks it), these only satisfy the compiler. */
+typedef struct RecordIndex_s { int64_t dummy; } *RecordIndex;
+typedef struct SynchrotronRadiationRecordData_s { int64_t dummy; } *SynchrotronRadiationRecordData;
+GPUFUN RecordIndex SynchrotronRadiationRecordData_getp__index(SynchrotronRadiationRecordData r){ (void)r; return NULL; }
+GPUFUN int64_t RecordIndex_get_slot(RecordIndex r){ (void)r; return -1; }
+#define XTB_REC_SET(f, T) GPUFUN void SynchrotronRadiationRecordData_set_##f(SynchrotronRadiationRecordData r, int64_t i, T v){ (void)r; (void)i; (void)v; }
+XTB_REC_SET(photon_energy, double) XTB_REC_SET(at_element, int64_t) XTB_REC_SET(at_turn, int64_t)
+XTB_REC_SET(particle_id, int64_t) XTB_REC_SET(particle_delta, double)
+'''
+
+
+def generate():
+    out = []
+    out.append('/* GENERATED by oracle/gen_shim.py -- ORACLE test infrastructure, do not edit. */')
+    out.append('#ifndef XTB_ORACLE_GENERATED_H\n#define XTB_ORACLE_GENERATED_H')
+    out.append('#include "xobjects/headers/common.h"')
+    out.append('#define XS_FLAG_BACKTRACK (0)\n#define XS_FLAG_KILL_CAVITY_KICK (2)\n'
+               '#define XS_FLAG_IGNORE_GLOBAL_APERTURE (3)\n#define XS_FLAG_IGNORE_LOCAL_APERTURE (4)\n'
+               '#define XS_FLAG_SR_TAPER (5)\n#define XS_FLAG_SR_KICK_SAME_AS_FIRST (6)')
+    out.append('#include "xtrack/particles/rng_src/base_rng.h"')
+    out.append(gen_particles_api())
+    out.append('#include "xtrack/particles/rng_src/particles_rng.h"')
+    out.append('#include "xtrack/particles/local_particle_custom_api.h"')
+    out.append('#include "xtrack/headers/constants.h"')
+    out.append('#include "xtrack/headers/checks.h"')
+    out.append('#include "xtrack/headers/particle_states.h"')
+    out.append(RECORD_STUBS)
+    out.append('#ifndef XTRACK_MULTIPOLE_NO_SYNRAD')
+    out.append('#include "xtrack/random/random_src/uniform.h"')
+    out.append('#include "xtrack/random/random_src/uniform_accurate.h"')
+    out.append('#include "xtrack/random/random_src/exponential.h"')
+    out.append('#endif')
+    out.append('#include "xtrack/beam_elements/elements_src/track_srotation.h"')
+    out.append('#include "xtrack/beam_elements/elements_src/track_drift.h"')
+    out.append(MONITOR_API)
+    out.append('#include "xtrack/monitors/particles_monitor.h"')
+    out.append('#include "xtrack/monitors/last_turns_monitor.h"')
+    for name in CLASS_ORDER:
+        out.append(gen_element_struct(name))
+        out.append(f'#include "xtrack/beam_elements/elements_src/{SPECS[name]["header"]}"')
+        out.append(gen_with_transformations(name))
+    # dispatch (tracker.py:660-697)
+    out.append('/* ---- element dispatch: tracker.py:660-697 ---- */')
+    out.append('GPUFUN void xtb_oracle_dispatch(int64_t elem_type, void* el, LocalParticle* lpart){')
+    out.append('    switch(elem_type){')
+    for name in CLASS_ORDER:
+        out.append(f'        case {TYPE_ID[name]}:')
+        out.append(f'            {name}_track_local_particle_with_transformations(({name}Data) el, lpart);')
+        if SPECS[name].get('isthick') is True:
+            out.append('            #ifdef XTRACK_GLOBAL_XY_LIMIT')
+            out.append('            global_aperture_check(lpart);')
+            out.append('            #endif')
+        out.append('            break;')
+    out.append('        case 1000: ParticlesMonitor_track_local_particle((ParticlesMonitorData) el, lpart); break;')
+    out.append('        case 1001: LastTurnsMonitor_track_local_particle((LastTurnsMonitorData) el, lpart); break;')
+    out.append('    }\n}')
+    out.append('#endif')
+    return '\n'.join(out) + '\n'
+
+
+if __name__ == '__main__':
+    dest = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, '_ref', 'gen')
+    os.makedirs(dest, exist_ok=True)
+    with open(os.path.join(dest, 'xt_generated.h'), 'w') as fid:
+        fid.write(generate())
+    print('wrote', os.path.join(dest, 'xt_generated.h'))

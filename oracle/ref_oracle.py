@@ -1,0 +1,286 @@
+"""ORACLE driver (test infrastructure; only tests/, smoke() and bench.py's CPU
+legs may import this).
+
+Runs the reference's own tracking code -- the unmodified physics headers of
+/root/reference compiled by `build_ref.py` into `oracle/_ref/libxt_ref_*.so` --
+on host numpy arrays.  The element structs it fills are the ones `gen_shim.py`
+declares from `element_specs.py`.
+
+Particle ordering: the CPU contexts of the reference permute particles (lost
+ones are swapped to the end, local_particle_custom_api.h:108-164); results are
+therefore returned sorted by `particle_id` when `restore_order=True`.
+"""
+import ctypes as ct
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
+
+import build_ref                                   # noqa: E402
+from element_specs import SPECS, TYPE_ID, all_fields   # noqa: E402
+
+LAST_INVALID_STATE = -999999999
+
+F64_VARS = ('p0c', 'gamma0', 'beta0', 's', 'zeta', 'x', 'y', 'px', 'py', 'ptau',
+            'delta', 'rpp', 'rvv', 'chi', 'charge_ratio', 'weight', 'ax', 'ay',
+            'spin_x', 'spin_y', 'spin_z', 'anomalous_magnetic_moment')
+I64_VARS = ('pdg_id', 'particle_id', 'at_element', 'at_turn', 'state',
+            'parent_particle_id')
+U32_VARS = ('_rng_s1', '_rng_s2', '_rng_s3', '_rng_s4')
+ALL_VARS = F64_VARS + I64_VARS + U32_VARS
+_NP = {**{n: np.float64 for n in F64_VARS}, **{n: np.int64 for n in I64_VARS},
+       **{n: np.uint32 for n in U32_VARS}}
+_CT = {np.float64: ct.c_double, np.int64: ct.c_int64, np.uint32: ct.c_uint32}
+
+
+class ParticlesDataC(ct.Structure):
+    _fields_ = ([(n, ct.c_int64) for n in ('_capacity', '_num_active_particles',
+                                           '_num_lost_particles',
+                                           'start_tracking_at_element')]
+                + [(n, ct.c_double) for n in ('q0', 'mass0', 't_sim')]
+                + [(n, ct.POINTER(_CT[_NP[n]])) for n in ALL_VARS])
+
+
+class ParticlesMonitorC(ct.Structure):
+    _fields_ = ([(n, ct.c_int64) for n in (
+        'start_at_turn', 'stop_at_turn', 'part_id_start', 'part_id_end', 'ebe_mode',
+        'n_records', 'n_repetitions', 'repetition_period', 'flag_auto_to_numpy')]
+        + [('data', ct.POINTER(ParticlesDataC))])
+
+
+class LastTurnsDataC(ct.Structure):
+    _fields_ = ([(n, ct.POINTER(ct.c_uint32)) for n in ('lost_at_offset', 'particle_id', 'at_turn')]
+                + [(n, ct.POINTER(ct.c_float)) for n in ('x', 'px', 'y', 'py', 'delta', 'zeta')])
+
+
+class LastTurnsMonitorC(ct.Structure):
+    _fields_ = ([(n, ct.c_int64) for n in ('particle_id_start', 'num_particles',
+                                           'n_last_turns', 'every_n_turns')]
+                + [('data', ct.POINTER(LastTurnsDataC))])
+
+
+_STRUCTS = {}
+
+
+def _struct_for(name):
+    if name not in _STRUCTS:
+        ff = []
+        for fn, kind in all_fields(name):
+            if kind == 'arr':
+                ff += [(fn, ct.POINTER(ct.c_double)), (fn + '__len', ct.c_int64)]
+            else:
+                ff.append((fn, ct.c_double if kind == 'f64' else ct.c_int64))
+        _STRUCTS[name] = type(name + 'DataC', (ct.Structure,), {'_fields_': ff})
+    return _STRUCTS[name]
+
+
+_LIBS = {}
+
+
+def available():
+    return os.path.exists(build_ref.lib_path('serial')) or build_ref.available()
+
+
+def load(variant='serial'):
+    if variant not in _LIBS:
+        path = build_ref.lib_path(variant)
+        if build_ref.available():
+            build_ref.build([variant])
+        if not os.path.exists(path):
+            raise RuntimeError(f'{path} missing and /root/reference not available to build it')
+        lib = ct.CDLL(path)
+        lib.xt_ref_track_line.restype = None
+        lib.xt_ref_track_line.argtypes = [
+            ct.POINTER(ParticlesDataC), ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_int64),
+            ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int,
+            ct.c_double, ct.c_void_p, ct.c_uint64]
+        lib.xt_ref_set_global_xy_limit.argtypes = [ct.c_double]
+        lib.xt_ref_init_rand_gen.argtypes = [ct.POINTER(ParticlesDataC),
+                                             ct.POINTER(ct.c_uint32), ct.c_int]
+        lib.xt_ref_num_threads.restype = ct.c_int
+        _LIBS[variant] = lib
+    return _LIBS[variant]
+
+
+class HostParticles:
+    """Plain numpy SoA + the C view of it."""
+
+    def __init__(self, fields, q0=1.0, mass0=938272088.16, t_sim=0.0):
+        n = len(fields['x'])
+        self.arrays = {nn: np.ascontiguousarray(fields[nn], dtype=_NP[nn]).copy()
+                       for nn in ALL_VARS}
+        self.q0, self.mass0, self.t_sim = q0, mass0, t_sim
+        self.capacity = n
+        self.c = ParticlesDataC()
+        self.c._capacity = n
+        self.c.start_tracking_at_element = -1
+        self.c.q0, self.c.mass0, self.c.t_sim = q0, mass0, t_sim
+        for nn in ALL_VARS:
+            setattr(self.c, nn, self.arrays[nn].ctypes.data_as(ct.POINTER(_CT[_NP[nn]])))
+        self.reorganize()
+
+    @classmethod
+    def from_particles(cls, p):
+        """From an `xtrack_b200.Particles` (any device)."""
+        return cls({nn: p.get(nn) for nn in ALL_VARS}, q0=p.q0, mass0=p.mass0,
+                   t_sim=p.t_sim)
+
+    def reorganize(self):
+        st = self.arrays['state']
+        act = st > 0
+        lost = (st < 1) & (st > LAST_INVALID_STATE)
+        na, nl = int(act.sum()), int(lost.sum())
+        if not act[:na].all():
+            for nn in ALL_VARS:
+                if nn.startswith('_rng'):
+                    continue
+                vv = self.arrays[nn]
+                va, vl = vv[act].copy(), vv[lost].copy()
+                vv[:na] = va
+                vv[na:na + nl] = vl
+                vv[na + nl:] = LAST_INVALID_STATE
+        self.c._num_active_particles = na
+        self.c._num_lost_particles = nl
+
+    def sorted_by_id(self):
+        """dict of arrays ordered by particle_id (allocated particles only)."""
+        st = self.arrays['state']
+        alloc = np.where(st > LAST_INVALID_STATE)[0]
+        order = alloc[np.argsort(self.arrays['particle_id'][alloc], kind='stable')]
+        return {nn: self.arrays[nn][order].copy() for nn in ALL_VARS}
+
+
+def _attr(el, name, fn):
+    spec = SPECS[name]
+    an = spec.get('attr', {}).get(fn, fn)
+    if hasattr(el, an):
+        return getattr(el, an)
+    if fn in spec.get('defaults', {}):
+        return spec['defaults'][fn]
+    if fn == '_dummy':
+        return 0
+    raise AttributeError(f'{name}: no attribute {an}')
+
+
+class RefElements:
+    """ElementRefData: array of pointers to element structs + type ids
+    (tracker_data.py:237-255)."""
+
+    def __init__(self, elements):
+        self._keep = []
+        n = len(elements)
+        self.ptrs = (ct.c_void_p * n)()
+        self.type_ids = (ct.c_int64 * n)()
+        cache = {}
+        for ii, el in enumerate(elements):
+            key = id(el)
+            if key not in cache:
+                cache[key] = self._make(el)
+            self.ptrs[ii], self.type_ids[ii] = cache[key]
+
+    def _make(self, el):
+        name = type(el).__name__
+        if name == 'ParticlesMonitor':
+            return self._make_monitor(el), 1000
+        if name == 'LastTurnsMonitor':
+            return self._make_last_turns(el), 1001
+        if name not in SPECS:
+            raise NotImplementedError(f'oracle: element class {name} not supported')
+        st = _struct_for(name)()
+        for fn, kind in all_fields(name):
+            vv = _attr(el, name, fn)
+            if kind == 'arr':
+                arr = np.ascontiguousarray(vv, dtype=np.float64)
+                self._keep.append(arr)
+                setattr(st, fn, arr.ctypes.data_as(ct.POINTER(ct.c_double)))
+                setattr(st, fn + '__len', len(arr))
+            elif kind == 'f64':
+                setattr(st, fn, float(vv))
+            else:
+                setattr(st, fn, int(vv))
+        self._keep.append(st)
+        return ct.addressof(st), TYPE_ID[name]
+
+    def _make_monitor(self, mon):
+        cm, keep = make_monitor_struct(mon)
+        self._keep += [cm, keep]
+        return ct.addressof(cm)
+
+    def _make_last_turns(self, mon):
+        d = LastTurnsDataC()
+        for nn in ('lost_at_offset', 'particle_id', 'at_turn'):
+            setattr(d, nn, mon._host[nn].ctypes.data_as(ct.POINTER(ct.c_uint32)))
+        for nn in ('x', 'px', 'y', 'py', 'delta', 'zeta'):
+            setattr(d, nn, mon._host[nn].ctypes.data_as(ct.POINTER(ct.c_float)))
+        cm = LastTurnsMonitorC()
+        cm.particle_id_start = mon.particle_id_start
+        cm.num_particles = mon.num_particles
+        cm.n_last_turns = mon.n_last_turns
+        cm.every_n_turns = mon.every_n_turns
+        cm.data = ct.pointer(d)
+        self._keep += [d, cm]
+        return ct.addressof(cm)
+
+
+class HostMonitor:
+    """Host ParticlesMonitor record store for the oracle (zero-initialised,
+    monitors/particles_monitor.py:78-104)."""
+
+    def __init__(self, start_at_turn, stop_at_turn, part_id_start, part_id_end,
+                 ebe_mode=0, n_repetitions=1, repetition_period=-1):
+        self.start_at_turn, self.stop_at_turn = int(start_at_turn), int(stop_at_turn)
+        self.part_id_start, self.part_id_end = int(part_id_start), int(part_id_end)
+        self.ebe_mode = int(ebe_mode)
+        self.n_repetitions, self.repetition_period = int(n_repetitions), int(repetition_period)
+        n_turns = self.stop_at_turn - self.start_at_turn
+        self.n_records = n_turns * (self.part_id_end - self.part_id_start) * self.n_repetitions
+        self.arrays = {nn: np.zeros(self.n_records, dtype=_NP[nn]) for nn in ALL_VARS}
+
+    def field(self, name):
+        n_cols = self.stop_at_turn - self.start_at_turn
+        if self.n_repetitions == 1:
+            return self.arrays[name].reshape(-1, n_cols)
+        return self.arrays[name].reshape(self.n_repetitions, -1, n_cols)
+
+
+def make_monitor_struct(mon):
+    data = ParticlesDataC()
+    data._capacity = mon.n_records
+    for nn in ALL_VARS:
+        setattr(data, nn, mon.arrays[nn].ctypes.data_as(ct.POINTER(_CT[_NP[nn]])))
+    cm = ParticlesMonitorC()
+    for nn in ('start_at_turn', 'stop_at_turn', 'part_id_start', 'part_id_end',
+               'ebe_mode', 'n_records', 'n_repetitions', 'repetition_period'):
+        setattr(cm, nn, getattr(mon, nn))
+    cm.data = ct.pointer(data)
+    return cm, data
+
+
+def track_line(hp, ref_elements, *, num_turns, ele_start, num_ele_track,
+               flag_end_turn_actions, flag_reset_s_at_end_turn, flag_monitor=0,
+               num_ele_line=None, line_length=0.0, monitor=None, track_flags=0,
+               global_xy_limit=1.0, variant='serial'):
+    """One `track_line` launch (argument meaning of tracker.py:546-564)."""
+    lib = load(variant)
+    lib.xt_ref_set_global_xy_limit(float(global_xy_limit))
+    mon_ptr, keep = None, None
+    if monitor is not None:
+        cm, keep = make_monitor_struct(monitor)
+        mon_ptr = ct.addressof(cm)
+    lib.xt_ref_track_line(
+        ct.byref(hp.c), ref_elements.ptrs, ref_elements.type_ids,
+        int(num_turns), int(ele_start), int(num_ele_track),
+        int(bool(flag_end_turn_actions)), int(bool(flag_reset_s_at_end_turn)),
+        int(flag_monitor), int(num_ele_line or len(ref_elements.ptrs)),
+        float(line_length), mon_ptr, int(track_flags))
+
+
+def init_rand_gen(hp, seeds, variant='serial'):
+    lib = load(variant)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    lib.xt_ref_init_rand_gen(ct.byref(hp.c), seeds.ctypes.data_as(ct.POINTER(ct.c_uint32)),
+                             len(seeds))

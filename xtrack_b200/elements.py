@@ -1,0 +1,589 @@
+"""Host-side beam-element model for the tracking hot path.
+
+Each class mirrors the *fields and constructor semantics* of the xtrack element
+of the same name (reference `_xofields` tables and `__init__` logic), so that a
+line stored as xtrack JSON can be loaded with plain `json` and handed either to
+the lowering pass (`xtrack_b200.lowering`, product) or to the reference-header
+oracle (`oracle/`, tests only).  No tracking physics lives here.
+
+Reference field tables / constructors followed:
+  Drift            xtrack/beam_elements/drift.py            (length, model)
+  Marker           xtrack/beam_elements/marker.py
+  Multipole        xtrack/beam_elements/multipole.py:80-97,143-176
+  Quadrupole/...   xtrack/beam_elements/quadrupole.py:65-83, sextupole.py, octupole.py
+  Bend / RBend     xtrack/beam_elements/_common.py:559-743, rbend.py:91-213
+  Cavity           xtrack/beam_elements/cavity.py:63-122
+  DipoleEdge       xtrack/beam_elements/dipole_edge.py:40-134
+  SRotation        xtrack/beam_elements/s_rotation.py:30-82
+  XYShift          xtrack/beam_elements/xy_shift.py
+  LimitRect/Ellipse/Polygon  xtrack/beam_elements/limit_*.py
+  misalignment fields        xtrack/base_element.py:274-282
+  enumerations               xtrack/beam_elements/_common.py:20-83
+"""
+import math
+
+import numpy as np
+
+DEFAULT_MULTIPOLE_ORDER = 5          # _common.py:18
+UNLIMITED = 1e10                     # _aperture_common.py:6
+
+MODEL_DRIFT = {'adaptive': 0, 'expanded': 1, 'exact': 2}
+MODEL_CURVED = {'adaptive': 0, 'full': 1, 'bend-kick-bend': 2, 'rot-kick-rot': 3,
+                'mat-kick-mat': 4, 'drift-kick-drift-exact': 5,
+                'drift-kick-drift-expanded': 6, 'rot-kick-rot-low-order': 7,
+                'rot-kick-rot-high-order': 8, 'expanded': 4}
+MODEL_STRAIGHT = {k: v for k, v in MODEL_CURVED.items()
+                  if v not in (2, 3) or k == 'expanded'}
+MODEL_RF = {k: v for k, v in MODEL_STRAIGHT.items() if v not in (1, 4)}
+INTEGRATOR = {'adaptive': 0, 'teapot': 1, 'yoshida4': 2, 'uniform': 3}
+EDGE_MODEL = {'suppressed': -1, 'linear': 0, 'full': 1, 'dipole-only': 2}
+RBEND_MODEL = {'adaptive': 0, 'curved-body': 1, 'straight-body': 2}
+
+MISALIGN_FIELDS = ('shift_x', 'shift_y', 'shift_s', 'rot_s_rad', 'rot_x_rad',
+                   'rot_y_rad', 'rot_s_rad_no_frame', 'rot_shift_anchor')
+
+# keys that xtrack's JSON carries but that have no effect on tracking
+_IGNORED_KEYS = {'__class__', 'name_associated_aperture', 'prototype', 'extra',
+                 '_isthick', 'hyl', 'auto_to_numpy', 'flag_auto_to_numpy'}
+
+
+def _enum(value, table, what):
+    if value is None:
+        return 0
+    if isinstance(value, str):
+        try:
+            return table[value]
+        except KeyError:
+            raise ValueError(f'Invalid {what}: {value}')
+    return int(value)
+
+
+def _inv_factorial(n):
+    """`1.0 / factorial(n, exact=True)` as in _common.py:366,544."""
+    return 1.0 / math.factorial(int(n))
+
+
+def _f(v):
+    if isinstance(v, (list, tuple, np.ndarray)):
+        v = np.asarray(v).reshape(-1)[0]
+    return float(v)
+
+
+def _prepare_multipolar_params(order, **arrays):
+    """Pads coefficient arrays to a common length (reference _common.py:481-546)."""
+    order = order or 0
+    lengths = [len(a) if a is not None else 0 for a in arrays.values()]
+    target_len = max(order + 1, *lengths)
+    out = {}
+    for name, arr in arrays.items():
+        new = np.zeros(target_len, dtype=np.float64)
+        if arr is not None:
+            new[:len(arr)] = np.asarray(arr, dtype=np.float64)
+        out[name] = new
+    out['order'] = target_len - 1
+    out['inv_factorial_order'] = _inv_factorial(target_len - 1)
+    return out
+
+
+def _rel_arrays(kwargs):
+    """knl_rel / ksl_rel default to [0] and are padded to equal length
+    (reference _common.py:548-557)."""
+    knl_rel = list(kwargs.pop('knl_rel', [0]))
+    ksl_rel = list(kwargs.pop('ksl_rel', [0]))
+    n = max(len(knl_rel), len(ksl_rel))
+    knl_rel += [0] * (n - len(knl_rel))
+    ksl_rel += [0] * (n - len(ksl_rel))
+    return (np.asarray(knl_rel, dtype=np.float64),
+            np.asarray(ksl_rel, dtype=np.float64))
+
+
+class BeamElement:
+    """Base class: class-level flags have the meaning of base_element.py:410-419."""
+    isthick = False              # *static* thickness (drives the global-aperture check)
+    allow_rot_and_shift = True
+    behaves_like_drift = False
+    has_backtrack = False
+    needs_rng = False
+    iscollective = False
+
+    def _init_misalign(self, kwargs):
+        if self.allow_rot_and_shift:
+            for nn in MISALIGN_FIELDS:
+                setattr(self, nn, float(kwargs.pop(nn, 0.0)))
+
+    def _finish(self, kwargs):
+        for kk in list(kwargs):
+            if kk in _IGNORED_KEYS:
+                kwargs.pop(kk)
+        if kwargs:
+            raise NameError(f'{type(self).__name__}: invalid argument(s) {sorted(kwargs)}')
+
+    @property
+    def has_misalignment(self):
+        """`rot_shift_active` of track_local_particle_with_transformations.h:189-196."""
+        if not self.allow_rot_and_shift:
+            return False
+        return any(getattr(self, nn) != 0.0 for nn in MISALIGN_FIELDS[:7])
+
+    @classmethod
+    def from_dict(cls, dct):
+        dct = dict(dct)
+        dct.pop('__class__', None)
+        return cls(**dct)
+
+    def get_length(self):
+        return float(getattr(self, 'length', 0.0)) if self.isthick_now else 0.0
+
+    @property
+    def isthick_now(self):
+        return bool(self.isthick)
+
+    def __repr__(self):
+        return f'{type(self).__name__}(...)'
+
+
+class Marker(BeamElement):
+    allow_rot_and_shift = False
+    behaves_like_drift = True
+    has_backtrack = True
+
+    def __init__(self, **kwargs):
+        kwargs.pop('_dummy', None)
+        self._finish(kwargs)
+
+
+class Drift(BeamElement):
+    isthick = True
+    allow_rot_and_shift = False
+    behaves_like_drift = True
+    has_backtrack = True
+
+    def __init__(self, length=0.0, model=None, **kwargs):
+        self.length = float(length)
+        self.model = _enum(model, MODEL_DRIFT, 'model')
+        self._finish(kwargs)
+
+
+class DriftExact(BeamElement):
+    isthick = True
+    allow_rot_and_shift = False
+    behaves_like_drift = True
+    has_backtrack = True
+
+    def __init__(self, length=0.0, **kwargs):
+        self.length = float(length)
+        self._finish(kwargs)
+
+
+class _Magnet(BeamElement):
+    """Common handling of knl/ksl/order/model/integrator (`_HasKnlKsl.__init__`,
+    _common.py:419-460)."""
+    has_backtrack = True
+    _model_table = MODEL_STRAIGHT
+    _default_order = DEFAULT_MULTIPOLE_ORDER
+
+    def _init_knl_ksl(self, kwargs, default_order=True):
+        order = kwargs.pop('order', None)
+        knl = kwargs.pop('knl', None)
+        ksl = kwargs.pop('ksl', None)
+        if default_order:
+            order = order or self._default_order
+        pp = _prepare_multipolar_params(order, knl=knl, ksl=ksl)
+        kwargs.pop('inv_factorial_order', None)
+        self.knl = pp['knl']
+        self.ksl = pp['ksl']
+        self.order = pp['order']
+        self.inv_factorial_order = pp['inv_factorial_order']
+        self.knl_rel, self.ksl_rel = _rel_arrays(kwargs)
+        self.model = _enum(kwargs.pop('model', None), self._model_table, 'model')
+        self.integrator = _enum(kwargs.pop('integrator', None), INTEGRATOR, 'integrator')
+
+    def _init_common_scalars(self, kwargs):
+        self.num_multipole_kicks = int(kwargs.pop('num_multipole_kicks', 0))
+        self.radiation_flag = int(kwargs.pop('radiation_flag', 0))
+        self.delta_taper = float(kwargs.pop('delta_taper', 0.0))
+
+
+class Multipole(_Magnet):
+    isthick = False          # dynamic: field `isthick`
+
+    def __init__(self, **kwargs):
+        if 'bal' in kwargs:
+            raise ValueError('`bal` not supported anymore')
+        if 'hyl' in kwargs:
+            assert _f(kwargs['hyl']) == 0.0, 'hyl is not supported anymore'
+        self._init_knl_ksl(kwargs, default_order=False)
+        self.length = float(kwargs.pop('length', 0.0))
+        self.hxl = float(kwargs.pop('hxl', 0.0))
+        self.main_order = int(kwargs.pop('main_order', 0))
+        self.main_is_skew = int(bool(kwargs.pop('main_is_skew', 0)))
+        self._isthick_field = int(bool(kwargs.pop('isthick', 0)))
+        self._init_common_scalars(kwargs)
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+    @property
+    def isthick_now(self):
+        return self._isthick_field > 0
+
+    @property
+    def main_strength(self):
+        return (self.ksl if self.main_is_skew else self.knl)[self.main_order]
+
+
+class _StraightMagnet(_Magnet):
+    isthick = True
+    _main = None     # ('k1', 'k1s') ...
+
+    def __init__(self, **kwargs):
+        self._init_knl_ksl(kwargs)
+        kn, ks = self._main
+        setattr(self, kn, float(kwargs.pop(kn, 0.0)))
+        setattr(self, ks, float(kwargs.pop(ks, 0.0)))
+        self.length = float(kwargs.pop('length', 0.0))
+        self.main_is_skew = int(bool(kwargs.pop('main_is_skew', 0)))
+        self.edge_entry_active = int(bool(kwargs.pop('edge_entry_active', 0)))
+        self.edge_exit_active = int(bool(kwargs.pop('edge_exit_active', 0)))
+        self._init_common_scalars(kwargs)
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+
+class Quadrupole(_StraightMagnet):
+    _main = ('k1', 'k1s')
+
+
+class Sextupole(_StraightMagnet):
+    _main = ('k2', 'k2s')
+
+
+class Octupole(_StraightMagnet):
+    _main = ('k3', 'k3s')
+
+
+class _BendCommon(_Magnet):
+    isthick = True
+    _model_table = MODEL_CURVED
+
+    def _init_bend_fields(self, kwargs):
+        self.k1 = float(kwargs.pop('k1', 0.0))
+        self.k2 = float(kwargs.pop('k2', 0.0))
+        self.edge_entry_active = int(bool(kwargs.pop('edge_entry_active', 1)))
+        self.edge_exit_active = int(bool(kwargs.pop('edge_exit_active', 1)))
+        for nn in ('edge_entry_angle', 'edge_exit_angle', 'edge_entry_angle_fdown',
+                   'edge_exit_angle_fdown', 'edge_entry_fint', 'edge_exit_fint',
+                   'edge_entry_hgap', 'edge_exit_hgap'):
+            setattr(self, nn, float(kwargs.pop(nn, 0.0)))
+        self._init_common_scalars(kwargs)
+        self._init_misalign(kwargs)
+        # raw defaults before properties fire
+        self._k0 = 0.0
+        self._k0_from_h = 1
+        self._h = 0.0
+        self._angle = 0.0
+        self._length = 0.0
+        self.edge_entry_model = 0
+        self.edge_exit_model = 0
+
+    # -- properties that the reference triggers in a fixed order ------------
+    @property
+    def h(self):
+        return self._h
+
+    @property
+    def angle(self):
+        return self._angle
+
+    @property
+    def length(self):
+        return self._length
+
+    @property
+    def k0(self):
+        return self._k0
+
+    @property
+    def k0_from_h(self):
+        return bool(self._k0_from_h)
+
+    def _set_k0(self, value):
+        # _common.py:660-670
+        if isinstance(value, str):
+            if value != 'from_h':
+                raise ValueError("k0 can only be set to 'from_h' as a string")
+            self._set_k0_from_h(True)
+        else:
+            self._set_k0_from_h(False)
+            self._k0 = float(value)
+
+    def _set_k0_from_h(self, value):
+        # _common.py:676-682
+        if value:
+            self._k0 = self._h
+        elif self._k0_from_h:
+            self._k0 = 0.0
+        self._k0_from_h = int(bool(value))
+
+
+class Bend(_BendCommon):
+
+    def __init__(self, **kwargs):
+        if 'h' in kwargs:
+            # backward compatibility of from_dict (_common.py:733-738)
+            if 'angle' not in kwargs:
+                kwargs['angle'] = kwargs['h'] * kwargs['length']
+            kwargs.pop('h')
+        if kwargs.get('k0_from_h', False) and 'k0' not in kwargs:
+            kwargs['k0'] = 'from_h'
+            kwargs.pop('k0_from_h')
+        props = [(nn, kwargs.pop(nn)) for nn in
+                 ('length', 'angle', 'k0_from_h', 'edge_entry_model',
+                  'edge_exit_model', 'k0') if nn in kwargs]
+        self._init_knl_ksl(kwargs)
+        self._init_bend_fields(kwargs)
+        self._finish(kwargs)
+        for nn, val in props:
+            if nn == 'length':
+                # _common.py:634-643
+                self._length = float(val)
+                self._h = self._angle / self._length if self._length != 0 else 0.0
+                if self._k0_from_h:
+                    self._k0 = self._h
+            elif nn == 'angle':
+                # _common.py:622-628
+                self._angle = float(val)
+                if self._length != 0:
+                    self._h = self._angle / self._length
+                    if self._k0_from_h:
+                        self._k0 = self._h
+            elif nn == 'k0_from_h':
+                self._set_k0_from_h(val)
+            elif nn == 'k0':
+                self._set_k0(val)
+            else:
+                setattr(self, nn, _enum(val, EDGE_MODEL, nn))
+
+
+class RBend(_BendCommon):
+
+    def __init__(self, **kwargs):
+        if 'h' in kwargs:
+            raise ValueError('Setting `h` directly is not allowed.')
+        if 'length' in kwargs:
+            assert 'length_straight' in kwargs
+            kwargs.pop('length')
+        if kwargs.get('k0_from_h', False) and 'k0' not in kwargs:
+            kwargs['k0'] = 'from_h'
+            kwargs.pop('k0_from_h')
+        props = [(nn, kwargs.pop(nn)) for nn in
+                 ('length_straight', 'angle', 'k0_from_h', 'edge_entry_model',
+                  'edge_exit_model', 'rbend_angle_diff', 'rbend_model', 'k0')
+                 if nn in kwargs]
+        self._init_knl_ksl(kwargs)
+        self._init_bend_fields(kwargs)
+        self.length_straight = 0.0
+        self.rbend_model = 0
+        self.rbend_compensate_sagitta = int(bool(kwargs.pop('rbend_compensate_sagitta', 1)))
+        self.rbend_shift = float(kwargs.pop('rbend_shift', 0.0))
+        self.rbend_angle_diff = 0.0
+        self._finish(kwargs)
+        for nn, val in props:
+            if nn == 'length_straight':
+                self.length_straight = float(val)
+                self._update_rbend_h_length_k0()
+            elif nn == 'angle':
+                self._angle = float(val)
+                self._update_rbend_h_length_k0()
+            elif nn == 'rbend_angle_diff':
+                self.rbend_angle_diff = float(val)
+                self._update_rbend_h_length_k0()
+            elif nn == 'k0_from_h':
+                self._set_k0_from_h(val)
+            elif nn == 'k0':
+                self._set_k0(val)
+            elif nn == 'rbend_model':
+                self.rbend_model = _enum(val, RBEND_MODEL, nn)
+            else:
+                setattr(self, nn, _enum(val, EDGE_MODEL, nn))
+
+    def _update_rbend_h_length_k0(self):
+        # rbend.py:192-213
+        angle = self._angle
+        ls = self.length_straight
+        diff = self.rbend_angle_diff
+        theta_in = 0.5 * angle - diff / 2
+        theta_out = 0.5 * angle + diff / 2
+        if abs(angle) < 1e-10:
+            length = ls
+            h = 0.0
+        elif abs(ls) < 1e-10:
+            length = 0.0
+            h = 0.0
+        else:
+            h = (math.sin(theta_in) + math.sin(theta_out)) / ls
+            length = angle / h
+        self._h = h
+        self._length = length
+        if self._k0_from_h:
+            self._k0 = self._h
+
+
+class Cavity(BeamElement):
+    isthick = True
+    has_backtrack = True
+
+    def __init__(self, **kwargs):
+        self.model = _enum(kwargs.pop('model', None), MODEL_RF, 'model')
+        self.integrator = _enum(kwargs.pop('integrator', None), INTEGRATOR, 'integrator')
+        for nn in ('length', 'voltage', 'frequency', 'lag', 'phase', 'harmonic',
+                   'lag_taper', 'phase_taper'):
+            setattr(self, nn, float(kwargs.pop(nn, 0.0)))
+        self.absolute_time = int(kwargs.pop('absolute_time', 0))
+        self.num_kicks = int(kwargs.pop('num_kicks', 0))
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+
+class RFMultipole(BeamElement):
+    """rf_multipole.py:51-65; constructor `_HasKnlKsl.__init__` with the phase
+    arrays (pn/ps in degrees, phase_n/phase_s in radians)."""
+    has_backtrack = True
+
+    def __init__(self, **kwargs):
+        order = kwargs.pop('order', None)
+        arrays = {nn: kwargs.pop(nn, None) for nn in
+                  ('knl', 'ksl', 'pn', 'ps', 'phase_n', 'phase_s')}
+        order = order or DEFAULT_MULTIPOLE_ORDER
+        pp = _prepare_multipolar_params(order, **arrays)
+        kwargs.pop('inv_factorial_order', None)
+        for nn in arrays:
+            setattr(self, nn, pp[nn])
+        self.order = pp['order']
+        self.inv_factorial_order = pp['inv_factorial_order']
+        for nn in ('voltage', 'frequency', 'lag', 'phase'):
+            setattr(self, nn, float(kwargs.pop(nn, 0.0)))
+        self.absolute_time = int(kwargs.pop('absolute_time', 0))
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+
+class DipoleEdge(BeamElement):
+    has_backtrack = True
+
+    def __init__(self, k=None, e1=None, e1_fd=None, hgap=None, fint=None,
+                 model=None, side=None, **kwargs):
+        if 'h' in kwargs:
+            assert k is None
+            k = kwargs.pop('h')
+        self.k = float(k or 0.0)
+        self.e1 = float(e1 or 0.0)
+        self.e1_fd = float(e1_fd or 0.0)
+        self.hgap = float(hgap or 0.0)
+        self.fint = float(fint or 0.0)
+        self.model = _enum(model, {'linear': 0, 'full': 1, 'suppressed': -1}, 'model')
+        self.side = _enum(side, {'entry': 0, 'exit': 1}, 'side')
+        self.delta_taper = float(kwargs.pop('delta_taper', 0.0))
+        kwargs.pop('r21', None)
+        kwargs.pop('r43', None)
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+        self._update_r21_r43()
+
+    def _update_r21_r43(self):
+        # dipole_edge.py:127-134 (numpy scalar math in the reference)
+        corr = np.float64(2.0) * self.k * self.hgap * self.fint
+        r21 = self.k * np.tan(self.e1)
+        e1_v = self.e1 + self.e1_fd
+        temp = corr / np.cos(e1_v) * (np.float64(1) + np.sin(e1_v) * np.sin(e1_v))
+        r43 = -self.k * np.tan(e1_v - temp)
+        self.r21 = float(r21)
+        self.r43 = float(r43)
+
+
+class SRotation(BeamElement):
+    allow_rot_and_shift = False
+    has_backtrack = True
+
+    def __init__(self, angle=None, cos_z=None, sin_z=None, **kwargs):
+        # s_rotation.py:53-82 (angle in degrees)
+        if angle is None and (cos_z is not None or sin_z is not None):
+            if cos_z is None or sin_z is None:
+                raise ValueError('At least two of (cos, sin, tan) must be given')
+            anglerad = math.atan2(sin_z, cos_z)
+        elif angle is not None:
+            anglerad = angle / 180 * np.pi
+        else:
+            anglerad = 0.0
+        self.cos_z = float(np.cos(anglerad)) if cos_z is None else float(cos_z)
+        self.sin_z = float(np.sin(anglerad)) if sin_z is None else float(sin_z)
+        self._finish(kwargs)
+
+
+class XYShift(BeamElement):
+    allow_rot_and_shift = False
+    has_backtrack = True
+
+    def __init__(self, dx=0.0, dy=0.0, **kwargs):
+        self.dx = float(dx)
+        self.dy = float(dy)
+        self._finish(kwargs)
+
+
+class LimitRect(BeamElement):
+    has_backtrack = True
+
+    def __init__(self, min_x=-UNLIMITED, max_x=UNLIMITED, min_y=-UNLIMITED,
+                 max_y=UNLIMITED, **kwargs):
+        self.min_x, self.max_x = float(min_x), float(max_x)
+        self.min_y, self.max_y = float(min_y), float(max_y)
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+
+class LimitEllipse(BeamElement):
+    has_backtrack = True
+
+    def __init__(self, a=None, b=None, a_squ=None, b_squ=None, **kwargs):
+        # limit_ellipse.py:50-70
+        if a is None and a_squ is None:
+            a = UNLIMITED
+        if b is None and b_squ is None:
+            b = UNLIMITED
+        if a is not None:
+            a_squ = a * a
+        if b is not None:
+            b_squ = b * b
+        a_b_squ = kwargs.pop('a_b_squ', a_squ * b_squ)
+        if not (a_squ > 0.0 and b_squ > 0.0):
+            raise ValueError('a_squ and b_squ have to be positive definite')
+        self.a_squ, self.b_squ, self.a_b_squ = float(a_squ), float(b_squ), float(a_b_squ)
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+
+class LimitPolygon(BeamElement):
+    has_backtrack = True
+
+    def __init__(self, x_vertices=None, y_vertices=None, **kwargs):
+        assert len(x_vertices) == len(y_vertices)
+        self.x_vertices = np.asarray(x_vertices, dtype=np.float64)
+        self.y_vertices = np.asarray(y_vertices, dtype=np.float64)
+        for nn in ('x_normal', 'y_normal', 'resc_fac', 'svg'):
+            kwargs.pop(nn, None)
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+
+class _Placeholder(Marker):
+    """Element classes outside the hot-path contract (out-of-scope
+    list).  They are loaded as markers only when `Line.from_dict` is called with
+    `replace_unsupported=True`; their count is reported by the loader."""
+
+    def __init__(self, **kwargs):
+        pass
+
+
+ELEMENT_CLASSES = {cls.__name__: cls for cls in (
+    Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupole, Octupole, Bend,
+    RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, LimitRect, LimitEllipse,
+    LimitPolygon)}

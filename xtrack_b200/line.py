@@ -1,0 +1,219 @@
+"""`Line`: element sequence + the `track()` entry point kept from xtrack.
+
+Reference API mirrored (xtrack/line.py):
+  Line.from_dict / from_json  :384-503   (plain `json`; deferred expressions ignored)
+  Line.build_tracker          :1537
+  Line.track                  :1902-1990 (signature and argument meaning)
+  config defaults             :284-293   (XTRACK_GLOBAL_XY_LIMIT=1.0, reset_s_at_end_turn=True,
+                                          XTRACK_MULTIPOLE_NO_SYNRAD=True)
+  get_length                  :3447-3457
+  configure_radiation         :4744-4837
+  freeze_longitudinal         :4446-4508
+
+Everything else of `xt.Line` (optics, matching, editing, knobs) is outside the
+hot-path scope.
+"""
+import json
+
+import numpy as np
+
+from . import elements as _el
+from .monitors import ParticlesMonitor, LastTurnsMonitor
+from .particles import Particles
+
+_MONITOR_CLASSES = {'ParticlesMonitor': ParticlesMonitor,
+                    'LastTurnsMonitor': LastTurnsMonitor}
+
+
+class Line:
+
+    def __init__(self, elements=(), element_names=None, particle_ref=None):
+        if isinstance(elements, dict):
+            self.element_dict = dict(elements)
+            if element_names is None:
+                raise ValueError('`element_names` must be provided if `elements` is a dict.')
+            self.element_names = list(element_names)
+        else:
+            if element_names is None:
+                element_names = [f'e{ii}' for ii in range(len(elements))]
+            self.element_dict = dict(zip(element_names, elements))
+            self.element_names = list(element_names)
+        self.particle_ref = particle_ref
+        self.config = {
+            'XTRACK_MULTIPOLE_NO_SYNRAD': True,
+            'XTRACK_GLOBAL_XY_LIMIT': 1.0,
+        }
+        self._extra_config = {
+            'skip_end_turn_actions': False,
+            'reset_s_at_end_turn': True,
+            '_radiation_model': None,
+            '_needs_rng': False,
+        }
+        self.track_flags = {'XS_FLAG_BACKTRACK': False,
+                            'XS_FLAG_KILL_CAVITY_KICK': False,
+                            'XS_FLAG_IGNORE_GLOBAL_APERTURE': False,
+                            'XS_FLAG_IGNORE_LOCAL_APERTURE': False,
+                            'XS_FLAG_SR_TAPER': False,
+                            'XS_FLAG_SR_KICK_SAME_AS_FIRST': False}
+        self.tracker = None
+        self.record_last_track = None
+        self.time_last_track = None
+        self.unsupported_replaced = {}
+
+    # -- construction ------------------------------------------------------
+    @classmethod
+    def from_dict(cls, dct, replace_unsupported=False):
+        """Loads the `elements` / `element_names` / `particle_ref` / `config`
+        sections of an xtrack line dictionary.  The xdeps `_var_manager`
+        section (deferred expressions) is ignored: element values are taken as
+        stored.  Classes outside the hot-path contract raise, unless
+        `replace_unsupported=True`, in which case they become markers and are
+        counted in `line.unsupported_replaced`."""
+        if dct.get('__class__', 'Line') != 'Line':
+            raise ValueError(f"Expected __class__ to be 'Line', got {dct['__class__']!r}")
+        eld = dct['elements']
+        names = dct.get('element_names', None)
+        if isinstance(eld, list):
+            assert names is not None and len(names) == len(eld)
+            eld = dict(zip(names, eld))
+        replaced = {}
+        used = set(names) if names is not None else set(eld)
+        elements = {}
+        for nn, ed in eld.items():
+            if nn not in used:
+                continue
+            cname = ed['__class__']
+            if cname in _el.ELEMENT_CLASSES:
+                elements[nn] = _el.ELEMENT_CLASSES[cname].from_dict(ed)
+            elif cname in _MONITOR_CLASSES:
+                elements[nn] = _MONITOR_CLASSES[cname].from_dict(ed)
+            elif replace_unsupported:
+                replaced[cname] = replaced.get(cname, 0) + 1
+                elements[nn] = _el.Marker()
+            else:
+                raise NotImplementedError(
+                    f'element class {cname} ({nn}) is outside the hot-path contract; '
+                    'load with replace_unsupported=True to turn it into a Marker')
+        pref = None
+        if dct.get('particle_ref') is not None:
+            pref = Particles.from_dict(dct['particle_ref'])
+        self = cls(elements=elements, element_names=names or list(elements),
+                   particle_ref=pref)
+        self.unsupported_replaced = replaced
+        if 'config' in dct:
+            for kk in ('XTRACK_MULTIPOLE_NO_SYNRAD', 'XTRACK_GLOBAL_XY_LIMIT'):
+                if kk in dct['config']:
+                    self.config[kk] = dct['config'][kk]
+        if '_extra_config' in dct:
+            for kk in ('skip_end_turn_actions', 'reset_s_at_end_turn'):
+                if kk in dct['_extra_config']:
+                    self._extra_config[kk] = dct['_extra_config'][kk]
+        return self
+
+    @classmethod
+    def from_json(cls, path, **kwargs):
+        with open(path) as fid:
+            dct = json.load(fid)
+        if 'line' in dct and 'elements' not in dct:
+            dct = dct['line']
+        return cls.from_dict(dct, **kwargs)
+
+    # -- introspection -----------------------------------------------------
+    @property
+    def elements(self):
+        return tuple(self.element_dict[nn] for nn in self.element_names)
+
+    def __len__(self):
+        return len(self.element_names)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.element_dict[key]
+        return self.element_dict[self.element_names[key]]
+
+    def get_length(self):
+        ll = 0
+        for ee in self.elements:
+            if ee.isthick_now:
+                ll += ee.length
+        return ll
+
+    @property
+    def skip_end_turn_actions(self):
+        return self._extra_config['skip_end_turn_actions']
+
+    @skip_end_turn_actions.setter
+    def skip_end_turn_actions(self, value):
+        self._extra_config['skip_end_turn_actions'] = bool(value)
+
+    @property
+    def reset_s_at_end_turn(self):
+        return self._extra_config['reset_s_at_end_turn']
+
+    @reset_s_at_end_turn.setter
+    def reset_s_at_end_turn(self, value):
+        self._extra_config['reset_s_at_end_turn'] = bool(value)
+
+    @property
+    def _needs_rng(self):
+        return self._extra_config['_needs_rng']
+
+    def get_flags_register(self):
+        """track_flags.py:5-12,42-50"""
+        bits = {'XS_FLAG_BACKTRACK': 0, 'XS_FLAG_KILL_CAVITY_KICK': 2,
+                'XS_FLAG_IGNORE_GLOBAL_APERTURE': 3, 'XS_FLAG_IGNORE_LOCAL_APERTURE': 4,
+                'XS_FLAG_SR_TAPER': 5, 'XS_FLAG_SR_KICK_SAME_AS_FIRST': 6}
+        reg = 0
+        for nn, bb in bits.items():
+            if self.track_flags.get(nn, False):
+                reg |= (1 << bb)
+        return reg
+
+    # -- configuration -----------------------------------------------------
+    def configure_radiation(self, model=None):
+        """line.py:4744-4837 (model_beamstrahlung / bhabha / spin are out of scope)."""
+        table = {None: 0, 'mean': 1, 'quantum': 2, 'quantum-kick': 3}
+        if model not in table:
+            raise ValueError(f'Invalid radiation model: {model}')
+        flag = table[model]
+        self._extra_config['_radiation_model'] = model
+        for ee in self.element_dict.values():
+            if hasattr(ee, 'radiation_flag'):
+                ee.radiation_flag = flag
+        self._extra_config['_needs_rng'] = model in ('quantum', 'quantum-kick')
+        self.config['XTRACK_MULTIPOLE_NO_SYNRAD'] = (model is None)
+        self._invalidate()
+
+    def _invalidate(self):
+        self.tracker = None
+
+    # -- tracking ----------------------------------------------------------
+    def build_tracker(self, _device=None, **kwargs):
+        """Lowers the lattice and uploads it to the GPU (replaces
+        `Tracker.__init__` + JIT compile, tracker.py:38-147)."""
+        from .tracker import Tracker
+        self.tracker = Tracker(self, device=_device, **kwargs)
+        return self.tracker
+
+    def track(self, particles, ele_start=0, ele_stop=None, num_elements=None,
+              num_turns=None, turn_by_turn_monitor=None,
+              multi_element_monitor_at=None, freeze_longitudinal=False,
+              time=False, with_progress=False, **kwargs):
+        """Same arguments as xtrack `Line.track` (line.py:1902-1914).  Particles
+        are updated in place; `line.record_last_track` holds the monitor and
+        `line.time_last_track` the device time when `time=True`."""
+        if multi_element_monitor_at is not None:
+            raise NotImplementedError('MultiElementMonitor is CPU-only in the reference '
+                                      'and outside the hot-path contract')
+        if with_progress:
+            raise NotImplementedError('with_progress batches are host conveniences '
+                                      '(tracker.py:313-381), not provided')
+        if kwargs.get('backtrack', False):
+            raise NotImplementedError('backtracking is not part of the contract')
+        if self.tracker is None or self.tracker.device != particles.device:
+            self.build_tracker(_device=particles.device)
+        return self.tracker.track(
+            particles, ele_start=ele_start, ele_stop=ele_stop,
+            num_elements=num_elements, num_turns=num_turns,
+            turn_by_turn_monitor=turn_by_turn_monitor,
+            freeze_longitudinal=freeze_longitudinal, time=time)

@@ -1,0 +1,177 @@
+"""Turn-by-turn monitors kept from xtrack's API.
+
+ParticlesMonitor  -- xtrack/monitors/particles_monitor.py:12-142,180-260 and
+                     particles_monitor.h:13-77: one full 32-field particle
+                     record per (particle, turn); record index
+                     `n_turns*(particle_id - part_id_start) + (at_turn - start_at_turn)`.
+LastTurnsMonitor  -- xtrack/monitors/last_turns_monitor.py:18-117 and
+                     last_turns_monitor.h:16-55: rolling FP32 buffer of the
+                     last N recorded turns of every particle.
+
+Record storage lives on the tracking device as torch tensors in exactly the
+reference layout (`[field][particle_row][turn_col]`, zero-initialised), so that
+`monitor.x` etc. have the reference's shapes and content.
+"""
+import numpy as np
+import torch
+
+from .elements import BeamElement
+from .particles import PER_PARTICLE_VARS, U32_VARS, _TORCH_DTYPE
+
+
+class ParticlesMonitor(BeamElement):
+    allow_rot_and_shift = False
+    behaves_like_drift = True
+    has_backtrack = True
+
+    def __init__(self, start_at_turn=None, stop_at_turn=None, n_repetitions=None,
+                 repetition_period=None, num_particles=None, particle_id_range=None,
+                 ebe_mode=0, _device='cpu', **kwargs):
+        if particle_id_range is not None:
+            assert num_particles is None
+            part_id_start, part_id_end = particle_id_range
+        else:
+            assert num_particles is not None
+            part_id_start, part_id_end = 0, num_particles
+        assert part_id_end - part_id_start >= 0
+        if repetition_period is not None:
+            assert n_repetitions is not None
+        if n_repetitions is not None:
+            assert repetition_period is not None
+        if repetition_period is None:
+            repetition_period = -1
+            n_repetitions = 1
+        self.start_at_turn = int(start_at_turn)
+        self.stop_at_turn = int(stop_at_turn)
+        self.part_id_start = int(part_id_start)
+        self.part_id_end = int(part_id_end)
+        self.ebe_mode = int(ebe_mode)
+        self.n_repetitions = int(n_repetitions)
+        self.repetition_period = int(repetition_period)
+        n_turns = self.stop_at_turn - self.start_at_turn
+        self.n_records = n_turns * (self.part_id_end - self.part_id_start) * self.n_repetitions
+        self._device = torch.device(_device)
+        self._data = None
+        self._finish(kwargs)
+
+    @classmethod
+    def from_dict(cls, dct):
+        # particles_monitor.py:113-142
+        dct = dict(dct)
+        for kk in ('__class__', 'data', 'n_records'):
+            dct.pop(kk, None)
+        dct.setdefault('start_at_turn', 0)
+        ps, pe = dct.pop('part_id_start', None), dct.pop('part_id_end', None)
+        if 'particle_id_range' not in dct and pe is not None:
+            dct['particle_id_range'] = (ps or 0, pe)
+        if dct.get('repetition_period', None) == -1:
+            dct.pop('repetition_period')
+        if 'repetition_period' not in dct and dct.get('n_repetitions', None) == 1:
+            dct.pop('n_repetitions')
+        return cls(**dct)
+
+    # -- storage -------------------------------------------------------------
+    def allocate(self, device=None):
+        if device is not None:
+            self._device = torch.device(device)
+        if self._data is None or self._data[PER_PARTICLE_VARS[0][0]].device != self._device:
+            self._data = {nn: torch.zeros(self.n_records, dtype=_TORCH_DTYPE[dt],
+                                          device=self._device)
+                          for nn, dt in PER_PARTICLE_VARS}
+        return self._data
+
+    def field_pointers(self):
+        data = self.allocate()
+        return [int(data[nn].data_ptr()) for nn, _ in PER_PARTICLE_VARS]
+
+    def _shape(self):
+        n_cols = self.stop_at_turn - self.start_at_turn
+        if self.n_repetitions == 1:
+            return (self.n_records // n_cols, n_cols)
+        return (self.n_repetitions, self.n_records // n_cols // self.n_repetitions, n_cols)
+
+    def get(self, name):
+        """Field as numpy, shaped `(n_particles, n_turns)` (or with a leading
+        frame axis), particles_monitor.py:153-171."""
+        vv = self.allocate()[name].cpu().numpy()
+        if name in U32_VARS:
+            vv = vv.view(np.uint32)
+        return vv.reshape(self._shape())
+
+    def __getattr__(self, name):
+        if name.startswith('_') and name not in U32_VARS:
+            raise AttributeError(name)
+        if name in dict(PER_PARTICLE_VARS):
+            return self.get(name)
+        if name == 'pzeta':
+            return self.get('ptau') / self.get('beta0')
+        raise AttributeError(name)
+
+
+class LastTurnsMonitor(BeamElement):
+    allow_rot_and_shift = False
+    behaves_like_drift = True
+
+    properties = ('particle_id', 'at_turn', 'x', 'px', 'y', 'py', 'delta', 'zeta')
+
+    def __init__(self, *, n_last_turns=None, num_particles=None, particle_id_range=None,
+                 every_n_turns=1, _device='cpu', **kwargs):
+        if num_particles is not None and particle_id_range is None:
+            particle_id_start = 0
+        elif particle_id_range is not None and num_particles is None:
+            particle_id_start = particle_id_range[0]
+            num_particles = particle_id_range[1] - particle_id_range[0]
+        else:
+            raise ValueError('Exactly one of `num_particles` or `particle_id_range` '
+                             'parameters must be specified')
+        self.particle_id_start = int(particle_id_start)
+        self.num_particles = int(num_particles)
+        self.n_last_turns = int(n_last_turns)
+        self.every_n_turns = int(every_n_turns)
+        self._device = torch.device(_device)
+        self._data = None
+        self._finish(kwargs)
+
+    @classmethod
+    def from_dict(cls, dct):
+        dct = dict(dct)
+        for kk in ('__class__', 'data'):
+            dct.pop(kk, None)
+        ps = dct.pop('particle_id_start', None)
+        if ps is not None:
+            dct['particle_id_range'] = (ps, ps + dct.pop('num_particles'))
+        return cls(**dct)
+
+    def allocate(self, device=None):
+        if device is not None:
+            self._device = torch.device(device)
+        if self._data is None or self._data['x'].device != self._device:
+            size = self.num_particles * self.n_last_turns
+            dd = {'lost_at_offset': torch.zeros(self.num_particles, dtype=torch.int32,
+                                                device=self._device)}
+            for nn in ('particle_id', 'at_turn'):
+                dd[nn] = torch.zeros(size, dtype=torch.int32, device=self._device)
+            for nn in ('x', 'px', 'y', 'py', 'delta', 'zeta'):
+                dd[nn] = torch.zeros(size, dtype=torch.float32, device=self._device)
+            self._data = dd
+        return self._data
+
+    def field_pointers(self):
+        dd = self.allocate()
+        return [int(dd[nn].data_ptr()) for nn in
+                ('lost_at_offset', 'particle_id', 'at_turn', 'x', 'px', 'y', 'py',
+                 'delta', 'zeta')]
+
+    def __getattr__(self, attr):
+        if attr in LastTurnsMonitor.properties:
+            # un-roll the ring buffer (last_turns_monitor.py:108-117)
+            dd = self.allocate()
+            val = dd[attr].cpu().numpy()
+            if attr in ('particle_id', 'at_turn'):
+                val = val.view(np.uint32)
+            val = np.reshape(val, (self.num_particles, self.n_last_turns))
+            off = dd['lost_at_offset'].cpu().numpy().view(np.uint32).astype(np.int64) + 1
+            r, c = np.ogrid[:val.shape[0], :val.shape[1]]
+            c = (c + off[:, np.newaxis]) % val.shape[1]
+            return val[r, c]
+        raise AttributeError(attr)
