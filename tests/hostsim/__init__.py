@@ -1,0 +1,87 @@
+"""TEST INFRASTRUCTURE ONLY: host (g++) build of the device physics headers, used by
+the CPU test tier to check the lattice lowering and op semantics against the
+reference oracle where no GPU exists.  Nothing under xtrack_b200/ imports this."""
+import ctypes as ct
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+import xtrack_b200 as xb
+from xtrack_b200 import _cabi
+from xtrack_b200.tracker import Tracker
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
+LIB = os.path.join(HERE, '_build', 'libxtb_hostsim.so')
+_lib = None
+
+
+def _sources():
+    csrc = os.path.join(ROOT, 'xtrack_b200', 'csrc')
+    return [os.path.join(HERE, 'xtb_hostsim.cpp')] + [
+        os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(('.cuh', '.h'))]
+
+
+def load():
+    global _lib
+    if _lib is None:
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        if (not os.path.exists(LIB)
+                or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in _sources())):
+            subprocess.run(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared',
+                            os.path.join(HERE, 'xtb_hostsim.cpp'), '-o', LIB, '-lm'], check=True)
+        _lib = ct.CDLL(LIB)
+        _lib.xtb_hostsim_track.restype = None
+        _lib.xtb_hostsim_track.argtypes = [
+            ct.c_void_p, ct.c_void_p, ct.POINTER(_cabi.XtbParticles), ct.c_int64, ct.c_int32,
+            ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.POINTER(_cabi.XtbMonitor),
+            ct.c_uint64, ct.c_double, ct.c_uint32, ct.c_double, ct.c_void_p, ct.c_void_p]
+    return _lib
+
+
+class HostSimLattice:
+    def __init__(self, words, elem_offset, line_length):
+        self.words = np.ascontiguousarray(words, dtype=np.uint64)
+        self.elem_offset = np.ascontiguousarray(elem_offset, dtype=np.uint32)
+        self.line_length = float(line_length)
+        self._mons = None
+        self._ltms = None
+
+    def set_inline_monitors(self, monitors, last_turns):
+        self._mons = (_cabi.XtbMonitor * max(1, len(monitors)))(
+            *[_cabi.monitor_struct(m) for m in monitors])
+        self._ltms = (_cabi.XtbLastTurnsMonitor * max(1, len(last_turns)))(
+            *[_cabi.last_turns_struct(m) for m in last_turns])
+
+    def track(self, particles, *, num_turns, ele_start, num_ele_track, flag_end_turn_actions,
+              flag_reset_s_at_end_turn, flag_monitor=0, monitor=None, track_flags=0,
+              global_xy_limit=1.0, variant_flags=0, stream=None):
+        pst = _cabi.particles_struct(particles)
+        mst = ct.byref(_cabi.monitor_struct(monitor)) if monitor is not None else None
+        load().xtb_hostsim_track(
+            self.words.ctypes.data, self.elem_offset.ctypes.data, ct.byref(pst), int(num_turns),
+            int(ele_start), int(num_ele_track), int(bool(flag_end_turn_actions)),
+            int(bool(flag_reset_s_at_end_turn)), int(flag_monitor), mst, int(track_flags),
+            float(global_xy_limit), int(variant_flags), self.line_length,
+            ct.cast(self._mons, ct.c_void_p) if self._mons is not None else None,
+            ct.cast(self._ltms, ct.c_void_p) if self._ltms is not None else None)
+
+    def close(self):
+        pass
+
+
+class HostSimTracker(Tracker):
+    """`Tracker` whose launches go to the host build of the device code."""
+
+    def __init__(self, line, device=None, **kwargs):
+        super().__init__(line, device='cpu', **kwargs)
+
+    def _make_lattice(self, words, elem_offset):
+        return HostSimLattice(words, elem_offset, self.line_length)
+
+
+def build_hostsim_tracker(line):
+    line.tracker = HostSimTracker(line)
+    return line.tracker

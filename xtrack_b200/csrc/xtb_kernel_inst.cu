@@ -1,0 +1,35 @@
+// xtb_kernel_inst.cu -- instantiates the tracking kernel variants.
+//
+// Compiled twice by xtrack_b200/build.py:
+//   -DXTB_EXACT=0 -fmad=true   -> xtb_launch_track_fast   (default, FMA contraction)
+//   -DXTB_EXACT=1 -fmad=false  -> xtb_launch_track_exact  (reference rounding order;
+//                                 the reference CPU build has no FMA contraction)
+#include "xtb_kernel.cuh"
+
+#if XTB_EXACT
+#define XTB_LAUNCH_NAME xtb_launch_track_exact
+#else
+#define XTB_LAUNCH_NAME xtb_launch_track_fast
+#endif
+
+template <bool HEAVY, bool SYNRAD, bool FRZ>
+static cudaError_t launch(const XtbTrackArgs& a, unsigned grid, cudaStream_t stream) {
+    xtb_track_kernel<HEAVY, SYNRAD, FRZ><<<grid, XTB_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// variant bits: 1 = heavy ops present, 2 = synrad, 4 = freeze longitudinal
+extern "C" cudaError_t XTB_LAUNCH_NAME(unsigned variant, const XtbTrackArgs* a, unsigned grid,
+                                       cudaStream_t stream) {
+    switch (variant & 7u) {
+    case 0: return launch<false, false, false>(*a, grid, stream);
+    case 4: return launch<false, false, true>(*a, grid, stream);
+#ifdef XTB_WITH_HEAVY
+    case 1: return launch<true, false, false>(*a, grid, stream);
+    case 5: return launch<true, false, true>(*a, grid, stream);
+    case 2: case 3: return launch<true, true, false>(*a, grid, stream);
+    case 6: case 7: return launch<true, true, true>(*a, grid, stream);
+#endif
+    default: return cudaErrorNotSupported;
+    }
+}

@@ -1,0 +1,308 @@
+// xtb_thin.cuh -- single-particle maps of the thin element set, on registers.
+//
+// Every function restates the arithmetic of the cited reference routine in the
+// reference's operation order, so that the EXACT build (-fmad=false) rounds
+// like the reference's CPU build; the default build lets nvcc contract to FMA.
+// Element-constant work (coefficient scaling, factorials, trigonometry of
+// element parameters) is done once by the host lowering (xtrack_b200/lowering.py)
+// with the same IEEE operations, so only per-particle arithmetic remains here.
+#pragma once
+#include "xtb_state.cuh"
+
+#define XTB_C_LIGHT 299792458.0
+#define XTB_PI 3.1415926535897932384626433832795028841971693993751
+#define XTB_DEG2RAD 0.0174532925199432957692369076848861271344287188854
+
+// FRZ = freeze_longitudinal: writes to zeta, s, delta, ptau, rpp, rvv are
+// suppressed (FREEZE_VAR_*, xtrack/particles/particles.py:193-227, line.py:4446-4508).
+
+// xtrack/beam_elements/elements_src/track_drift.h:11-22
+template <bool FRZ>
+__device__ __forceinline__ void drift_expanded(PState& P, const double length) {
+    const double xp = P.px * P.rpp;
+    const double yp = P.py * P.rpp;
+    const double dzeta = 1 - P.rv0v * (1. + (xp * xp + yp * yp) / 2.);
+    P.x += xp * length;
+    P.y += yp * length;
+    if (!FRZ) {
+        P.s += length;
+        P.zeta += length * dzeta;
+    }
+}
+
+// track_drift.h:26-40
+template <bool FRZ>
+__device__ __forceinline__ void drift_exact(PState& P, const double length) {
+    const double one_plus_delta = 1. + P.delta;
+    const double one_over_pz =
+        1. / sqrt(one_plus_delta * one_plus_delta - P.px * P.px - P.py * P.py);
+    const double dzeta = 1 - P.rv0v * one_plus_delta * one_over_pz;
+    P.x += P.px * one_over_pz * length;
+    P.y += P.py * one_over_pz * length;
+    if (!FRZ) {
+        P.zeta += dzeta * length;
+        P.s += length;
+    }
+}
+
+// Horner evaluation of kick_simple_single_coordinates, track_magnet_kick.h:183-228.
+// c[] holds the host-scaled coefficients (knl[i]*factor*inv_factorial_i, same
+// product order as the reference) as pairs (normal, skew) from the highest
+// order down; chi multiplies each coefficient as in the reference.
+__device__ __forceinline__ void horner_kick(const double x, const double y, const double chi,
+                                            const double* __restrict__ c, const int order,
+                                            double& dpx_mul, double& dpy_mul) {
+    dpx_mul = chi * c[0];
+    dpy_mul = chi * c[1];
+    for (int i = 1; i <= order; ++i) {
+        const double zre = dpx_mul * x - dpy_mul * y;
+        const double zim = dpx_mul * y + dpy_mul * x;
+        dpx_mul = chi * c[2 * i] + zre;
+        dpy_mul = chi * c[2 * i + 1] + zim;
+    }
+}
+
+// Thin multipole without curvature: Multipole (model -1) of multipole.h:16-75
+// -> track_magnet_kick_single_particle, track_magnet_kick.h:24-144, with
+// hxl == 0 and all-zero knl_rel / main strengths (their kicks are exact zeros).
+__device__ __forceinline__ void mult_kick(PState& P, const double* __restrict__ c, const int order) {
+    double dpx_mul, dpy_mul;
+    horner_kick(P.x, P.y, P.chi, c, order, dpx_mul, dpy_mul);
+    P.px += -dpx_mul;
+    P.py += dpy_mul;
+}
+
+// Thin multipole with hxl != 0: adds the curvature terms of
+// track_magnet_kick.h:98-142.  q = [hl, B0, B1, 0], c = coefficients.
+//   hl = h*length*kw + hxl*kw ; B0 = -(k0_h_corr*length + k0l)*kw*htot ;
+//   B1 = htot*(k1_h_corr*length + k1l)*kw          (host, reference order, chi = 1)
+template <bool FRZ>
+__device__ __forceinline__ void mult_kick_h(PState& P, const double* __restrict__ q,
+                                            const double* __restrict__ c, const int order,
+                                            const bool has_b1) {
+    const double x = P.x, y = P.y, chi = P.chi;
+    double dpx_mul, dpy_mul;
+    horner_kick(x, y, chi, c, order, dpx_mul, dpy_mul);
+    P.px += -dpx_mul;
+    P.py += dpy_mul;
+
+    const double hl = q[0];
+    double dpx = hl * (1. + P.delta);
+    const double dzeta = -P.rv0v * hl * x;
+    dpx += chi * q[1] * x;
+    if (has_b1) {
+        const double b1 = chi * q[2];
+        dpx += b1 * (-x * x + 0.5 * y * y);
+        P.px += dpx;
+        P.py += b1 * x * y;
+    } else {
+        P.px += dpx;
+    }
+    if (!FRZ) P.zeta += dzeta;
+}
+
+// LocalParticle_update_ptau, local_particle_custom_api.h:21-32
+template <bool FRZ>
+__device__ __forceinline__ void update_ptau(PState& P, const PSlot& G, const double beta0,
+                                            const double ptau) {
+    if (FRZ) return;
+    const double irpp = sqrt(ptau * ptau + 2 * ptau / beta0 + 1);
+    const double new_rpp = 1. / irpp;
+    const double new_rvv = irpp / (1 + beta0 * ptau);
+    P.delta = irpp - 1;
+    P.rvv = new_rvv;
+    P.rv0v = 1. / new_rvv;
+    P.rpp = new_rpp;
+    G.st(F_PTAU, ptau);
+}
+
+// LocalParticle_update_delta, local_particle_custom_api.h:36-50
+template <bool FRZ>
+__device__ __forceinline__ void update_delta(PState& P, const PSlot& G, const double beta0,
+                                             const double new_delta) {
+    if (FRZ) return;
+    const double delta_beta0 = new_delta * beta0;
+    const double ptau_beta0 = sqrt(delta_beta0 * delta_beta0 + 2 * delta_beta0 * beta0 + 1) - 1;
+    const double one_plus_delta = 1 + new_delta;
+    const double rvv = one_plus_delta / (1 + ptau_beta0);
+    const double rpp = 1 / one_plus_delta;
+    const double ptau = ptau_beta0 / beta0;
+    P.delta = new_delta;
+    P.rvv = rvv;
+    P.rv0v = 1. / rvv;
+    P.rpp = rpp;
+    G.st(F_PTAU, ptau);
+}
+
+// LocalParticle_add_to_energy, local_particle_custom_api.h:196-216
+template <bool FRZ>
+__device__ __forceinline__ void add_to_energy(PState& P, const PSlot& G, const double beta0,
+                                              const double delta_energy, const int pz_only) {
+    double ptau = G.ld(F_PTAU);
+    const double p0c = G.ld(F_P0C);
+    const double charge_ratio = G.ld(F_CHARGE_RATIO);
+    const double mass_ratio = charge_ratio / P.chi;
+    ptau += delta_energy / p0c / mass_ratio;
+    const double old_rpp = P.rpp;
+    update_ptau<FRZ>(P, G, beta0, ptau);
+    if (!pz_only) {
+        const double f = old_rpp / P.rpp;
+        P.px *= f;
+        P.py *= f;
+    }
+}
+
+// LocalParticle_kill_particle, local_particle_custom_api.h:248-256
+template <bool FRZ>
+__device__ __forceinline__ void kill_particle(PState& P, const PSlot& G, const int kill_state) {
+    P.x = 1e30;  P.px = 1e30;  P.y = 1e30;  P.py = 1e30;
+    if (!FRZ) P.zeta = 1e30;
+    update_delta<FRZ>(P, G, G.ld(F_BETA0), -1.);
+    P.state = kill_state;
+}
+
+// Thin cavity kick: track_rf_kick_single_particle, track_rf.h:18-167 with
+// order = -1 and no transverse voltage.  q = [V, f, harmonic, lag, phase].
+template <bool FRZ>
+__device__ __forceinline__ void cavity_kick(PState& P, const PSlot& G, const XtbTrackArgs& a,
+                                            const double voltage, double frequency,
+                                            const double harmonic, const double lag,
+                                            const double phase, const int absolute_time) {
+    double phase0 = 0;
+    const double beta0 = G.ld(F_BETA0);
+    if (harmonic != 0) {
+        const double t_rev0 = a.line_length / (beta0 * XTB_C_LIGHT);
+        frequency += (harmonic / t_rev0);
+    }
+    if (absolute_time == 1) {
+        phase0 += 2 * XTB_PI * P.at_turn * frequency * a.part.t_sim;
+    }
+    const double q = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
+    const double tau = P.zeta / beta0;
+    const double energy_kick = q * voltage
+        * sin(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
+    if (!a.kill_cavity_kick) {
+        add_to_energy<FRZ>(P, G, beta0, energy_kick + 0., 1);
+    }
+}
+
+// RF multipole kick: track_rf.h:18-167 with order >= 0 (RFMultipole, rfmultipole.h).
+// q = [V, f, lag, phase, 0], then (knl, ksl, pn, ps, phase_n, phase_s) per order;
+// factor_knl_ksl is folded into knl/ksl by the host.
+template <bool FRZ>
+__device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const XtbTrackArgs& a,
+                                            const double* __restrict__ q, const int order) {
+    const double voltage = q[0], frequency = q[1], lag = q[2], phase = q[3];
+    const double* __restrict__ t = q + 5;
+    const double phase0 = 0;
+    const double beta0 = G.ld(F_BETA0);
+    const double qq = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
+    const double tau = P.zeta / beta0;
+    const double energy_kick = qq * voltage
+        * sin(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
+
+    double dpx = 0.0, dpy = 0.0, dptr = 0.0, zre = 1.0, zim = 0.0, factorial = 1.0;
+    const double x = P.x, y = P.y;
+    const double p0c = G.ld(F_P0C);
+    for (int kk = 0; kk <= order; kk++) {
+        if (kk > 0) factorial *= kk;
+        const double* __restrict__ e = t + 6 * kk;
+        const double pn_kk = phase0 + XTB_DEG2RAD * e[2] + e[4] - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau;
+        const double ps_kk = phase0 + XTB_DEG2RAD * e[3] + e[5] - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau;
+        const double bal_n_kk = e[0] / factorial;
+        const double bal_s_kk = e[1] / factorial;
+        const double cn = cos(pn_kk), cs = cos(ps_kk), sn = sin(pn_kk), ss = sin(ps_kk);
+        dpx += cn * (bal_n_kk * zre) - cs * (bal_s_kk * zim);
+        dpy += cs * (bal_s_kk * zre) + cn * (bal_n_kk * zim);
+        const double zret = zre * x - zim * y;
+        zim = zim * x + zre * y;
+        zre = zret;
+        dptr += sn * (bal_n_kk * zre) - ss * (bal_s_kk * zim);
+    }
+    const double rf_energy_kick = -qq * ((frequency * (2.0 * XTB_PI / XTB_C_LIGHT) * p0c) * dptr);
+    P.px += -P.chi * dpx;
+    P.py += P.chi * dpy;
+    if (!a.kill_cavity_kick) {
+        add_to_energy<FRZ>(P, G, beta0, energy_kick + rf_energy_kick, 1);
+    }
+}
+
+// DipoleEdgeLinear_single_particle, track_dipole_edge_linear.h:30-39
+__device__ __forceinline__ void edge_linear(PState& P, const double r21, const double r43) {
+    P.px += P.chi * r21 * P.x;
+    P.py += P.chi * r43 * P.y;
+}
+
+// SRotation_single_particle, track_srotation.h:12-40 (spin left untouched: spin
+// tracking is outside the contract and the reference skips it for zero spin)
+__device__ __forceinline__ void srotation(PState& P, const double sin_z, const double cos_z) {
+    const double x = P.x, y = P.y, px = P.px, py = P.py;
+    P.x = cos_z * x + sin_z * y;
+    P.y = -sin_z * x + cos_z * y;
+    P.px = cos_z * px + sin_z * py;
+    P.py = -sin_z * px + cos_z * py;
+}
+
+// YRotation_single_particle, track_yrotation.h:12-45
+template <bool FRZ>
+__device__ __forceinline__ void yrotation(PState& P, const PSlot& G, const double sin_angle,
+                                          const double cos_angle, const double tan_angle) {
+    const double beta0 = G.ld(F_BETA0);
+    const double x = P.x, y = P.y, px = P.px, py = P.py;
+    const double t = P.zeta / beta0;
+    const double pt = (G.ld(F_PTAU) / beta0) * beta0;
+    const double pz = sqrt(1.0 + 2.0 * pt / beta0 + pt * pt - px * px - py * py);
+    const double ptt = 1.0 + tan_angle * px / pz;
+    const double x_hat = x / (cos_angle * ptt);
+    const double px_hat = cos_angle * px - sin_angle * pz;
+    const double y_hat = y - tan_angle * x * py / (pz * ptt);
+    const double t_hat = t + tan_angle * x * (1.0 / beta0 + pt) / (pz * ptt);
+    P.x = x_hat;
+    P.px = px_hat;
+    P.y = y_hat;
+    if (!FRZ) P.zeta = t_hat * beta0;
+}
+
+// XRotation_single_particle, track_xrotation.h:12-45
+template <bool FRZ>
+__device__ __forceinline__ void xrotation(PState& P, const PSlot& G, const double sin_angle,
+                                          const double cos_angle, const double tan_angle) {
+    const double beta0 = G.ld(F_BETA0);
+    const double x = P.x, y = P.y, px = P.px, py = P.py;
+    const double t = P.zeta / beta0;
+    const double pt = (G.ld(F_PTAU) / beta0) * beta0;
+    const double pz = sqrt(1.0 + 2.0 * pt / beta0 + pt * pt - px * px - py * py);
+    const double ptt = 1.0 - tan_angle * py / pz;
+    const double y_hat = y / (cos_angle * ptt);
+    const double py_hat = cos_angle * py + sin_angle * pz;
+    const double x_hat = x + tan_angle * y * px / (pz * ptt);
+    const double t_hat = t - tan_angle * y * (1.0 / beta0 + pt) / (pz * ptt);
+    P.x = x_hat;
+    P.py = py_hat;
+    P.y = y_hat;
+    if (!FRZ) P.zeta = t_hat * beta0;
+}
+
+// LimitPolygon_track_local_particle, limitpolygon.h:63-88 (the CPU-only
+// inscribed-circle shortcut :28-61 does not change the result)
+__device__ __forceinline__ bool polygon_contains(const double x, const double y,
+                                                 const double* __restrict__ vx,
+                                                 const double* __restrict__ vy, const int n) {
+    int is_alive = 0;
+    int jj = n - 1;
+    for (int ii = 0; ii < n; ++ii) {
+        const double Vx_ii = vx[ii], Vx_jj = vx[jj], Vy_ii = vy[ii], Vy_jj = vy[jj];
+        if (((Vy_ii > y) != (Vy_jj > y))
+            && (x < (Vx_jj - Vx_ii) * (y - Vy_ii) / (Vy_jj - Vy_ii) + Vx_ii)) {
+            is_alive = !is_alive;
+        }
+        jj = ii;
+    }
+    return is_alive != 0;
+}
+
+// global_aperture_check, local_particle_custom_api.h:262-289
+__device__ __forceinline__ void global_aperture_check(PState& P, const double lim) {
+    const bool inside = (P.x >= -lim) && (P.x <= lim) && (P.y >= -lim) && (P.y <= lim);
+    if (P.state > 0 && !inside) P.state = -1;
+}

@@ -192,7 +192,8 @@ class Line:
         """Lowers the lattice and uploads it to the GPU (replaces
         `Tracker.__init__` + JIT compile, tracker.py:38-147)."""
         from .tracker import Tracker
-        self.tracker = Tracker(self, device=_device, **kwargs)
+        tracker_class = kwargs.pop('_tracker_class', Tracker)
+        self.tracker = tracker_class(self, device=_device, **kwargs)
         return self.tracker
 
     def track(self, particles, ele_start=0, ele_stop=None, num_elements=None,
@@ -216,4 +217,5 @@ class Line:
             particles, ele_start=ele_start, ele_stop=ele_stop,
             num_elements=num_elements, num_turns=num_turns,
             turn_by_turn_monitor=turn_by_turn_monitor,
-            freeze_longitudinal=freeze_longitudinal, time=time)
+            freeze_longitudinal=freeze_longitudinal, time=time,
+            _force_no_end_turn_actions=kwargs.get('_force_no_end_turn_actions', False))

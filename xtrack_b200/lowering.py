@@ -1,0 +1,958 @@
+"""Lattice lowering: xtrack elements -> the op stream ("program") that the CUDA
+tracking kernel interprets (format: csrc/xtb_ops.h).
+
+This replaces, on the host and once per `build_tracker`, everything the
+reference re-derives per element call inside its kernel from element-constant
+data: parent/slice weights, default model/integrator selection, automatic
+kick counts, `configure_tracking_model`, coefficient scaling with factorials,
+edge coefficients, rbend geometry and the misalignment frame algebra.  All of
+it is evaluated with plain IEEE doubles in the reference's operation order
+(Python floats and `math` = the same libm the CPU reference links), so the
+parameters the GPU receives are bit-identical to what the reference computes.
+
+Reference routines restated here (xtrack/beam_elements/elements_src/):
+  track_magnet.h:289-648            track_magnet_particles   -> `_lower_magnet`
+  track_magnet_configure.h:7-194    configure_tracking_model -> `_configure_tracking_model`
+  track_magnet_kick.h:149-228       kick_is_inactive / Horner scaling -> `_horner_coeffs`
+  track_magnet_edge.h:17-167        edge model selection     -> `_lower_edge`
+  track_dipole_edge_linear.h:12-27  linear edge coefficients
+  track_rf.h:317-453                track_rf_particles       -> `_lower_rf`
+  track_misalignments.h:38-357      misalignment algebra     -> `_misalign_*`
+  headers/track_local_particle_with_transformations.h:99-204 wrapper -> `_with_transformations`
+  drift.h, multipole.h, quadrupole.h, sextupole.h, octupole.h, bend.h, rbend.h,
+  cavity.h, rfmultipole.h, dipoleedge.h, srotation.h, xyshift.h, limit*.h (wrappers)
+"""
+import math
+
+import numpy as np
+
+# ---- opcodes / flags: mirror of csrc/xtb_ops.h ----------------------------
+F_START, F_END, F_GLOBAL = 0x01, 0x02, 0x04
+
+OP_NOP = 0
+OP_DRIFT = 1
+OP_DRIFT_EXACT = 2
+OP_MULT = 3
+OP_MULT_H = 4
+OP_CAVITY = 5
+OP_RFMULT = 6
+OP_EDGE_LIN = 7
+OP_SROT = 8
+OP_XYSHIFT = 9
+OP_SSHIFT = 10
+OP_YROT = 11
+OP_XROT = 12
+OP_LIMIT_RECT = 13
+OP_LIMIT_ELLIPSE = 14
+OP_LIMIT_POLYGON = 15
+OP_MONITOR = 16
+OP_LAST_TURNS = 17
+OP_KILL = 18
+OP_SET_STATE = 19
+OP_ADD_S_ZETA = 20
+OP_ADD_X = 21
+OP_MAGNET_BODY = 32
+OP_MAGNET_EDGE = 33
+OP_DIPEDGE_NL = 34
+
+TILE_WORDS = 1024
+
+ONE_OVER_FACT = [1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664,
+                 0.008333333333333333, 0.001388888888888889, 0.0001984126984126984,
+                 2.48015873015873e-05, 2.7557319223985893e-06, 2.755731922398589e-07,
+                 2.505210838544172e-08, 2.08767569878681e-09, 1.6059043836821613e-10,
+                 1.1470745597729725e-11, 7.647163731819816e-13, 4.779477332387385e-14,
+                 2.8114572543455206e-15, 1.5619206968586225e-16, 8.22063524662433e-18]
+
+
+def one_over_factorial(n):
+    """headers/factorial.h:5-37"""
+    if n < 0:
+        return 0.
+    if n < 20:
+        return ONE_OVER_FACT[n]
+    return 1. / math.gamma(float(n + 1))
+
+
+# Algorithmic flop table per op (SURVEY.md §8d convention: add/mul = 1, FMA = 2,
+# div = 1, sqrt = 1, libm call = 1; work on all-zero coefficient sets is not
+# credited).  Single source for bench.py's roofline.achieved.
+def flops_drift():
+    return 17
+
+
+def flops_mult(order):
+    return 8 * order + 4
+
+
+FLOPS = {
+    OP_NOP: 0, OP_DRIFT: 17, OP_DRIFT_EXACT: 21, OP_CAVITY: 25, OP_EDGE_LIN: 6,
+    OP_SROT: 12, OP_XYSHIFT: 2, OP_SSHIFT: 23, OP_YROT: 30, OP_XROT: 30,
+    OP_LIMIT_RECT: 0, OP_LIMIT_ELLIPSE: 5, OP_MONITOR: 0, OP_LAST_TURNS: 0,
+    OP_KILL: 0, OP_SET_STATE: 0, OP_ADD_S_ZETA: 2, OP_ADD_X: 1,
+}
+
+
+class Program:
+    """Accumulates ops; `finish()` returns the uint64 word array + element offsets."""
+
+    def __init__(self):
+        self.words = []
+        self.elem_offset = [0]
+        self._cur = []          # ops of the element being lowered: [op, flags, aux, params]
+        self.flops = 0.0        # algorithmic flop per particle-turn (sum over elements)
+        self.n_transc = 0.0
+        self.op_hist = {}
+        self.has_heavy = False
+        self.monitors = []      # in-line ParticlesMonitor objects (index = aux)
+        self.last_turns_monitors = []
+
+    def op(self, opcode, params=(), aux=0, flops=None, transc=0):
+        self._cur.append([int(opcode), 0, int(aux), [float(p) if not isinstance(p, _RawWord)
+                                                      else p for p in params]])
+        if flops is None:
+            flops = FLOPS.get(opcode, 0)
+        self.flops += flops
+        self.n_transc += transc
+        self.op_hist[opcode] = self.op_hist.get(opcode, 0) + 1
+        if opcode >= 32:
+            self.has_heavy = True
+
+    def end_element(self, static_thick):
+        if not self._cur:
+            self._cur.append([OP_NOP, 0, 0, []])
+            self.op_hist[OP_NOP] = self.op_hist.get(OP_NOP, 0) + 1
+        self._cur[0][1] |= F_START
+        self._cur[-1][1] |= F_END | (F_GLOBAL if static_thick else 0)
+        n_el_words = 0
+        for opcode, flags, aux, params in self._cur:
+            nw = 1 + len(params)
+            if nw & 1:
+                params = params + [0.0]
+                nw += 1
+            if nw > 0xffff:
+                raise ValueError('op too long')
+            hdr = opcode | (flags << 8) | (nw << 16) | ((aux & 0xffffffff) << 32)
+            self.words.append(np.uint64(hdr))
+            for pp in params:
+                if isinstance(pp, _RawWord):
+                    self.words.append(np.uint64(pp.value))
+                else:
+                    self.words.append(np.float64(pp).view(np.uint64))
+            n_el_words += nw
+        if n_el_words > TILE_WORDS:
+            raise ValueError(f'element lowers to {n_el_words} words > tile of {TILE_WORDS}')
+        self._cur = []
+        self.elem_offset.append(len(self.words))
+
+    def finish(self):
+        words = np.array(self.words, dtype=np.uint64)
+        return words, np.array(self.elem_offset, dtype=np.uint32)
+
+
+class _RawWord:
+    """A parameter word that is an integer bit pattern, not a double."""
+
+    def __init__(self, value):
+        self.value = int(value) & 0xffffffffffffffff
+
+
+# ---------------------------------------------------------------------------
+# helpers restating element-constant arithmetic of the reference
+# ---------------------------------------------------------------------------
+def _horner_coeffs(knl, ksl, order, inv_factorial_order, factor):
+    """Scaled coefficients in Horner order (highest first), as pairs.
+    track_magnet_kick.h:183-228: `chi * knl[index] * factor * inv_factorial`
+    with `inv_factorial *= index` going down (chi is applied on the device).
+    Leading all-zero orders are dropped (their contribution is an exact zero)."""
+    if order < 0 or knl is None or ksl is None:
+        return []
+    inv_factorial = float(inv_factorial_order)
+    index = int(order)
+    cn = [0.0] * (order + 1)
+    cs = [0.0] * (order + 1)
+    cn[index] = float(knl[index]) * factor * inv_factorial
+    cs[index] = float(ksl[index]) * factor * inv_factorial
+    while index > 0:
+        inv_factorial *= index
+        index -= 1
+        cn[index] = (float(knl[index]) * factor) * inv_factorial
+        cs[index] = (float(ksl[index]) * factor) * inv_factorial
+    top = order
+    while top > 0 and cn[top] == 0.0 and cs[top] == 0.0:
+        top -= 1
+    out = []
+    for ii in range(top, -1, -1):
+        out += [cn[ii], cs[ii]]
+    return out
+
+
+def _all_zero(c):
+    return all(v == 0.0 for v in c)
+
+
+def _kick_is_inactive(order, knl, ksl, k0, k1, k2, k3, k0s, k1s, k2s, k3s, h):
+    """track_magnet_kick.h:149-180"""
+    for v in (h, k0, k1, k2, k3, k0s, k1s, k2s, k3s):
+        if v != 0:
+            return False
+    for index in range(order, -1, -1):
+        if knl[index] != 0 or ksl[index] != 0:
+            return False
+    return True
+
+
+def _configure_tracking_model(model, k0, k1, h, ks):
+    """track_magnet_configure.h:7-194 -> dict"""
+    if model == 1:
+        model = 3
+    h_is_zero = abs(h) < 1e-8
+    if model == 2:
+        drift_model = 5 if h_is_zero else 4
+    elif model == 3:
+        drift_model = 1 if h_is_zero else 7
+    elif model == 4:
+        drift_model = 3
+    elif model == 5:
+        drift_model = 1
+    elif model == 6:
+        drift_model = 0
+    elif model == -1:
+        drift_model = -1
+    elif model == -2:
+        drift_model = 6
+    elif model == 7:
+        drift_model = 1 if h_is_zero else 2
+    elif model == 8:
+        drift_model = 1 if h_is_zero else 8
+    else:
+        drift_model = 99999999
+    c = dict(k0_drift=0.0, k1_drift=0.0, h_drift=0.0, ks_drift=0.0, k0_kick=0.0,
+             k1_kick=0.0, h_kick=0.0, k0_h_correction=0.0, k1_h_correction=0.0,
+             kick_rot_frame=0, drift_model=drift_model)
+    if drift_model in (-1, 0, 1):
+        c.update(k0_kick=k0, k1_kick=k1, h_kick=h, k0_h_correction=k0,
+                 k1_h_correction=k1, kick_rot_frame=1)
+    elif drift_model == 2:
+        c.update(h_drift=h, k0_kick=k0, k1_kick=k1, h_kick=h, k0_h_correction=k0,
+                 k1_h_correction=k1)
+    elif drift_model == 3:
+        c.update(k0_drift=k0, k1_drift=k1, h_drift=h, h_kick=h, k1_h_correction=k1)
+    elif drift_model == 4:
+        c.update(k0_drift=k0, h_drift=h, k1_kick=k1, h_kick=h, k1_h_correction=k1)
+    elif drift_model == 5:
+        c.update(k0_drift=k0, k1_kick=k1)
+    elif drift_model == 6:
+        c.update(ks_drift=ks, k0_kick=k0, k1_kick=k1, h_kick=h, k0_h_correction=k0,
+                 k1_h_correction=k1, kick_rot_frame=1)
+    elif drift_model in (7, 8):
+        c.update(k0_drift=k0, h_drift=h, k1_kick=k1, h_kick=h, k0_h_correction=k0,
+                 k1_h_correction=k1)
+    return c
+
+
+def _linear_edge_coefficients(k, e1, e1_fd, hgap, fint):
+    """track_dipole_edge_linear.h:12-27"""
+    corr = 2.0 * k * hgap * fint
+    r21 = k * math.tan(e1)
+    e1_v = e1 + e1_fd
+    sin_e1_v = math.sin(e1_v)
+    temp = corr / math.cos(e1_v) * (1.0 + sin_e1_v * sin_e1_v)
+    r43 = -k * math.tan(e1_v - temp)
+    return r21, r43
+
+
+# -- misalignment (track_misalignments.h) -------------------------------------
+def _emit_y_rotate(prog, theta):
+    if theta != 0.0:
+        prog.op(OP_YROT, [math.sin(theta), math.cos(theta), math.tan(theta)], transc=0)
+
+
+def _emit_x_rotate(prog, phi):
+    if phi != 0.0:
+        prog.op(OP_XROT, [-math.sin(phi), math.cos(phi), -math.tan(phi)])
+
+
+def _emit_s_rotate(prog, psi):
+    if psi != 0.0:
+        prog.op(OP_SROT, [math.sin(psi), math.cos(psi)])
+
+
+def _emit_s_shift(prog, ds):
+    if ds != 0.0:
+        prog.op(OP_SSHIFT, [ds])
+
+
+def _misalign_entry_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
+                             psi_with_frame):
+    """track_misalignments.h:38-75 (forward tracking)"""
+    mis_x = dx - anchor * math.cos(phi) * math.sin(theta)
+    mis_y = dy - anchor * math.sin(phi)
+    mis_s = ds - anchor * (math.cos(phi) * math.cos(theta) - 1)
+    prog.op(OP_XYSHIFT, [mis_x, mis_y])
+    _emit_s_shift(prog, mis_s)
+    _emit_y_rotate(prog, theta)
+    _emit_x_rotate(prog, phi)
+    _emit_s_rotate(prog, psi_no_frame)
+    _emit_s_rotate(prog, psi_with_frame)
+
+
+def _misalign_exit_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
+                            psi_with_frame):
+    """track_misalignments.h:78-113"""
+    neg_part_length = anchor - length
+    mis_x = neg_part_length * math.cos(phi) * math.sin(theta) - dx
+    mis_y = neg_part_length * math.sin(phi) - dy
+    mis_s = neg_part_length * (math.cos(phi) * math.cos(theta) - 1) - ds
+    _emit_s_rotate(prog, -psi_with_frame)
+    _emit_s_rotate(prog, -psi_no_frame)
+    _emit_x_rotate(prog, -phi)
+    _emit_y_rotate(prog, -theta)
+    _emit_s_shift(prog, mis_s)
+    prog.op(OP_XYSHIFT, [mis_x, mis_y])
+
+
+def _mat_mul(a, b):
+    """matrix_multiply_4x4, track_misalignments.h:381-389"""
+    r = [[0.0] * 4 for _ in range(4)]
+    for i in range(4):
+        for j in range(4):
+            r[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j] + a[i][3] * b[3][j]
+    return r
+
+
+def _rigid_inverse(m):
+    """matrix_rigid_affine_inverse, track_misalignments.h:392-420"""
+    inv = [[0.0] * 4 for _ in range(4)]
+    for i in range(3):
+        for j in range(3):
+            inv[i][j] = m[j][i]
+    inv[0][3] = -m[0][0] * m[0][3] - m[1][0] * m[1][3] - m[2][0] * m[2][3]
+    inv[1][3] = -m[0][1] * m[0][3] - m[1][1] * m[1][3] - m[2][1] * m[2][3]
+    inv[2][3] = -m[0][2] * m[0][3] - m[1][2] * m[1][3] - m[2][2] * m[2][3]
+    inv[3] = [0.0, 0.0, 0.0, 1.0]
+    return inv
+
+
+def _misalignment_matrix(dx, dy, ds, theta, phi, psi):
+    s_phi, c_phi = math.sin(phi), math.cos(phi)
+    s_theta, c_theta = math.sin(theta), math.cos(theta)
+    s_psi, c_psi = math.sin(psi), math.cos(psi)
+    return [
+        [-s_phi * s_psi * s_theta + c_psi * c_theta,
+         -c_psi * s_phi * s_theta - c_theta * s_psi, c_phi * s_theta, dx],
+        [c_phi * s_psi, c_phi * c_psi, s_phi, dy],
+        [-c_theta * s_phi * s_psi - c_psi * s_theta,
+         -c_psi * c_theta * s_phi + s_psi * s_theta, c_phi * c_theta, ds],
+        [0.0, 0.0, 0.0, 1.0]]
+
+
+def _misalign_entry_curved(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
+                           angle, h, psi_with_frame):
+    """track_misalignments.h:116-241"""
+    if angle == 0.0 and (length != 0.0 or h == 0.0):
+        return _misalign_entry_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor,
+                                        length, psi_with_frame)
+    mm = _misalignment_matrix(dx, dy, ds, theta, phi, psi_no_frame)
+    if length != 0.0:
+        h = angle / length
+    part_angle = anchor * h
+    cpa, spa = math.cos(part_angle), math.sin(part_angle)
+    cps, sps = math.cos(psi_with_frame), math.sin(psi_with_frame)
+    first = [
+        [(cpa - 1) * (cps * cps) + 1, (cpa - 1) * cps * sps, -cps * spa, (cpa - 1) * cps / h],
+        [(cpa - 1) * cps * sps, (cpa - 1) * (sps * sps) + 1, -spa * sps, (cpa - 1) * sps / h],
+        [cps * spa, spa * sps, cpa, spa / h],
+        [0.0, 0.0, 0.0, 1.0]]
+    inv_first = _rigid_inverse(first)
+    me = _mat_mul(_mat_mul(first, mm), inv_first)
+    mis_x, mis_y, mis_s = me[0][3], me[1][3], me[2][3]
+    rot_theta = math.atan2(me[0][2], me[2][2])
+    rot_phi = math.atan2(me[1][2], math.sqrt(me[1][0] * me[1][0] + me[1][1] * me[1][1]))
+    rot_psi = math.atan2(me[1][0], me[1][1])
+    prog.op(OP_XYSHIFT, [mis_x, mis_y])
+    _emit_s_shift(prog, mis_s)
+    _emit_y_rotate(prog, rot_theta)
+    _emit_x_rotate(prog, rot_phi)
+    _emit_s_rotate(prog, rot_psi)
+    _emit_s_rotate(prog, psi_with_frame)
+
+
+def _misalign_exit_curved(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
+                          angle, h, psi_with_frame):
+    """track_misalignments.h:244-378"""
+    if angle == 0.0 and (length != 0.0 or h == 0.0):
+        return _misalign_exit_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor,
+                                       length, psi_with_frame)
+    mm = _misalignment_matrix(dx, dy, ds, theta, phi, psi_no_frame)
+    inv_mm = _rigid_inverse(mm)
+    if length != 0.0:
+        h = angle / length
+    part_angle = angle - h * anchor
+    spa, cpa = math.sin(part_angle), math.cos(part_angle)
+    st, ct = math.sin(psi_with_frame), math.cos(psi_with_frame)
+    second = [
+        [(cpa - 1) * (ct * ct) + 1, (cpa - 1) * ct * st, ct * -spa, (cpa - 1) * ct / h],
+        [(cpa - 1) * ct * st, (cpa - 1) * (st * st) + 1, -spa * st, (cpa - 1) * st / h],
+        [ct * spa, spa * st, cpa, spa / h],
+        [0.0, 0.0, 0.0, 1.0]]
+    inv_second = _rigid_inverse(second)
+    re = _mat_mul(_mat_mul(inv_second, inv_mm), second)
+    mis_x, mis_y, mis_s = re[0][3], re[1][3], re[2][3]
+    rot_theta = math.atan2(re[0][2], re[2][2])
+    rot_phi = math.atan2(re[1][2], math.sqrt(re[1][0] * re[1][0] + re[1][1] * re[1][1]))
+    rot_psi = math.atan2(re[1][0], re[1][1])
+    _emit_s_rotate(prog, -psi_with_frame)
+    prog.op(OP_XYSHIFT, [mis_x, mis_y])
+    _emit_s_shift(prog, mis_s)
+    _emit_y_rotate(prog, rot_theta)
+    _emit_x_rotate(prog, rot_phi)
+    _emit_s_rotate(prog, rot_psi)
+
+
+def _with_transformations(prog, el, body, *, length=0.0, curved=False, weight=1.0):
+    """headers/track_local_particle_with_transformations.h:174-204 (+ :99-162)"""
+    if not el.allow_rot_and_shift or not el.has_misalignment:
+        body()
+        return
+    args = [el.shift_x, el.shift_y, el.shift_s, el.rot_y_rad, el.rot_x_rad,
+            el.rot_s_rad_no_frame, el.rot_shift_anchor, length * weight]
+    if curved:
+        cargs = args + [el.angle * weight, el.h, el.rot_s_rad]
+        _misalign_entry_curved(prog, *cargs)
+        body()
+        _misalign_exit_curved(prog, *cargs)
+    else:
+        sargs = args + [el.rot_s_rad]
+        _misalign_entry_straight(prog, *sargs)
+        body()
+        _misalign_exit_straight(prog, *sargs)
+
+
+# ---------------------------------------------------------------------------
+# magnets (track_magnet.h:289-648)
+# ---------------------------------------------------------------------------
+def _emit_thin_multipole(prog, coeffs, hl, b0, b1):
+    order = len(coeffs) // 2 - 1
+    if hl == 0.0 and b0 == 0.0 and b1 == 0.0:
+        if _all_zero(coeffs):
+            prog.op(OP_NOP)
+        else:
+            prog.op(OP_MULT, coeffs, aux=order, flops=flops_mult(order))
+    else:
+        has_b1 = 1 if b1 != 0.0 else 0
+        prog.op(OP_MULT_H, [hl, b0, b1, 0.0] + coeffs, aux=order | (has_b1 << 8),
+                flops=flops_mult(order) + 14 + (8 if has_b1 else 0))
+
+
+def _lower_edge(prog, synrad, *, model, is_exit, half_gap, knorm, kskew, knl, ksl,
+                factor_knl_ksl, kl_order, knl_rel, ksl_rel, factor_knl_ksl_rel, order_rel,
+                length, face_angle, face_angle_feed_down, fringe_integral):
+    """track_magnet_edge.h:17-167 (forward tracking, no solenoid)"""
+    k0 = 0.0
+    k0 += knorm[0]
+    if abs(length) > 1e-10 and kl_order > -1:
+        k0 += factor_knl_ksl * knl[0] / length
+    if abs(length) > 1e-10 and order_rel > -1 and knl_rel is not None:
+        k0 += factor_knl_ksl_rel * knl_rel[0] / length
+    if model == 0:
+        r21, r43 = _linear_edge_coefficients(k0, face_angle, face_angle_feed_down, half_gap,
+                                             fringe_integral)
+        r21 = r21 * 1.0
+        r43 = r43 * 1.0
+        prog.op(OP_EDGE_LIN, [r21, r43])
+    elif model in (1, 2):
+        should_rotate = 0
+        sin_, cos_, tan_ = 0.0, 1.0, 0.0
+        if abs(face_angle) > 10e-10:
+            should_rotate = 1
+            sin_, cos_, tan_ = math.sin(face_angle), math.cos(face_angle), math.tan(face_angle)
+        if is_exit:
+            k0 = -k0
+        nkl = kl_order + 1
+        params = [k0, sin_, cos_, tan_, fringe_integral, half_gap, face_angle,
+                  length / factor_knl_ksl, *[float(v) for v in knorm[:4]],
+                  *[float(v) for v in kskew[:4]],
+                  *[float(v) for v in knl[:nkl]], *[float(v) for v in ksl[:nkl]]]
+        aux = (1 if is_exit else 0) | (model << 1) | (should_rotate << 3) | (nkl << 4)
+        prog.op(OP_MAGNET_EDGE, params, aux=aux, flops=300, transc=6)
+    # model 3 / -1: nothing besides the (zero) ax, ay reset
+
+
+def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl, ksl,
+                  knl_rel, ksl_rel, rel_ref_strength, num_multipole_kicks, model,
+                  default_model, integrator, default_integrator, radiation_flag,
+                  delta_taper, h, hxl, k0, k1, k2, k3, k0s, k1s, k2s, k3s,
+                  rbend_model=-1, rbend_compensate_sagitta=0, rbend_shift=0.0,
+                  rbend_angle_diff=0.0, length_straight=0.0, body_active=1,
+                  edge_entry_active=0, edge_exit_active=0, edge_entry_model=0,
+                  edge_exit_model=0, edge_entry_angle=0.0, edge_exit_angle=0.0,
+                  edge_entry_angle_fdown=0.0, edge_exit_angle_fdown=0.0,
+                  edge_entry_fint=0.0, edge_exit_fint=0.0, edge_entry_hgap=0.0,
+                  edge_exit_hgap=0.0, radiation_flag_parent=0):
+    synrad = cfg['synrad']
+    order_rel = len(knl_rel) - 1
+    inv_factorial_order_rel = one_over_factorial(order_rel)
+    factor_knl_ksl = 1.0
+    theta_in = theta_out = 0.0
+    cos_theta_in, sin_theta_in, cos_theta_out, sin_theta_out = 1.0, 0.0, 1.0, 0.0
+    length_curved = 0.0
+    x0_mid = x0_in = x0_out = 0.0
+
+    if rbend_model == 0:
+        rbend_model = 1
+    angle = h * length
+    if rbend_model == 1:
+        edge_entry_angle += (angle - rbend_angle_diff) / 2.0
+        edge_exit_angle += (angle + rbend_angle_diff) / 2.0
+    elif rbend_model == 2:
+        theta_in = (angle - rbend_angle_diff) / 2.0
+        if abs(theta_in) > 1e-10:
+            sin_theta_in, cos_theta_in = math.sin(theta_in), math.cos(theta_in)
+        theta_out = (angle + rbend_angle_diff) / 2.0
+        if abs(theta_out) > 1e-10:
+            sin_theta_out, cos_theta_out = math.sin(theta_out), math.cos(theta_out)
+        length_curved = length
+        length = length_straight
+        x0_mid -= rbend_shift
+        if rbend_compensate_sagitta and abs(angle) > 1e-10:
+            cos_rbha = math.cos(angle / 2.)
+            x0_mid += 0.5 / h * (1 - cos_rbha)
+        x0_in = x0_mid
+        x0_out = x0_mid
+        if abs(angle) > 1e-10:
+            px0_in = math.sin(theta_in)
+            px0_mid = px0_in - h * length_straight / 2
+            sqrt_mid = math.sqrt(1 - px0_mid * px0_mid)
+            x0_in -= 1 / h * (sqrt_mid - cos_theta_in)
+            x0_out += 1 / h * (cos_theta_out - sqrt_mid)
+        h = 0.0
+        edge_entry_angle_fdown += theta_in
+        edge_exit_angle_fdown += theta_out
+
+    core_length = length * weight
+    core_length_curved = length_curved * weight
+    factor_knl_ksl_body = factor_knl_ksl * weight
+    factor_knl_ksl_edge = factor_knl_ksl
+
+    if synrad:
+        if radiation_flag == 10:
+            radiation_flag = radiation_flag_parent
+        if radiation_flag:
+            factor_knl_ksl_body *= (1. + delta_taper)
+            factor_knl_ksl_edge *= (1. + delta_taper)
+            k0 *= (1 + delta_taper); k1 *= (1 + delta_taper)
+            k2 *= (1 + delta_taper); k3 *= (1 + delta_taper)
+            k0s *= (1 + delta_taper); k1s *= (1 + delta_taper)
+            k2s *= (1 + delta_taper); k3s *= (1 + delta_taper)
+    else:
+        radiation_flag = 0
+
+    knorm = [k0, k1, k2, k3]
+    kskew = [k0s, k1s, k2s, k3s]
+    edge_common = dict(knorm=knorm, kskew=kskew, knl=knl, ksl=ksl,
+                       factor_knl_ksl=factor_knl_ksl_edge, kl_order=order,
+                       knl_rel=knl_rel, ksl_rel=ksl_rel,
+                       factor_knl_ksl_rel=factor_knl_ksl_edge * rel_ref_strength,
+                       order_rel=order_rel, length=length)
+
+    if edge_entry_active:
+        if rbend_model == 2:
+            prog.op(OP_YROT, [-sin_theta_in, cos_theta_in, -sin_theta_in / cos_theta_in])
+            prog.op(OP_ADD_X, [x0_in])
+        _lower_edge(prog, synrad, model=edge_entry_model, is_exit=0, half_gap=edge_entry_hgap,
+                    face_angle=edge_entry_angle, face_angle_feed_down=edge_entry_angle_fdown,
+                    fringe_integral=edge_entry_fint, **edge_common)
+
+    if body_active:
+        if integrator == 0:
+            integrator = default_integrator
+        if model == 0:
+            model = default_model
+        if model == -1:
+            integrator = 3
+            num_multipole_kicks = 1
+        if weight != 1.0 and num_multipole_kicks > 0:
+            num_multipole_kicks = int(math.ceil(num_multipole_kicks * weight))
+        if num_multipole_kicks == 0:
+            if not _kick_is_inactive(order, knl, ksl, k0, k1, k2, k3, k0s, k1s, k2s, k3s, h):
+                if abs(h) < 1e-8:
+                    num_multipole_kicks = 1
+                else:
+                    b_circum = 2 * 3.14159 / abs(h)
+                    num_multipole_kicks = int(abs(core_length) / b_circum / 0.5e-3)
+                    if num_multipole_kicks < 1:
+                        num_multipole_kicks = 1
+        c = _configure_tracking_model(model, k0, k1, h, 0.0)
+        if c['drift_model'] in (6, 99999999):
+            raise NotImplementedError('solenoid / invalid magnet model outside the contract')
+
+        coeffs = _horner_coeffs(knl, ksl, order, inv_factorial_order, factor_knl_ksl_body)
+        coeffs_rel = _horner_coeffs(knl_rel, ksl_rel, order_rel, inv_factorial_order_rel,
+                                    factor_knl_ksl_body * rel_ref_strength)
+        kmain_n = [c['k0_kick'], c['k1_kick'], k2, k3]
+        kmain_s = [k0s, k1s, k2s, k3s]
+        knl_main = [v * core_length for v in kmain_n]
+        ksl_main = [v * core_length for v in kmain_s]
+        coeffs_main = _horner_coeffs(knl_main, ksl_main, 3, 1. / (3 * 2), 1.0)
+
+        # curvature terms of track_magnet_kick.h:98-142 (element constants)
+        htot = c['h_kick']
+        if core_length != 0:
+            htot += hxl / core_length
+        k0l_mult = 0.0
+        if order >= 0:
+            k0l_mult = knl[0] * factor_knl_ksl_body
+        if order_rel >= 0:
+            k0l_mult += knl_rel[0] * factor_knl_ksl_body * rel_ref_strength
+        a0 = c['k0_h_correction'] * core_length + k0l_mult
+        k1l_mult = 0.0
+        if order >= 1:
+            k1l_mult = knl[1] * factor_knl_ksl_body
+        if order_rel >= 1:
+            k1l_mult += knl_rel[1] * factor_knl_ksl_body * rel_ref_strength
+        a1 = c['k1_h_correction'] * core_length + k1l_mult
+
+        drift_only = (num_multipole_kicks == 0 and c['k0_kick'] == 0 and c['k1_kick'] == 0
+                      and c['h_kick'] == 0)
+        thin_fast = (model == -1 and not (synrad and radiation_flag and core_length > 0)
+                     and _all_zero(coeffs_rel) and _all_zero(coeffs_main) and not synrad)
+        if thin_fast:
+            # kick-only element, kick_weight = 1: the fast thin-multipole ops
+            kw = 1.0
+            if c['kick_rot_frame']:
+                hl = c['h_kick'] * core_length * kw + hxl * kw
+            else:
+                hl = 0.0
+            b0 = ((-1.0 * a0) * kw) * htot
+            b1 = ((htot * 1.0) * a1) * kw
+            if not coeffs:
+                coeffs = [0.0, 0.0]
+            _emit_thin_multipole(prog, coeffs, hl, b0, b1)
+        elif drift_only and not (synrad and radiation_flag) and c['drift_model'] in (0, 1, -1):
+            if c['drift_model'] == 0 and core_length != 0.0:
+                prog.op(OP_DRIFT, [core_length])
+            elif c['drift_model'] == 1 and core_length != 0.0:
+                prog.op(OP_DRIFT_EXACT, [core_length])
+        else:
+            flags = ((integrator & 3) | ((c['drift_model'] + 1) << 2)
+                     | ((1 if c['kick_rot_frame'] else 0) << 6)
+                     | ((0 if _all_zero(coeffs) else 1) << 7)
+                     | ((0 if _all_zero(coeffs_rel) else 1) << 8)
+                     | ((0 if _all_zero(coeffs_main) else 1) << 9)
+                     | ((radiation_flag & 3) << 10)
+                     | ((1 if drift_only else 0) << 12))
+            if num_multipole_kicks >= (1 << 19):
+                raise ValueError('num_multipole_kicks too large')
+            aux = flags | (num_multipole_kicks << 13)
+            if not coeffs:
+                coeffs = [0.0, 0.0]
+            if not coeffs_rel:
+                coeffs_rel = [0.0, 0.0]
+            ou = len(coeffs) // 2 - 1
+            orl = len(coeffs_rel) // 2 - 1
+            params = [core_length, c['k0_drift'], c['k1_drift'], c['h_drift'], c['h_kick'], hxl,
+                      a0, a1, htot, _RawWord(ou | (orl << 32)),
+                      c['k0_drift'] + c['k0_kick'], c['k1_drift'] + c['k1_kick'], k2, k3,
+                      k0s, k1s, k2s, k3s,
+                      *coeffs_main, *coeffs, *coeffs_rel]
+            prog.op(OP_MAGNET_BODY, params, aux=aux,
+                    flops=_body_flops(c['drift_model'], integrator, num_multipole_kicks,
+                                      drift_only, ou, coeffs_main),
+                    transc=_body_transc(c['drift_model'], integrator, num_multipole_kicks,
+                                        drift_only))
+        if rbend_model == 2 and model >= 0:
+            ds = core_length_curved - core_length
+            prog.op(OP_ADD_S_ZETA, [ds])
+
+    if edge_exit_active:
+        _lower_edge(prog, synrad, model=edge_exit_model, is_exit=1, half_gap=edge_exit_hgap,
+                    face_angle=edge_exit_angle, face_angle_feed_down=edge_exit_angle_fdown,
+                    fringe_integral=edge_exit_fint, **edge_common)
+        if rbend_model == 2:
+            prog.op(OP_ADD_X, [-x0_out])
+            prog.op(OP_YROT, [-sin_theta_out, cos_theta_out, -sin_theta_out / cos_theta_out])
+
+
+_DRIFT_FLOPS = {-1: 0, 0: 17, 1: 21, 2: 45, 3: 95, 4: 60, 5: 40, 7: 4 * 45 + 9, 8: 8 * 45 + 21}
+_DRIFT_TRANSC = {-1: 0, 0: 0, 1: 0, 2: 3, 3: 4, 4: 4, 5: 2, 7: 12, 8: 24}
+
+
+def _body_steps(integrator, n_kicks, drift_only):
+    """(#drift calls, #kick calls) of the integrator loops, track_magnet.h:181-276"""
+    if drift_only:
+        return 1, 0
+    if integrator == 1:
+        return n_kicks + 1, n_kicks
+    if integrator == 3:
+        return 2 * n_kicks, n_kicks
+    n_slices = n_kicks // 7 + (1 if n_kicks % 7 else 0)
+    return 8 * n_slices, 7 * n_slices
+
+
+def _body_flops(drift_model, integrator, n_kicks, drift_only, order_user, coeffs_main):
+    nd, nk = _body_steps(integrator, n_kicks, drift_only)
+    kick = flops_mult(order_user) + (0 if _all_zero(coeffs_main) else flops_mult(3)) + 10
+    return nd * _DRIFT_FLOPS.get(drift_model, 0) + nk * kick
+
+
+def _body_transc(drift_model, integrator, n_kicks, drift_only):
+    nd, _ = _body_steps(integrator, n_kicks, drift_only)
+    return nd * _DRIFT_TRANSC.get(drift_model, 0)
+
+
+# ---------------------------------------------------------------------------
+# RF (track_rf.h:317-453)
+# ---------------------------------------------------------------------------
+def _lower_rf(prog, cfg, *, weight, length, voltage, frequency, harmonic, lag, phase,
+              absolute_time, order, knl, ksl, pn, ps, phase_n, phase_s, num_kicks, model,
+              default_model, integrator, default_integrator, lag_taper, phase_taper):
+    if cfg['synrad']:
+        lag += lag_taper
+        phase += phase_taper
+    body_length = length
+    factor_knl_ksl_body = 1.0
+    if integrator == 0:
+        integrator = default_integrator
+    if model == 0:
+        model = default_model
+    if model == -1:
+        integrator = 3
+        num_kicks = 1
+    if weight != 1.0 and num_kicks > 0:
+        num_kicks = int(math.ceil(num_kicks * weight))
+    if num_kicks == 0:
+        num_kicks = 1
+    c = _configure_tracking_model(model, 0., 0., 0., 0.)
+    drift_model = c['drift_model']
+    if drift_model == 5:
+        drift_model = 1        # straight exact bend with k0 = 0 is the exact drift
+    if drift_model not in (-1, 0, 1):
+        raise NotImplementedError(f'RF element model {model} outside the contract')
+    ll = body_length * weight
+    vv = voltage * weight
+    ff = factor_knl_ksl_body * weight
+
+    def drift(dl):
+        if drift_model == -1 or dl == 0.0:
+            return
+        prog.op(OP_DRIFT if drift_model == 0 else OP_DRIFT_EXACT, [dl])
+
+    def kick(kw):
+        if order >= 0:
+            fk = ff * kw
+            params = [vv * kw, frequency, lag, phase, 0.0]
+            for kk in range(order + 1):
+                params += [fk * float(knl[kk]), fk * float(ksl[kk]), float(pn[kk]), float(ps[kk]),
+                           float(phase_n[kk]), float(phase_s[kk])]
+            prog.op(OP_RFMULT, params, aux=order, flops=25 + 30 * (order + 1),
+                    transc=1 + 4 * (order + 1))
+        else:
+            prog.op(OP_CAVITY, [vv * kw, frequency, harmonic, lag, phase, 0.0, 0.0],
+                    aux=int(absolute_time), transc=1)
+
+    if integrator == 1:
+        kick_weight = 1. / num_kicks
+        edge_drift_weight = 0.5
+        inside_drift_weight = 0.0
+        if num_kicks > 1:
+            edge_drift_weight = 1. / (2 * (1 + num_kicks))
+            inside_drift_weight = float(num_kicks) / (float(num_kicks * num_kicks) - 1)
+        drift(edge_drift_weight * ll)
+        for _ in range(num_kicks - 1):
+            kick(kick_weight)
+            drift(inside_drift_weight * ll)
+        kick(kick_weight)
+        drift(edge_drift_weight * ll)
+    elif integrator == 3:
+        kick_weight = 1. / num_kicks
+        drift_weight = kick_weight
+        for _ in range(num_kicks):
+            drift(0.5 * drift_weight * ll)
+            kick(kick_weight)
+            drift(0.5 * drift_weight * ll)
+    elif integrator == 2:
+        num_slices = num_kicks // 7 + (1 if num_kicks % 7 != 0 else 0)
+        slice_length = ll / num_slices
+        kick_weight = 1. / num_slices
+        d = [3.922568052387799819591407413100e-01, 5.100434119184584780271052295575e-01,
+             -4.710533854097565531482416645304e-01, 6.875316825251809316199569366290e-02]
+        k = [7.845136104775599639182814826199e-01, 2.355732133593569921359289764951e-01,
+             -1.177679984178870098432412305556e+00, 1.315186320683906284756403692882e+00]
+        seq = [0, 1, 2, 3, 3, 2, 1, 0]
+        for _ in range(num_slices):
+            for ii, dd in enumerate(seq):
+                drift(slice_length * d[dd])
+                if ii < 7:
+                    kick(kick_weight * k[[0, 1, 2, 3, 2, 1, 0][ii]])
+
+
+# ---------------------------------------------------------------------------
+# per-class lowering
+# ---------------------------------------------------------------------------
+def _magnet_common_kwargs(el):
+    return dict(order=el.order, inv_factorial_order=el.inv_factorial_order,
+                knl=[float(v) for v in el.knl], ksl=[float(v) for v in el.ksl],
+                knl_rel=[float(v) for v in el.knl_rel], ksl_rel=[float(v) for v in el.ksl_rel],
+                num_multipole_kicks=el.num_multipole_kicks, integrator=el.integrator,
+                radiation_flag=el.radiation_flag, delta_taper=el.delta_taper)
+
+
+def lower_element(prog, el, cfg):
+    """Appends the ops of one element; returns True if the class is statically
+    thick (global aperture check after it, tracker.py:681-689)."""
+    name = type(el).__name__
+
+    if name in ('Marker', '_Placeholder'):
+        return False
+
+    if name == 'Drift':
+        model = 2 if cfg.get('exact_drifts') else (el.model or 1)
+        if model == 1:
+            prog.op(OP_DRIFT, [el.length])
+        elif model == 2:
+            prog.op(OP_DRIFT_EXACT, [el.length])
+        return True
+
+    if name == 'DriftExact':
+        prog.op(OP_DRIFT_EXACT, [el.length])
+        return True
+
+    if name == 'Multipole':
+        thick = el._isthick_field > 0
+
+        def body():
+            _lower_magnet(
+                prog, cfg, weight=1., length=el.length, **_magnet_common_kwargs(el),
+                rel_ref_strength=float(el.main_strength),
+                model=(el.model if thick else -1), default_model=6, default_integrator=3,
+                h=0., hxl=el.hxl, k0=0., k1=0., k2=0., k3=0., k0s=0., k1s=0., k2s=0., k3s=0.)
+        _with_transformations(prog, el, body, length=(el.length if thick else 0.0))
+        return False
+
+    if name in ('Quadrupole', 'Sextupole', 'Octupole'):
+        kk = dict(k1=0., k2=0., k3=0., k1s=0., k2s=0., k3s=0.)
+        kn, ks = el._main
+        kk[kn], kk[ks] = getattr(el, kn), getattr(el, ks)
+        main = getattr(el, ks) if el.main_is_skew else getattr(el, kn)
+
+        def body():
+            _lower_magnet(
+                prog, cfg, weight=1., length=el.length, **_magnet_common_kwargs(el),
+                rel_ref_strength=el.length * main, model=el.model,
+                default_model=4 if name == 'Quadrupole' else 6, default_integrator=3,
+                h=0., hxl=0., k0=0., k0s=0., **kk,
+                edge_entry_active=el.edge_entry_active, edge_exit_active=el.edge_exit_active,
+                edge_entry_model=1, edge_exit_model=1)
+        _with_transformations(prog, el, body, length=el.length)
+        return True
+
+    if name in ('Bend', 'RBend'):
+        extra = {}
+        if name == 'RBend':
+            extra = dict(rbend_model=el.rbend_model,
+                         rbend_compensate_sagitta=el.rbend_compensate_sagitta,
+                         rbend_shift=el.rbend_shift, rbend_angle_diff=el.rbend_angle_diff,
+                         length_straight=el.length_straight)
+
+        def body():
+            _lower_magnet(
+                prog, cfg, weight=1., length=el.length, **_magnet_common_kwargs(el),
+                rel_ref_strength=el.k0 * el.length, model=el.model, default_model=3,
+                default_integrator=2, h=el.h, hxl=0., k0=el.k0, k1=el.k1, k2=el.k2, k3=0.,
+                k0s=0., k1s=0., k2s=0., k3s=0.,
+                edge_entry_active=el.edge_entry_active, edge_exit_active=el.edge_exit_active,
+                edge_entry_model=el.edge_entry_model, edge_exit_model=el.edge_exit_model,
+                edge_entry_angle=el.edge_entry_angle, edge_exit_angle=el.edge_exit_angle,
+                edge_entry_angle_fdown=el.edge_entry_angle_fdown,
+                edge_exit_angle_fdown=el.edge_exit_angle_fdown,
+                edge_entry_fint=el.edge_entry_fint, edge_exit_fint=el.edge_exit_fint,
+                edge_entry_hgap=el.edge_entry_hgap, edge_exit_hgap=el.edge_exit_hgap, **extra)
+        _with_transformations(prog, el, body, length=el.length, curved=True)
+        return True
+
+    if name == 'Cavity':
+        def body():
+            _lower_rf(prog, cfg, weight=1., length=el.length, voltage=el.voltage,
+                      frequency=el.frequency, harmonic=el.harmonic, lag=el.lag, phase=el.phase,
+                      absolute_time=el.absolute_time, order=-1, knl=None, ksl=None, pn=None,
+                      ps=None, phase_n=None, phase_s=None, num_kicks=el.num_kicks,
+                      model=el.model, default_model=6, integrator=el.integrator,
+                      default_integrator=3, lag_taper=el.lag_taper, phase_taper=el.phase_taper)
+        _with_transformations(prog, el, body, length=el.length)
+        return True
+
+    if name == 'RFMultipole':
+        def body():
+            _lower_rf(prog, cfg, weight=1., length=0., voltage=el.voltage,
+                      frequency=el.frequency, harmonic=0., lag=el.lag, phase=el.phase,
+                      absolute_time=0, order=el.order, knl=el.knl, ksl=el.ksl, pn=el.pn,
+                      ps=el.ps, phase_n=el.phase_n, phase_s=el.phase_s, num_kicks=1, model=-1,
+                      default_model=0, integrator=0, default_integrator=0, lag_taper=0.,
+                      phase_taper=0.)
+        _with_transformations(prog, el, body, length=0.0)
+        return False
+
+    if name == 'DipoleEdge':
+        def body():
+            delta_taper = el.delta_taper if cfg['synrad'] else 0.0
+            if el.model == 0:
+                r21 = el.r21 * (1 + delta_taper)
+                r43 = el.r43 * (1 + delta_taper)
+                prog.op(OP_EDGE_LIN, [r21, r43])
+            elif el.model == 1:
+                if abs(el.e1) < 10e-10:
+                    sct = [-999.0, -999.0, -999.0]
+                else:
+                    sct = [math.sin(el.e1), math.cos(el.e1), math.tan(el.e1)]
+                prog.op(OP_DIPEDGE_NL, [el.k, el.e1, el.fint, el.hgap, *sct], aux=el.side,
+                        flops=300, transc=6)
+        _with_transformations(prog, el, body)
+        return False
+
+    if name == 'SRotation':
+        prog.op(OP_SROT, [el.sin_z, el.cos_z])
+        return False
+
+    if name == 'XYShift':
+        prog.op(OP_XYSHIFT, [el.dx, el.dy])
+        return False
+
+    if name == 'LimitRect':
+        _with_transformations(prog, el, lambda: prog.op(
+            OP_LIMIT_RECT, [el.min_x, el.max_x, el.min_y, el.max_y]))
+        return False
+
+    if name == 'LimitEllipse':
+        _with_transformations(prog, el, lambda: prog.op(
+            OP_LIMIT_ELLIPSE, [el.a_squ, el.b_squ, el.a_b_squ]))
+        return False
+
+    if name == 'LimitPolygon':
+        nv = len(el.x_vertices)
+        _with_transformations(prog, el, lambda: prog.op(
+            OP_LIMIT_POLYGON, [*el.x_vertices, *el.y_vertices], aux=nv, flops=7 * nv))
+        return False
+
+    if name == 'ParticlesMonitor':
+        prog.monitors.append(el)
+        prog.op(OP_MONITOR, aux=len(prog.monitors) - 1)
+        return False
+
+    if name == 'LastTurnsMonitor':
+        prog.last_turns_monitors.append(el)
+        prog.op(OP_LAST_TURNS, aux=len(prog.last_turns_monitors) - 1)
+        return False
+
+    raise NotImplementedError(f'element class {name} is outside the hot-path contract')
+
+
+def lower_line(elements, *, synrad=False, exact_drifts=False):
+    """Lowers a sequence of host elements.  Returns the `Program`."""
+    cfg = dict(synrad=bool(synrad), exact_drifts=bool(exact_drifts))
+    prog = Program()
+    cache = {}
+    for el in elements:
+        static_thick = lower_element(prog, el, cfg)
+        prog.end_element(static_thick)
+    return prog

@@ -1,0 +1,235 @@
+"""`Tracker`: host orchestration of a `Line.track` call.
+
+Mirrors the non-collective path of the reference tracker:
+  Tracker.__init__                  xtrack/tracker.py:38-147   -> lattice lowering + upload
+  Tracker._track_no_collective      xtrack/tracker.py:1200-1443 (turn splitting :1270-1333,
+                                    end-of-turn flags :1335-1342, monitor :1344-1352,
+                                    rng seeding :1364-1365, <= 3 kernel launches :1372-1436)
+  Tracker._get_monitor              xtrack/tracker.py:1445-1480
+The kernel launches go through the C-ABI (`_cabi.Lattice.track` -> `xtb_track`).
+"""
+import numpy as np
+import torch
+
+from . import _cabi
+from . import lowering
+from .monitors import ParticlesMonitor
+
+
+class Tracker:
+
+    def __init__(self, line, device=None, exact_arithmetic=False, compact_every=None):
+        self.line = line
+        if device is None:
+            device = 'cuda'
+        device = torch.device(device)
+        if device.type == 'cuda' and device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = device
+        self.exact_arithmetic = bool(exact_arithmetic)
+        self.compact_every = compact_every
+        self.num_elements = len(line.element_names)
+        self._config_key = None
+        self._lattice = None
+        self.program = None
+        self._ensure_lattice()
+
+    # -- lattice ------------------------------------------------------------
+    def _current_config_key(self):
+        return (not self.line.config.get('XTRACK_MULTIPOLE_NO_SYNRAD', True),
+                bool(self.line.config.get('XTRACK_USE_EXACT_DRIFTS', False)))
+
+    def _ensure_lattice(self):
+        """One lowered lattice per distinct compile-time config, like the
+        reference's kernel cache keyed by the config hash (tracker.py:1564-1596)."""
+        key = self._current_config_key()
+        if self._lattice is not None and key == self._config_key:
+            return
+        synrad, exact_drifts = key
+        prog = lowering.lower_line(self.line.elements, synrad=synrad, exact_drifts=exact_drifts)
+        words, elem_offset = prog.finish()
+        self.line_length = self.line.get_length()
+        if self._lattice is not None:
+            self._lattice.close()
+        self._lattice = self._make_lattice(words, elem_offset)
+        for mm in prog.monitors + prog.last_turns_monitors:
+            mm.allocate(self.device)
+        if prog.monitors or prog.last_turns_monitors:
+            self._lattice.set_inline_monitors(prog.monitors, prog.last_turns_monitors)
+        self.program = prog
+        self._config_key = key
+
+    def _make_lattice(self, words, elem_offset):
+        # the C-ABI handle; raises unless `self.device` is a CUDA device (no CPU fallback)
+        return _cabi.Lattice(words, elem_offset, self.line_length, self.device)
+
+    # -- monitor ------------------------------------------------------------
+    def _get_monitor(self, particles, turn_by_turn_monitor, num_turns):
+        if turn_by_turn_monitor is None or turn_by_turn_monitor is False:
+            return 0, None
+        if turn_by_turn_monitor is True:
+            monitor = ParticlesMonitor(
+                _device=particles.device, start_at_turn=0, stop_at_turn=num_turns,
+                particle_id_range=particles.get_active_particle_id_range())
+            return 1, monitor
+        if isinstance(turn_by_turn_monitor, str) and turn_by_turn_monitor == 'ONE_TURN_EBE':
+            _, monitor = self._get_monitor(particles, True, self.num_elements + 1)
+            monitor.ebe_mode = 1
+            return 2, monitor
+        if isinstance(turn_by_turn_monitor, ParticlesMonitor):
+            return (2 if turn_by_turn_monitor.ebe_mode == 1 else 1), turn_by_turn_monitor
+        raise ValueError('Please provide a valid monitor object')
+
+    # -- tracking -----------------------------------------------------------
+    def track(self, particles, ele_start=0, ele_stop=None, num_elements=None, num_turns=None,
+              turn_by_turn_monitor=None, freeze_longitudinal=False, time=False,
+              _force_no_end_turn_actions=False):
+        line = self.line
+        if particles.device != self.device:
+            raise ValueError(f'particles are on {particles.device}, tracker on {self.device}')
+        self._ensure_lattice()
+
+        # start position (tracker.py:1252-1266)
+        if particles.start_tracking_at_element >= 0:
+            if ele_start != 0:
+                raise ValueError('The argument ele_start is used, but '
+                                 'particles.start_tracking_at_element is set as well. '
+                                 'Please use only one of those methods.')
+            ele_start = particles.start_tracking_at_element
+            particles.start_tracking_at_element = -1
+        if isinstance(ele_start, str):
+            ele_start = line.element_names.index(ele_start)
+        if ele_start is None:
+            ele_start = 0
+        assert ele_start >= 0
+        assert ele_start <= self.num_elements
+
+        # turn splitting (tracker.py:1270-1333)
+        num_middle_turns = 0
+        num_elements_last_turn = 0
+        if num_elements is not None:
+            assert num_elements >= 0
+            if ele_stop is not None:
+                raise ValueError('Cannot use both num_elements and ele_stop!')
+            if num_turns is not None:
+                raise ValueError('Cannot use both num_elements and num_turns!')
+            if num_elements + ele_start <= self.num_elements:
+                num_elements_first_turn = num_elements
+            else:
+                num_elements_first_turn = self.num_elements - ele_start
+                num_middle_turns, ele_stop = divmod(ele_start + num_elements, self.num_elements)
+                num_elements_last_turn = ele_stop
+                num_middle_turns -= 1
+        else:
+            if num_turns is None:
+                num_turns = 1
+            else:
+                assert num_turns > 0
+            if ele_stop is None:
+                num_elements_first_turn = self.num_elements - ele_start
+                num_middle_turns = num_turns - 1
+            else:
+                if isinstance(ele_stop, str):
+                    ele_stop = line.element_names.index(ele_stop)
+                assert ele_stop >= 0
+                assert ele_stop <= self.num_elements
+                if ele_stop <= ele_start:
+                    num_turns += 1
+                if num_turns == 1:
+                    num_elements_first_turn = ele_stop - ele_start
+                else:
+                    num_elements_first_turn = self.num_elements - ele_start
+                    num_middle_turns = num_turns - 2
+                    num_elements_last_turn = ele_stop
+
+        if line.skip_end_turn_actions or _force_no_end_turn_actions:
+            flag_end_first_turn_actions = False
+            flag_end_middle_turn_actions = False
+        else:
+            flag_end_first_turn_actions = (
+                num_elements_first_turn + ele_start == self.num_elements)
+            flag_end_middle_turn_actions = True
+
+        if num_elements_last_turn > 0:
+            monitor_turns = num_middle_turns + 2
+        else:
+            monitor_turns = num_middle_turns + 1
+
+        flag_monitor, monitor = self._get_monitor(particles, turn_by_turn_monitor, monitor_turns)
+        if monitor is not None:
+            monitor.allocate(self.device)
+
+        if line._needs_rng and not particles._has_valid_rng_state():
+            particles._init_random_number_generator()
+
+        variant = 0
+        if self.exact_arithmetic:
+            variant |= _cabi.VARIANT_EXACT
+        if not line.config.get('XTRACK_MULTIPOLE_NO_SYNRAD', True):
+            variant |= _cabi.VARIANT_SYNRAD
+        if freeze_longitudinal:
+            variant |= _cabi.VARIANT_FREEZE_LONG
+        common = dict(flag_reset_s_at_end_turn=line.reset_s_at_end_turn,
+                      flag_monitor=flag_monitor, monitor=monitor,
+                      track_flags=line.get_flags_register(),
+                      global_xy_limit=float(line.config.get('XTRACK_GLOBAL_XY_LIMIT', 1.0)),
+                      variant_flags=variant)
+
+        if time:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(self.device))
+
+        # first turn (tracker.py:1372-1390)
+        assert num_elements_first_turn >= 0
+        self._lattice.track(particles, num_turns=1, ele_start=ele_start,
+                            num_ele_track=num_elements_first_turn,
+                            flag_end_turn_actions=flag_end_first_turn_actions, **common)
+        # middle turns (:1393-1413)
+        if num_middle_turns > 0:
+            assert self.num_elements > 0
+            self._track_middle(particles, num_middle_turns, flag_end_middle_turn_actions, common)
+        # last, incomplete turn (:1416-1436)
+        if num_elements_last_turn > 0:
+            self._lattice.track(particles, num_turns=1, ele_start=0,
+                                num_ele_track=num_elements_last_turn,
+                                flag_end_turn_actions=False, **common)
+
+        if time:
+            ev1.record(torch.cuda.current_stream(self.device))
+            ev1.synchronize()
+            line.time_last_track = ev0.elapsed_time(ev1) * 1e-3
+        else:
+            line.time_last_track = None
+        line.record_last_track = monitor
+        self.record_last_track = monitor
+
+    def _track_middle(self, particles, num_turns, flag_end_turn_actions, common):
+        """Full turns.  With `compact_every=N` the turns are issued in chunks of N
+        and the surviving particles are compacted into dense warps between chunks
+        (GPU stream compaction in place of the CPU contexts' reorganize,
+        particles.py:1198-1259); the original slot order is restored at the end."""
+        nn = self.compact_every
+        if not nn or nn >= num_turns:
+            self._lattice.track(particles, num_turns=num_turns, ele_start=0,
+                                num_ele_track=self.num_elements,
+                                flag_end_turn_actions=flag_end_turn_actions, **common)
+            return
+        perm_total = None
+        done = 0
+        while done < num_turns:
+            chunk = min(nn, num_turns - done)
+            self._lattice.track(particles, num_turns=chunk, ele_start=0,
+                                num_ele_track=self.num_elements,
+                                flag_end_turn_actions=flag_end_turn_actions, **common)
+            done += chunk
+            if done < num_turns:
+                perm, n_active, _ = _cabi.compact(particles)
+                perm_total = perm if perm_total is None else perm_total[perm]
+                if n_active == 0:
+                    break
+        if perm_total is not None:
+            inv = torch.empty_like(perm_total)
+            inv[perm_total] = torch.arange(len(perm_total), device=perm_total.device)
+            for nn_, tt in particles._fields.items():
+                tt.copy_(tt[inv])
