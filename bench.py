@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- particle-element-turns/s of the fused tracking kernel.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (for N > 1 under torchrun,
+one rank per GPU) prints ONE JSON line from rank 0.
+
+Workload (BASELINE.json configs[1]): HL-LHC thin-lattice dynamic-aperture tracking --
+the `hllhc_14` stand-in of the missing hllhc15 fixture (11 843 elements, beam-beam
+elements replaced by markers), 10^6 particles per GPU on a polar grid in (x, y),
+FP64.  A "step" is one pass of the hot path over that batch: `--turns` turns of all
+particles (the 10^5-turn production run is this step repeated; the state never leaves
+the GPU between steps).  Particles shard over the GPUs with no per-turn communication
+(weak scaling: 10^6 per GPU); the only collective is the final all-reduce of the loss /
+beam statistics (NCCL), outside the hot loop but inside the timed region.
+
+  value      PET/s with the particle SoA resident in HBM (device-timed, CUDA events)
+  e2e        the same through the public API `Line.track` with HOST buffers: pinned
+             host -> device copy of the SoA, track, device -> host copy of the result
+  roofline   bound = fp64 (FP64 FMA pipe; there is no contraction and ~0 HBM traffic
+             per element-turn): achieved = algorithmic flop/PET x PET/s, peak = DFMA
+             chain measured in this run by `xtb_measure_dfma_peak` (MEASURED_PEAKS.json
+             has no FP64 figure)
+  cpu_baseline  the reference's own C physics (oracle/_ref, OpenMP, all host cores) on a
+             bounded sample of the same workload
+`--impl reference` times that CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for pp in (ROOT, os.path.join(ROOT, 'tests')):
+    if pp not in sys.path:
+        sys.path.insert(0, pp)
+
+WORKLOADS = {
+    # name: (fixture, description)
+    'hllhc_da': ('hllhc_14', 'HL-LHC thin DA (hllhc_14 stand-in, BB->Marker), polar grid'),
+    'sps_apertures': ('sps', 'SPS thin lattice with LimitRect/LimitEllipse, Gaussian beam'),
+    'lep_thick': ('lep', 'LEP thick lattice (RBend/Quadrupole/Sextupole), Gaussian beam'),
+}
+
+
+def load_line(fixture):
+    import gzip
+    import xtrack_b200 as xb
+    with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'lattices', fixture + '.json.gz'),
+                   'rt') as fid:
+        dd = json.load(fid)
+    line = xb.Line.from_dict(dd, replace_unsupported=True)
+    if line.particle_ref is None and 'particle' in dd:
+        line.particle_ref = xb.Particles.from_dict(dd['particle'])
+    return line
+
+
+def initial_conditions(workload, line, n, rank):
+    """Synthetic initial conditions as numpy arrays (seeded; each rank its own shard)."""
+    if workload == 'hllhc_da':
+        # polar grid r in (0, 2 mm], theta in [0, pi/2], delta = 2.7e-4
+        # (cf. examples/dynamic_aperture/000_tracking_for_da.py:15-31 of the reference)
+        nr = int(round(np.sqrt(n)))
+        nt = (n + nr - 1) // nr
+        r = np.linspace(0, 2e-3, nr + 1)[1:]
+        th = np.linspace(0, np.pi / 2, nt) + 1e-4 * rank
+        rr, tt = np.meshgrid(r, th, indexing='ij')
+        x = (rr * np.cos(tt)).ravel()[:n]
+        y = (rr * np.sin(tt)).ravel()[:n]
+        return dict(x=x, y=y, delta=np.full(n, 2.7e-4))
+    rng = np.random.default_rng(100 + rank)
+    if workload == 'sps_apertures':
+        sig = dict(x=4e-3, px=1e-4, y=2e-3, py=1e-4, zeta=0.2, delta=1e-3)
+    else:
+        sig = dict(x=2e-4, px=2e-6, y=5e-5, py=1e-6, zeta=5e-3, delta=3e-4)
+    return {kk: rng.normal(0, vv, n) for kk, vv in sig.items()}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                      '-i', str(self.index)], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                ff = [f.strip() for f in out.split(',')]
+                self.samples.append(float(ff[0]))
+                self.max_mhz = float(ff[1])
+                for nn, vv in zip(names, ff[2:]):
+                    if vv.lower().startswith('active'):
+                        self.reasons.add(nn)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+def pet_done(at_turn0, at_turn1, at_element1, state1, n_elements):
+    """Particle-element-turns actually traversed (lost particles stop counting)."""
+    dturn = (at_turn1 - at_turn0).astype(np.float64)
+    return float(np.sum(dturn * n_elements + np.where(state1 > 0, 0, at_element1)))
+
+
+def cpu_reference_run(workload, line, n_particles, target_seconds, warm=True):
+    """Times the reference's own CPU implementation (its C headers compiled through the
+    oracle shim, OpenMP, all host cores) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_oracle as ro
+    import xtrack_b200 as xb
+    ref = line.particle_ref
+    ic = initial_conditions(workload, line, n_particles, 0)
+    p = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0, **ic)
+    re = ro.RefElements(line.elements)
+    cores = ro.load('omp').xt_ref_num_threads()
+    kw = dict(ele_start=0, num_ele_track=len(line), flag_end_turn_actions=1,
+              flag_reset_s_at_end_turn=1, line_length=line.get_length(), variant='omp')
+    hp = ro.HostParticles.from_particles(p)
+    t0 = time.perf_counter()
+    ro.track_line(hp, re, num_turns=1, **kw)          # warm-up turn, also calibrates
+    t_turn = time.perf_counter() - t0
+    turns = max(2, int(target_seconds / max(t_turn, 1e-6)))
+    hp = ro.HostParticles.from_particles(p)
+    t0 = time.perf_counter()
+    ro.track_line(hp, re, num_turns=turns, **kw)
+    dt = time.perf_counter() - t0
+    pet = pet_done(np.zeros(n_particles), hp.arrays['at_turn'], hp.arrays['at_element'],
+                   hp.arrays['state'], len(line))
+    return {'value': pet / dt, 'unit': 'particle-element-turns/s', 'cores': int(cores),
+            'kind': 'reference',
+            'sample': f'{n_particles} particles x {turns} turns of the same lattice '
+                      f'({dt:.1f} s; reference C headers via oracle/_ref, OpenMP)'}, dt, turns
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='hllhc_da', choices=sorted(WORKLOADS))
+    ap.add_argument('--particles', type=int, default=1_000_000, help='per GPU')
+    ap.add_argument('--turns', type=int, default=20, help='turns per step')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exact', action='store_true', help='EXACT kernel variant (no FMA contraction)')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    fixture, descr = WORKLOADS[args.workload]
+    config = {'workload': f'{args.workload}: {descr}; {args.particles} particles/GPU x '
+                          f'{args.turns} turns/step', 'fixture': fixture,
+              'particles_per_gpu': args.particles, 'turns_per_step': args.turns,
+              'l2_policy': 'particle SoA (240 B/particle) larger than L2; program streamed per turn',
+              'parallelism': f'particles sharded over {world} GPU(s), no per-turn communication'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        line = load_line(fixture)
+        config['n_elements'] = len(line)
+        vals = []
+        for ii in range(args.warmup + args.steps):
+            res, dt, turns = cpu_reference_run(args.workload, line, 20000,
+                                               max(2.0, args.cpu_seconds / max(1, args.steps)))
+            if ii >= args.warmup:
+                vals.append((res, dt))
+        value = float(np.mean([r['value'] for r, _ in vals]))
+        res = dict(vals[-1][0])
+        res['value'] = value
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'particle-element-turns/s', 'value': value,
+            'unit': 'particle-element-turns/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean([d for _, d in vals])),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': config, 'cpu_baseline': res,
+            'e2e': {'value': value, 'unit': 'particle-element-turns/s',
+                    'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import xtrack_b200 as xb
+    from xtrack_b200 import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    line = load_line(fixture)
+    n_el = len(line)
+    config['n_elements'] = n_el
+    ref = line.particle_ref
+    n = args.particles
+    ic = initial_conditions(args.workload, line, n, rank)
+    p_host = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0, **ic)
+    tracker = line.build_tracker(_device=dev, exact_arithmetic=args.exact)
+    flop_per_turn = tracker.program.flops          # algorithmic flop per particle-turn
+    config['flop_per_pet'] = flop_per_turn / n_el
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def final_reduction(p):
+        stats = _cabi.reduce_stats(p)               # per-GPU partial sums (K5)
+        if world > 1:
+            dist.all_reduce(stats)                  # NCCL: 29 doubles, end of run only
+        return stats
+
+    # ---- resident-in-HBM measurement ("value") -----------------------------------------
+    p = p_host.copy(_device=dev)
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(args.warmup):
+        line.track(p, num_turns=args.turns)
+    barrier()
+    launches0 = _cabi.launch_count()
+    at_turn0 = p.get('at_turn').copy()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    ev0.record(stream)
+    for ii in range(args.steps):
+        kev[ii][0].record(stream)
+        line.track(p, num_turns=args.turns)
+        kev[ii][1].record(stream)
+    stats = final_reduction(p)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    launches = _cabi.launch_count() - launches0
+    pet = pet_done(at_turn0, p.get('at_turn'), p.get('at_element'), p.get('state'), n_el)
+    tt = torch.tensor([ms_total, pet, float(np.sum(kernel_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, pet_all, kms = float(mx[0]), float(sm[1]), float(mx[2])
+    else:
+        ms_total, pet_all, kms = float(tt[0]), float(tt[1]), float(tt[2])
+    value = pet_all / (ms_total * 1e-3)
+    n_alive, n_lost = int(stats[0]), int(stats[1])
+
+    # ---- end-to-end through the public API with host buffers ("e2e") -------------------
+    names = [nn for nn, _ in xb.Particles.per_particle_vars]
+    pinned_in = {nn: p_host._fields[nn].clone().pin_memory() for nn in names}
+    pinned_out = {nn: torch.empty_like(pinned_in[nn]).pin_memory() for nn in names}
+    bytes_io = sum(t.numel() * t.element_size() for t in pinned_in.values())
+    p_dev = p_host.copy(_device=dev)
+
+    def e2e_step():
+        for nn in names:                             # H2D of this step's inputs
+            p_dev._fields[nn].copy_(pinned_in[nn], non_blocking=True)
+        line.track(p_dev, num_turns=args.turns)      # the call a user makes
+        for nn in names:                             # D2H of the result
+            pinned_out[nn].copy_(p_dev._fields[nn], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(2, args.steps // 2)
+    e0.record(stream)
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    pet_e2e = pet_done(np.zeros(n), pinned_out['at_turn'].numpy(), pinned_out['at_element'].numpy(),
+                       pinned_out['state'].numpy(), n_el) * n_e2e
+    te = torch.tensor([e2e_ms, pet_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = te.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = te.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_ms, pet_e2e = float(mx[0]), float(sm[1])
+    e2e_value = pet_e2e / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: FP64 FMA peak measured in this run ----------------------------------
+    peak_sustained, peak_burst = _cabi.measure_dfma_peak(local_rank, 2.0)
+    pet_rank0 = pet
+    achieved = (pet_rank0 / n_el) * flop_per_turn / (float(np.sum(kernel_ms)) * 1e-3)
+    roofline = {
+        'bound': 'fp64', 'achieved': achieved / 1e12, 'peak': peak_sustained / 1e12,
+        'unit': 'TFLOP/s', 'frac': achieved / peak_sustained, 'traffic': None,
+        'peak_source': 'measured in this run: register-resident DFMA chains on all SMs '
+                       '(xtb_measure_dfma_peak, sustained); burst %.2f TFLOP/s; '
+                       'MEASURED_PEAKS.json holds no FP64 figure' % (peak_burst / 1e12),
+        'algorithmic_flop_per_pet': flop_per_turn / n_el,
+        'kernel': 'xtb_track_kernel', 'kernel_ms_per_step': float(np.mean(kernel_ms)),
+        'hbm_algorithmic_bytes_per_step': 2 * 240 * n,
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu, _, _ = cpu_reference_run(args.workload, line, 20000, args.cpu_seconds)
+        except Exception as err:      # the oracle library did not travel / build
+            cpu = {'value': None, 'unit': 'particle-element-turns/s', 'cores': os.cpu_count(),
+                   'kind': 'reference', 'sample': f'unavailable: {err}'}
+
+    print(json.dumps({
+        'metric': 'particle-element-turns/s', 'value': value,
+        'unit': 'particle-element-turns/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': config, 'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'particle-element-turns/s',
+                'h2d_bytes_per_step': bytes_io, 'd2h_bytes_per_step': bytes_io},
+        'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+        'kernel_variant': 'exact' if args.exact else 'fma',
+        'beam': {'n_alive': n_alive, 'n_lost': n_lost}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,112 @@
+"""Shared helpers of the test-suite (fixtures, oracle driver, comparisons)."""
+import os
+
+import numpy as np
+
+import xtrack_b200 as xb
+import ref_oracle as ro
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LATTICES = os.path.join(HERE, 'golden', 'lattices')
+
+COORDS = ('x', 'px', 'y', 'py', 'zeta', 'delta')
+ALL_F64 = ('x', 'px', 'y', 'py', 'zeta', 'delta', 's', 'ptau', 'rpp', 'rvv')
+INT_FIELDS = ('state', 'at_turn', 'at_element', 'particle_id')
+
+# beam sizes used for the synthetic Gaussian beams
+SIGMAS = {
+    'hllhc_14': dict(x=2e-4, px=3e-6, y=2e-4, py=3e-6, zeta=5e-2, delta=1e-4),
+    'sps': dict(x=2e-3, px=5e-5, y=1e-3, py=3e-5, zeta=0.2, delta=1e-3),
+    'lep': dict(x=2e-4, px=2e-6, y=5e-5, py=1e-6, zeta=5e-3, delta=3e-4),
+    'clic_dr': dict(x=1e-4, px=2e-5, y=2e-5, py=4e-6, zeta=2e-3, delta=1e-3),
+    'toy': dict(x=1e-3, px=1e-4, y=1e-3, py=1e-4, zeta=5e-2, delta=1e-4),
+}
+
+
+def load_fixture(name):
+    import gzip
+    import json
+    with gzip.open(os.path.join(LATTICES, name + '.json.gz'), 'rt') as fid:
+        return json.load(fid)
+
+
+def load_line(name, **kwargs):
+    dd = load_fixture(name)
+    line = xb.Line.from_dict(dd, replace_unsupported=True, **kwargs)
+    if line.particle_ref is None and 'particle' in dd:
+        line.particle_ref = xb.Particles.from_dict(dd['particle'])
+    return line
+
+
+def gaussian_particles(line, n, seed, sig, device='cpu', capacity=None, scale=1.0, **extra):
+    rng = np.random.default_rng(seed)
+    ref = line.particle_ref
+    kw = {kk: rng.normal(0, sig[kk] * scale, n) for kk in COORDS}
+    kw.update(extra)
+    return xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0,
+                        _device=device, _capacity=capacity, **kw)
+
+
+def toy_ring(thin=False):
+    """The 16-element ring of the reference's examples/toy_ring/000_toy_ring.py:13-36
+    (4 FODO-like cells: quadrupoles, 1 m drifts, sector bends of pi/2... scaled so
+    that the ring closes), or a thin variant with multipoles and one cavity."""
+    import math
+    n_bends = 4
+    if not thin:
+        els, names = [], []
+        for ii in range(4):
+            els += [xb.Quadrupole(length=0.3, k1=0.1 if ii % 2 == 0 else -0.7),
+                    xb.Drift(length=1.0),
+                    xb.Bend(length=3.0, angle=2 * math.pi / n_bends, k0='from_h', model='full',
+                            edge_entry_active=0, edge_exit_active=0),
+                    xb.Drift(length=1.0)]
+        line = xb.Line(elements=els)
+    else:
+        els = []
+        for ii in range(8):
+            els += [xb.Drift(length=1.0),
+                    xb.Multipole(knl=[0, 0.3 if ii % 2 == 0 else -0.3]),
+                    xb.Drift(length=1.0),
+                    xb.Multipole(knl=[2 * math.pi / 8], hxl=2 * math.pi / 8, length=0.5)]
+        els.append(xb.Cavity(voltage=1e5, frequency=1e7, lag=180.))
+        line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=1.2e9, mass0=xb.PROTON_MASS_EV)
+    return line
+
+
+def oracle_track(line, particles, num_turns, *, ele_start=0, num_ele_track=None,
+                 flag_end_turn_actions=True, monitor=None, flag_monitor=0, variant='serial',
+                 track_flags=0):
+    """Runs the reference-header oracle on a copy of `particles`; returns the fields
+    ordered by particle_id."""
+    hp = ro.HostParticles.from_particles(particles)
+    re = ro.RefElements(line.elements)
+    ro.track_line(hp, re, num_turns=num_turns, ele_start=ele_start,
+                  num_ele_track=len(line) if num_ele_track is None else num_ele_track,
+                  flag_end_turn_actions=flag_end_turn_actions,
+                  flag_reset_s_at_end_turn=line.reset_s_at_end_turn, line_length=line.get_length(),
+                  global_xy_limit=line.config['XTRACK_GLOBAL_XY_LIMIT'], monitor=monitor,
+                  flag_monitor=flag_monitor, variant=variant, track_flags=track_flags)
+    return hp.sorted_by_id()
+
+
+def by_id(particles):
+    """Fields of an xb.Particles ordered by particle_id (allocated slots only)."""
+    st = particles.get('state')
+    alloc = np.where(st > xb.LAST_INVALID_STATE)[0]
+    order = alloc[np.argsort(particles.get('particle_id')[alloc], kind='stable')]
+    return {nn: particles.get(nn)[order] for nn, _ in xb.Particles.per_particle_vars}
+
+
+def max_rel_dev(got, ref, fields=COORDS, mask=None):
+    """max over particles of |got-ref| / scale, scale = max(|ref|) of that coordinate over
+    the beam (the "1e-12 relative" of BASELINE.json is read against the beam size)."""
+    out = {}
+    for ff in fields:
+        a, b = got[ff], ref[ff]
+        if mask is not None:
+            a, b = a[mask], b[mask]
+        scale = np.max(np.abs(b)) if len(b) and np.max(np.abs(b)) > 0 else 1.0
+        out[ff] = float(np.max(np.abs(a - b)) / scale) if len(b) else 0.0
+    return out

@@ -1,0 +1,199 @@
+"""CPU tier: the lattice lowering (xtrack_b200/lowering.py) and the device op
+semantics, exercised through the HOST build of the device headers
+(tests/hostsim -- test infrastructure, never used by the product) against the
+reference-header oracle.  The host build rounds like the EXACT kernel variant and
+links the same libm as the oracle, so the expected result is bit-identity.
+The real CUDA kernel is covered by tests/test_gpu_parity.py (-m gpu).
+"""
+import numpy as np
+import pytest
+
+import xtrack_b200 as xb
+import common
+import hostsim
+
+
+def _track(line, p_host, num_turns, **kw):
+    p = p_host.copy()
+    hostsim.build_hostsim_tracker(line)
+    line.track(p, num_turns=num_turns, **kw)
+    return p
+
+
+def _assert_identical(got, ref, fields=common.ALL_F64 + ('state', 'at_turn', 'at_element')):
+    for ff in fields:
+        assert np.array_equal(got[ff], ref[ff]), ff
+
+
+@pytest.mark.parametrize('name', ['hllhc_14', 'sps', 'clic_dr', 'lep'])
+def test_ten_turns_bit_identical(name):
+    line = common.load_line(name)
+    p_host = common.gaussian_particles(line, 60, 11, common.SIGMAS[name])
+    ref = common.oracle_track(line, p_host, 10 if name != 'lep' else 4)
+    got = common.by_id(_track(line, p_host, 10 if name != 'lep' else 4))
+    _assert_identical(got, ref)
+
+
+def test_ducktrack_golden_full_rings():
+    """The reference's own pin of this path (tests/test_full_rings.py:24-118): 10 turns of
+    the fixture particle vs ducktrack, tolerances of the reference test."""
+    import json
+    import os
+    with open(os.path.join(common.HERE, 'golden', 'ducktrack_full_rings.json')) as fid:
+        golden = json.load(fid)
+    for name in ('hllhc_14', 'sps'):
+        dd = common.load_fixture(name)
+        line = xb.Line.from_dict(dd, replace_unsupported=True)
+        line.reset_s_at_end_turn = False
+        p = xb.Particles.from_dict(dd['particle'])
+        got = common.by_id(_track(line, p, 10))
+        gg = golden[name]
+        for ff in ('x', 'px', 'y', 'py', 'zeta', 'delta', 's'):
+            np.testing.assert_allclose(got[ff][0], gg[ff], rtol=gg['rtol'], atol=gg['atol'],
+                                       err_msg=f'{name} {ff}')
+
+
+@pytest.mark.parametrize('thin', [True, False])
+def test_toy_ring(thin):
+    line = common.toy_ring(thin=thin)
+    p_host = common.gaussian_particles(line, 200, 1, common.SIGMAS['toy'])
+    ref = common.oracle_track(line, p_host, 20)
+    _assert_identical(common.by_id(_track(line, p_host, 20)), ref)
+
+
+def test_losses_sps_apertures():
+    line = common.load_line('sps')
+    p_host = common.gaussian_particles(line, 400, 3, common.SIGMAS['sps'], scale=6.0)
+    ref = common.oracle_track(line, p_host, 5)
+    assert 5 < (ref['state'] <= 0).sum() < 395
+    _assert_identical(common.by_id(_track(line, p_host, 5)), ref)
+
+
+def test_global_limit_and_partial_turns():
+    line = common.load_line('hllhc_14')
+    line.config['XTRACK_GLOBAL_XY_LIMIT'] = 2e-3
+    p_host = common.gaussian_particles(line, 300, 5, common.SIGMAS['hllhc_14'], scale=3.0)
+    ref = common.oracle_track(line, p_host, 2)
+    assert (ref['state'] == -1).sum() > 3
+    _assert_identical(common.by_id(_track(line, p_host, 2)), ref)
+
+    line.config['XTRACK_GLOBAL_XY_LIMIT'] = 1.0
+    p_host = common.gaussian_particles(line, 50, 6, common.SIGMAS['hllhc_14'])
+    p = p_host.copy()
+    hostsim.build_hostsim_tracker(line)
+    line.track(p, ele_start=5000, num_elements=len(line) + 300)
+    hp = common.ro.HostParticles.from_particles(p_host)
+    re = common.ro.RefElements(line.elements)
+    kw = dict(flag_reset_s_at_end_turn=1, line_length=line.get_length())
+    common.ro.track_line(hp, re, num_turns=1, ele_start=5000, num_ele_track=len(line) - 5000,
+                         flag_end_turn_actions=1, **kw)
+    common.ro.track_line(hp, re, num_turns=1, ele_start=0, num_ele_track=5300,
+                         flag_end_turn_actions=0, **kw)
+    _assert_identical(common.by_id(p), hp.sorted_by_id())
+
+
+def test_turn_by_turn_monitor():
+    line = common.load_line('sps')
+    p_host = common.gaussian_particles(line, 40, 8, common.SIGMAS['sps'], scale=5.0)
+    mon_ref = common.ro.HostMonitor(0, 4, 0, 40)
+    common.oracle_track(line, p_host, 4, monitor=mon_ref, flag_monitor=1)
+    p = p_host.copy()
+    hostsim.build_hostsim_tracker(line)
+    line.track(p, num_turns=4, turn_by_turn_monitor=True)
+    mon = line.record_last_track
+    assert mon.x.shape == (40, 4)
+    for ff, _ in xb.Particles.per_particle_vars:
+        assert np.array_equal(mon.get(ff), mon_ref.field(ff)), ff
+
+
+def test_misaligned_elements():
+    """Shifts / tilts on thin and thick, straight and curved elements
+    (track_misalignments.h through the transformations wrapper)."""
+    mis = dict(shift_x=1e-3, shift_y=-2e-3, shift_s=5e-3, rot_s_rad=0.02, rot_x_rad=1e-3,
+               rot_y_rad=-2e-3, rot_s_rad_no_frame=0.01, rot_shift_anchor=0.2)
+    els = [xb.Multipole(knl=[0, 0.1, 2.0], ksl=[0, 0.05], **mis),
+           xb.Drift(length=1.0),
+           xb.Quadrupole(length=0.5, k1=0.3, **mis),
+           xb.LimitRect(min_x=-0.05, max_x=0.05, min_y=-0.05, max_y=0.05, shift_x=0.01),
+           xb.Bend(length=1.5, angle=0.1, k0='from_h', edge_entry_angle=0.02, edge_exit_angle=0.03,
+                   edge_entry_fint=0.5, edge_entry_hgap=0.02, **mis),
+           xb.Sextupole(length=0.3, k2=5., rot_s_rad=0.3),
+           xb.Cavity(voltage=1e5, frequency=4e8, lag=30., shift_x=2e-3, rot_s_rad=0.1),
+           xb.LimitEllipse(a=0.05, b=0.03, rot_s_rad=0.2, shift_y=1e-3),
+           xb.RBend(length_straight=1.2, angle=0.08, k0='from_h', rbend_model='straight-body', **mis),
+           xb.DipoleEdge(k=0.05, e1=0.03, hgap=0.02, fint=0.4, shift_x=1e-3)]
+    line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=2e9)
+    p_host = common.gaussian_particles(line, 100, 2, common.SIGMAS['toy'])
+    ref = common.oracle_track(line, p_host, 1)
+    _assert_identical(common.by_id(_track(line, p_host, 1)), ref)
+
+
+@pytest.mark.parametrize('model', ['adaptive', 'full', 'bend-kick-bend', 'rot-kick-rot',
+                                   'mat-kick-mat', 'drift-kick-drift-exact',
+                                   'drift-kick-drift-expanded', 'rot-kick-rot-low-order',
+                                   'rot-kick-rot-high-order'])
+@pytest.mark.parametrize('integrator', ['adaptive', 'teapot', 'yoshida4', 'uniform'])
+def test_bend_models_and_integrators(model, integrator):
+    """All body models x integrators of track_magnet.h on a combined-function bend with
+    full edges, and on a straight quadrupole-like magnet where the model exists."""
+    els = [xb.Bend(length=2.0, angle=0.15, k0=0.08, k1=0.02, k2=0.5, knl=[0, 0, 0.1, 2.0],
+                   ksl=[0, 1e-3], model=model, integrator=integrator, num_multipole_kicks=5,
+                   edge_entry_model='full', edge_exit_model='full', edge_entry_angle=0.03,
+                   edge_exit_angle=0.04, edge_entry_fint=0.5, edge_exit_fint=0.4,
+                   edge_entry_hgap=0.02, edge_exit_hgap=0.02),
+           xb.Bend(length=1.0, angle=0.0, k0=0.0, k1=0.1, model=model, integrator=integrator,
+                   num_multipole_kicks=3, edge_entry_model='dipole-only',
+                   edge_exit_model='suppressed')]
+    if model not in ('bend-kick-bend', 'rot-kick-rot'):
+        els.append(xb.Quadrupole(length=0.7, k1=0.2, k1s=0.01, model=model, integrator=integrator,
+                                 num_multipole_kicks=4, edge_entry_active=1, edge_exit_active=1))
+    line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=3e9)
+    p_host = common.gaussian_particles(line, 50, 4, common.SIGMAS['toy'])
+    ref = common.oracle_track(line, p_host, 1)
+    _assert_identical(common.by_id(_track(line, p_host, 1)), ref)
+
+
+def test_rbend_models():
+    els = []
+    for rm in ('adaptive', 'curved-body', 'straight-body'):
+        for diff in (0.0, 0.01):
+            els.append(xb.RBend(length_straight=1.5, angle=0.12, k0='from_h', rbend_model=rm,
+                                rbend_angle_diff=diff, k1=0.05, edge_entry_model='full',
+                                edge_exit_model='linear', edge_entry_fint=0.5, edge_entry_hgap=0.02,
+                                rbend_shift=1e-3))
+            els.append(xb.Drift(length=0.2))
+    line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=3e9)
+    p_host = common.gaussian_particles(line, 50, 4, common.SIGMAS['toy'])
+    ref = common.oracle_track(line, p_host, 1)
+    _assert_identical(common.by_id(_track(line, p_host, 1)), ref)
+
+
+def test_polygon_drift_exact_rfmultipole_thick_multipole():
+    els = [xb.LimitPolygon(x_vertices=[-0.03, 0.03, 0.04, 0.0, -0.04],
+                           y_vertices=[-0.02, -0.02, 0.02, 0.035, 0.02]),
+           xb.DriftExact(length=2.0), xb.Drift(length=1.0, model='exact'),
+           xb.RFMultipole(voltage=1e4, frequency=4e8, lag=10., knl=[1e-3, 1e-2], ksl=[0, 2e-2],
+                          pn=[10., 20.], ps=[0., 30.]),
+           xb.Multipole(knl=[0.01, 0.2, 1.0], hxl=0.01, length=0.4, isthick=True,
+                        num_multipole_kicks=3),
+           xb.SRotation(angle=20.), xb.XYShift(dx=1e-3, dy=-1e-3),
+           xb.Octupole(length=0.3, k3=100., k3s=20.)]
+    line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=3e9)
+    p_host = common.gaussian_particles(line, 300, 4, common.SIGMAS['toy'], scale=20.)
+    ref = common.oracle_track(line, p_host, 1)
+    assert 10 < (ref['state'] == 0).sum() < 290
+    _assert_identical(common.by_id(_track(line, p_host, 1)), ref)
+
+
+def test_freeze_longitudinal():
+    line = common.load_line('sps')
+    p_host = common.gaussian_particles(line, 30, 9, common.SIGMAS['sps'])
+    p = _track(line, p_host, 2, freeze_longitudinal=True)
+    for ff in ('zeta', 'delta', 'ptau', 'rpp', 'rvv', 's'):
+        assert np.array_equal(p.get(ff), p_host.get(ff)), ff
+    assert np.all(p.get('at_turn') == 2)
+    assert not np.array_equal(p.get('x'), p_host.get('x'))

@@ -112,8 +112,13 @@ class Line:
 
     @classmethod
     def from_json(cls, path, **kwargs):
-        with open(path) as fid:
-            dct = json.load(fid)
+        if str(path).endswith('.gz'):
+            import gzip
+            with gzip.open(path, 'rt') as fid:
+                dct = json.load(fid)
+        else:
+            with open(path) as fid:
+                dct = json.load(fid)
         if 'line' in dct and 'elements' not in dct:
             dct = dct['line']
         return cls.from_dict(dct, **kwargs)

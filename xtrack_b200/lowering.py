@@ -160,7 +160,7 @@ class _RawWord:
 # ---------------------------------------------------------------------------
 # helpers restating element-constant arithmetic of the reference
 # ---------------------------------------------------------------------------
-def _horner_coeffs(knl, ksl, order, inv_factorial_order, factor):
+def _horner_coeffs(knl, ksl, order, inv_factorial_order, factor, trim=True):
     """Scaled coefficients in Horner order (highest first), as pairs.
     track_magnet_kick.h:183-228: `chi * knl[index] * factor * inv_factorial`
     with `inv_factorial *= index` going down (chi is applied on the device).
@@ -179,7 +179,7 @@ def _horner_coeffs(knl, ksl, order, inv_factorial_order, factor):
         cn[index] = (float(knl[index]) * factor) * inv_factorial
         cs[index] = (float(ksl[index]) * factor) * inv_factorial
     top = order
-    while top > 0 and cn[top] == 0.0 and cs[top] == 0.0:
+    while trim and top > 0 and cn[top] == 0.0 and cs[top] == 0.0:
         top -= 1
     out = []
     for ii in range(top, -1, -1):
@@ -594,7 +594,7 @@ def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl,
         kmain_s = [k0s, k1s, k2s, k3s]
         knl_main = [v * core_length for v in kmain_n]
         ksl_main = [v * core_length for v in kmain_s]
-        coeffs_main = _horner_coeffs(knl_main, ksl_main, 3, 1. / (3 * 2), 1.0)
+        coeffs_main = _horner_coeffs(knl_main, ksl_main, 3, 1. / (3 * 2), 1.0, trim=False)
 
         # curvature terms of track_magnet_kick.h:98-142 (element constants)
         htot = c['h_kick']
