@@ -89,14 +89,14 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits',
                                       '-i', str(self.index)], capture_output=True, text=True,
@@ -109,10 +109,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nn)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
                 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
@@ -166,7 +166,8 @@ def main():
     ap.add_argument('--turns', type=int, default=20, help='turns per step')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--exact', action='store_true', help='EXACT kernel variant (no FMA contraction)')
+    ap.add_argument('--fma', action='store_true',
+                    help='FMA-contracted kernel variant (default: exact, reference rounding)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -222,7 +223,7 @@ def main():
     n = args.particles
     ic = initial_conditions(args.workload, line, n, rank)
     p_host = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0, **ic)
-    tracker = line.build_tracker(_device=dev, exact_arithmetic=args.exact)
+    tracker = line.build_tracker(_device=dev, exact_arithmetic=not args.fma)
     flop_per_turn = tracker.program.flops          # algorithmic flop per particle-turn
     config['flop_per_pet'] = flop_per_turn / n_el
 
@@ -313,6 +314,20 @@ def main():
         e2e_ms, pet_e2e = float(mx[0]), float(sm[1])
     e2e_value = pet_e2e / (e2e_ms * 1e-3)
 
+    # ---- the other kernel variant, for information (2 steps, rank-local) ---------------
+    tracker.exact_arithmetic = bool(args.fma)
+    p_alt = p_host.copy(_device=dev)
+    line.track(p_alt, num_turns=args.turns)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a0.record(stream)
+    for _ in range(2):
+        line.track(p_alt, num_turns=args.turns)
+    a1.record(stream)
+    barrier()
+    alt_ms = a0.elapsed_time(a1) / 2
+    tracker.exact_arithmetic = not args.fma
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -350,7 +365,11 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'particle-element-turns/s',
                 'h2d_bytes_per_step': bytes_io, 'd2h_bytes_per_step': bytes_io},
         'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
-        'kernel_variant': 'exact' if args.exact else 'fma',
+        'kernel_variant': 'fma' if args.fma else 'exact',
+        'other_variant': {'name': 'exact' if args.fma else 'fma', 'ms_per_step_1gpu': alt_ms,
+                          'value_1gpu': n * args.turns * n_el / (alt_ms * 1e-3),
+                          'frac_of_fp64_peak': (n * args.turns * flop_per_turn / (alt_ms * 1e-3))
+                          / peak_sustained},
         'beam': {'n_alive': n_alive, 'n_lost': n_lost}}))
     if world > 1:
         dist.destroy_process_group()

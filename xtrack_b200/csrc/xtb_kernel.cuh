@@ -173,7 +173,9 @@ __device__ __noinline__ void rare_op(const uint32_t op, const int32_t aux,
     }
 }
 
-template <bool HEAVY, bool SYNRAD, bool FRZ>
+// EXACT only distinguishes the symbols of the two builds of this translation unit
+// (template instantiations are COMDAT: identical names would be merged at link time).
+template <bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT>
 __global__ void __launch_bounds__(XTB_THREADS, HEAVY ? 1 : 3)
 xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     __shared__ __align__(128) uint64_t tile[XTB_NUM_BUF][XTB_TILE_WORDS];

@@ -14,7 +14,7 @@
 
 template <bool HEAVY, bool SYNRAD, bool FRZ>
 static cudaError_t launch(const XtbTrackArgs& a, unsigned grid, cudaStream_t stream) {
-    xtb_track_kernel<HEAVY, SYNRAD, FRZ><<<grid, XTB_THREADS, 0, stream>>>(a);
+    xtb_track_kernel<HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0)><<<grid, XTB_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
