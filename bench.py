@@ -166,6 +166,8 @@ def main():
     ap.add_argument('--turns', type=int, default=20, help='turns per step')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true',
+                    help='tuning runs: skip the e2e and other-variant legs')
     ap.add_argument('--fma', action='store_true',
                     help='FMA-contracted kernel variant (default: exact, reference rounding)')
     args = ap.parse_args()
@@ -277,6 +279,22 @@ def main():
         ms_total, pet_all, kms = float(tt[0]), float(tt[1]), float(tt[2])
     value = pet_all / (ms_total * 1e-3)
     n_alive, n_lost = int(stats[0]), int(stats[1])
+
+    if args.quick:
+        peak_sustained, peak_burst = _cabi.measure_dfma_peak(local_rank, 0.5)
+        achieved = (pet / n_el) * flop_per_turn / (float(np.sum(kernel_ms)) * 1e-3)
+        if rank == 0:
+            print(json.dumps({'metric': 'particle-element-turns/s', 'value': value, 'quick': True,
+                              'ms_per_step': ms_total / args.steps, 'config': config,
+                              'clocks': clocks, 'gpu_launches': int(launches),
+                              'kernel_variant': 'fma' if args.fma else 'exact',
+                              'roofline': {'bound': 'fp64', 'achieved': achieved / 1e12,
+                                           'peak': peak_sustained / 1e12,
+                                           'frac': achieved / peak_sustained,
+                                           'kernel_ms_per_step': float(np.mean(kernel_ms))}}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end-to-end through the public API with host buffers ("e2e") -------------------
     names = [nn for nn, _ in xb.Particles.per_particle_vars]

@@ -45,6 +45,7 @@ extern "C" {
 #define XTB_VARIANT_EXACT        1u   /* no FMA contraction: arithmetic in the reference's order */
 #define XTB_VARIANT_SYNRAD       2u   /* reference built WITHOUT XTRACK_MULTIPOLE_NO_SYNRAD      */
 #define XTB_VARIANT_FREEZE_LONG  4u   /* FREEZE_VAR_{zeta,delta,ptau,rpp,rvv,s} (line.py:4446)   */
+#define XTB_VARIANT_PLAIN_PROGRAM 8u  /* force the unfused program (diagnostics / tests)         */
 
 /* track flags: bit positions of xtrack/track_flags.py:5-12 */
 #define XTB_FLAG_BACKTRACK              0
@@ -89,11 +90,15 @@ typedef struct xtb_stats {
 
 typedef struct xtb_lattice* xtb_lattice_handle;
 
-/* Upload a lowered lattice ("program") to `device`.  `words` is the op stream
- * (8-byte words, format in xtrack_b200/csrc/xtb_ops.h), `elem_offset[n_elements+1]`
- * the word offset of each element's first op.  Immutable afterwards. */
-int xtb_lattice_create(const uint64_t* words, size_t n_words,
-                       const uint32_t* elem_offset, size_t n_elements,
+/* Upload a lowered lattice to `device`: two op streams ("programs", 8-byte words, format
+ * in xtrack_b200/csrc/xtb_ops.h) of the same line -- FUSED (drift-prefixed fast ops; may
+ * be NULL) and PLAIN (one element = its own ops).  `*_elem_offset[n_elements+1]` is the
+ * word offset of each element's first op; in the fused program an element absorbed in
+ * the op of its predecessor carries 0xffffffff.  Immutable afterwards. */
+int xtb_lattice_create(const uint64_t* fused_words, size_t n_fused_words,
+                       const uint32_t* fused_elem_offset,
+                       const uint64_t* plain_words, size_t n_plain_words,
+                       const uint32_t* plain_elem_offset, size_t n_elements,
                        double line_length, int device, xtb_lattice_handle* out);
 int xtb_lattice_destroy(xtb_lattice_handle h);
 

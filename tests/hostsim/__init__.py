@@ -33,19 +33,29 @@ def load():
             subprocess.run(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared',
                             os.path.join(HERE, 'xtb_hostsim.cpp'), '-o', LIB, '-lm'], check=True)
         _lib = ct.CDLL(LIB)
-        _lib.xtb_hostsim_track.restype = None
+        _lib.xtb_hostsim_track.restype = ct.c_int
         _lib.xtb_hostsim_track.argtypes = [
             ct.c_void_p, ct.c_void_p, ct.POINTER(_cabi.XtbParticles), ct.c_int64, ct.c_int32,
             ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.POINTER(_cabi.XtbMonitor),
-            ct.c_uint64, ct.c_double, ct.c_uint32, ct.c_double, ct.c_void_p, ct.c_void_p]
+            ct.c_uint64, ct.c_double, ct.c_uint32, ct.c_double, ct.c_void_p, ct.c_void_p,
+            ct.c_int32]
     return _lib
 
 
 class HostSimLattice:
-    def __init__(self, words, elem_offset, line_length):
-        self.words = np.ascontiguousarray(words, dtype=np.uint64)
-        self.elem_offset = np.ascontiguousarray(elem_offset, dtype=np.uint32)
+    """Mirrors the program selection of `xtb_track` (csrc/xtb_api.cu): the FUSED program
+    when the element range falls on its op boundaries, else the PLAIN one."""
+    npt = 2          # particle slots carried together, as in the thin CUDA kernels
+
+    def __init__(self, fused, plain, line_length):
+        self.plain = (np.ascontiguousarray(plain[0], dtype=np.uint64),
+                      np.ascontiguousarray(plain[1], dtype=np.uint32))
+        self.fused = None
+        if fused is not None and fused[0] is not None:
+            self.fused = (np.ascontiguousarray(fused[0], dtype=np.uint64),
+                          np.ascontiguousarray(fused[1], dtype=np.uint32))
         self.line_length = float(line_length)
+        self.programs_used = []
         self._mons = None
         self._ltms = None
 
@@ -60,13 +70,22 @@ class HostSimLattice:
               global_xy_limit=1.0, variant_flags=0, stream=None):
         pst = _cabi.particles_struct(particles)
         mst = ct.byref(_cabi.monitor_struct(monitor)) if monitor is not None else None
-        load().xtb_hostsim_track(
-            self.words.ctypes.data, self.elem_offset.ctypes.data, ct.byref(pst), int(num_turns),
+        na = 0xffffffff
+        prog = self.plain
+        if (self.fused is not None and flag_monitor != 2
+                and not (variant_flags & _cabi.VARIANT_PLAIN_PROGRAM)
+                and self.fused[1][ele_start] != na
+                and self.fused[1][ele_start + num_ele_track] != na):
+            prog = self.fused
+        self.programs_used.append('fused' if prog is self.fused else 'plain')
+        rc = load().xtb_hostsim_track(
+            prog[0].ctypes.data, prog[1].ctypes.data, ct.byref(pst), int(num_turns),
             int(ele_start), int(num_ele_track), int(bool(flag_end_turn_actions)),
             int(bool(flag_reset_s_at_end_turn)), int(flag_monitor), mst, int(track_flags),
             float(global_xy_limit), int(variant_flags), self.line_length,
             ct.cast(self._mons, ct.c_void_p) if self._mons is not None else None,
-            ct.cast(self._ltms, ct.c_void_p) if self._ltms is not None else None)
+            ct.cast(self._ltms, ct.c_void_p) if self._ltms is not None else None, self.npt)
+        assert rc == 0
 
     def close(self):
         pass
@@ -78,8 +97,8 @@ class HostSimTracker(Tracker):
     def __init__(self, line, device=None, **kwargs):
         super().__init__(line, device='cpu', **kwargs)
 
-    def _make_lattice(self, words, elem_offset):
-        return HostSimLattice(words, elem_offset, self.line_length)
+    def _make_lattice(self, fused, plain):
+        return HostSimLattice(fused, plain, self.line_length)
 
 
 def build_hostsim_tracker(line):

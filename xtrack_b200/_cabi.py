@@ -17,6 +17,7 @@ NUM_FIELDS = 32
 VARIANT_EXACT = 1
 VARIANT_SYNRAD = 2
 VARIANT_FREEZE_LONG = 4
+VARIANT_PLAIN_PROGRAM = 8
 
 
 class XtbParticles(ct.Structure):
@@ -57,17 +58,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if _build.needs_build():
+    # an existing library is used as it is (it was built by `__graft_entry__.build()` /
+    # `python -m xtrack_b200.build`; file times do not survive the copy to a GPU box)
+    if not os.path.exists(_build.LIB):
         try:
             _build.build()
-        except Exception as err:       # no nvcc on this box: use the shipped .so if any
-            if not os.path.exists(_build.LIB):
-                raise XtbError(f'libxtb200.so is missing and could not be built: {err}')
+        except Exception as err:
+            raise XtbError(f'libxtb200.so is missing and could not be built: {err}')
     lib = ct.CDLL(_build.LIB)
     lib.xtb_last_error_string.restype = ct.c_char_p
     lib.xtb_version.restype = ct.c_char_p
     lib.xtb_launch_count.restype = ct.c_int64
-    lib.xtb_lattice_create.argtypes = [ct.c_void_p, ct.c_size_t, ct.c_void_p, ct.c_size_t,
+    lib.xtb_lattice_create.argtypes = [ct.c_void_p, ct.c_size_t, ct.c_void_p,
+                                       ct.c_void_p, ct.c_size_t, ct.c_void_p, ct.c_size_t,
                                        ct.c_double, ct.c_int, ct.POINTER(ct.c_void_p)]
     lib.xtb_lattice_destroy.argtypes = [ct.c_void_p]
     lib.xtb_lattice_set_inline_monitors.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_size_t,
@@ -137,14 +140,22 @@ def last_turns_struct(mon):
 class Lattice:
     """Handle of a lowered lattice resident on one GPU."""
 
-    def __init__(self, words, elem_offset, line_length, device):
+    def __init__(self, fused, plain, line_length, device):
+        """`fused`, `plain`: (words, elem_offset) of the two programs of the line
+        (lowering.Program.finish); `fused` may be (None, None)."""
         self.device_index = _require_cuda(device)
         lib = load()
-        words = np.ascontiguousarray(words, dtype=np.uint64)
-        elem_offset = np.ascontiguousarray(elem_offset, dtype=np.uint32)
-        self.n_elements = len(elem_offset) - 1
+        pw = np.ascontiguousarray(plain[0], dtype=np.uint64)
+        po = np.ascontiguousarray(plain[1], dtype=np.uint32)
+        self.n_elements = len(po) - 1
+        if fused is not None and fused[0] is not None:
+            fw = np.ascontiguousarray(fused[0], dtype=np.uint64)
+            fo = np.ascontiguousarray(fused[1], dtype=np.uint32)
+            fargs = (fw.ctypes.data, len(fw), fo.ctypes.data)
+        else:
+            fargs = (None, 0, None)
         hh = ct.c_void_p()
-        _check(lib.xtb_lattice_create(words.ctypes.data, len(words), elem_offset.ctypes.data,
+        _check(lib.xtb_lattice_create(*fargs, pw.ctypes.data, len(pw), po.ctypes.data,
                                       self.n_elements, float(line_length), self.device_index,
                                       ct.byref(hh)))
         self.handle = hh

@@ -12,12 +12,16 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(HERE, 'libxtb200.so')
-OBJ = os.path.join(HERE, 'csrc', '_build')
+# Tuning experiments: XTB_LIB_SUFFIX=_x XTB_EXTRA_DEFINES="-DXTB_NPT_THIN=1" builds
+# libxtb200_x.so beside the product library; XTB_LIB_SUFFIX alone selects it at load time.
+SUFFIX = os.environ.get('XTB_LIB_SUFFIX', '')
+EXTRA = os.environ.get('XTB_EXTRA_DEFINES', '').split()
+LIB = os.path.join(HERE, f'libxtb200{SUFFIX}.so')
+OBJ = os.path.join(HERE, 'csrc', '_build' + SUFFIX)
 
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 HEAVY = ['-DXTB_WITH_HEAVY']
-COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', *HEAVY]
+COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', *HEAVY, *EXTRA]
 
 
 def _nvcc():

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -13,8 +14,8 @@
 #include "xtb_ops.h"
 #include "xtb_state.cuh"
 
-extern "C" cudaError_t xtb_launch_track_fast(unsigned, const XtbTrackArgs*, unsigned, cudaStream_t);
-extern "C" cudaError_t xtb_launch_track_exact(unsigned, const XtbTrackArgs*, unsigned, cudaStream_t);
+extern "C" cudaError_t xtb_launch_track_fast(unsigned, const XtbTrackArgs*, cudaStream_t);
+extern "C" cudaError_t xtb_launch_track_exact(unsigned, const XtbTrackArgs*, cudaStream_t);
 
 #define XTB_THREADS 256
 
@@ -34,90 +35,115 @@ static int fail(int code, const char* fmt, const char* detail = "") {
         }                                                                       \
     } while (0)
 
+// One lowered program resident on the device (see xtb_ops.h: FUSED and PLAIN).
+struct xtb_program {
+    size_t n_words = 0, n_tiles = 0;
+    bool has_heavy = false;
+    uint64_t* d_prog = nullptr;
+    uint32_t* d_tile_off = nullptr;
+    std::vector<uint32_t> elem_offset;   // host copy [n_elements + 1], XTB_NOT_ADDRESSABLE allowed
+    std::vector<uint32_t> tile_off;      // host copy [n_tiles + 1]
+};
+
 struct xtb_lattice {
     int device;
-    size_t n_words, n_elements, n_tiles;
+    size_t n_elements;
     double line_length;
-    bool has_heavy;
-    uint64_t* d_prog;
-    uint32_t* d_tile_off;
-    std::vector<uint32_t> elem_offset;   // host copy [n_elements + 1]
-    std::vector<uint32_t> tile_off;      // host copy [n_tiles + 1]
-    std::vector<uint32_t> tile_of_elem;  // tile index holding each element's first op
+    xtb_program fused, plain;
     xtb_monitor_t* d_mon;
     xtb_last_turns_monitor_t* d_ltm;
 };
 
 extern "C" const char* xtb_last_error_string(void) { return g_err; }
-extern "C" const char* xtb_version(void) { return "xtb200 0.1 (sm_100a)"; }
+extern "C" const char* xtb_version(void) { return "xtb200 0.2 (sm_100a)"; }
 extern "C" int64_t xtb_launch_count(void) { return g_launches.load(); }
 
-extern "C" int xtb_lattice_create(const uint64_t* words, size_t n_words,
-                                  const uint32_t* elem_offset, size_t n_elements,
-                                  double line_length, int device, xtb_lattice_handle* out) {
-    if (!out || (!words && n_words) || !elem_offset) return fail(XTB_E_INVALID, "null argument");
+// Validates the op stream and cuts it into tiles at addressable element boundaries.
+static int program_prepare(xtb_program& G, const uint64_t* words, size_t n_words,
+                           const uint32_t* elem_offset, size_t n_elements) {
     if (elem_offset[0] != 0 || elem_offset[n_elements] != n_words)
         return fail(XTB_E_INVALID, "elem_offset does not span the program");
-    xtb_lattice* L = new (std::nothrow) xtb_lattice();
-    if (!L) return fail(XTB_E_NOMEM, "out of host memory");
-    L->device = device;
-    L->n_words = n_words;
-    L->n_elements = n_elements;
-    L->line_length = line_length;
-    L->has_heavy = false;
-    L->d_prog = nullptr;
-    L->d_tile_off = nullptr;
-    L->d_mon = nullptr;
-    L->d_ltm = nullptr;
-    L->elem_offset.assign(elem_offset, elem_offset + n_elements + 1);
-
-    // validate the op stream and cut it into tiles at element boundaries
-    L->tile_off.push_back(0);
-    L->tile_of_elem.resize(n_elements + 1);
-    for (size_t e = 0; e < n_elements; ++e) {
-        const uint32_t w0 = elem_offset[e], w1 = elem_offset[e + 1];
-        if (w1 < w0 || w1 > n_words || (w0 & 1u)) {
-            delete L;
-            return fail(XTB_E_INVALID, "bad element offsets");
-        }
-        if (w1 - w0 > XTB_TILE_WORDS) {
-            delete L;
-            return fail(XTB_E_INVALID, "element larger than a program tile");
-        }
+    G.n_words = n_words;
+    G.elem_offset.assign(elem_offset, elem_offset + n_elements + 1);
+    G.tile_off.push_back(0);
+    uint32_t w0 = 0;
+    for (size_t e = 1; e <= n_elements; ++e) {
+        const uint32_t w1 = elem_offset[e];
+        if (w1 == XTB_NOT_ADDRESSABLE) continue;     // absorbed in the op that starts at w0
+        if (w1 < w0 || w1 > n_words || (w0 & 1u)) return fail(XTB_E_INVALID, "bad element offsets");
+        if (w1 - w0 > XTB_TILE_WORDS) return fail(XTB_E_INVALID, "element larger than a program tile");
         uint32_t pc = w0;
         while (pc < w1) {
             const uint64_t h = words[pc];
             const uint32_t nw = (uint32_t) ((h >> 16) & 0xffffu);
             const uint32_t op = (uint32_t) (h & 0xffu);
-            if (nw == 0 || (nw & 1u) || pc + nw > w1) {
-                delete L;
-                return fail(XTB_E_INVALID, "malformed op in program");
-            }
-            if (op >= XTB_HEAVY_FIRST) L->has_heavy = true;
+            if (nw < 2 || (nw & 1u) || pc + nw > w1) return fail(XTB_E_INVALID, "malformed op in program");
+            if (op >= XTB_HEAVY_FIRST) G.has_heavy = true;
             pc += nw;
         }
-        if (w1 - L->tile_off.back() > XTB_TILE_WORDS) L->tile_off.push_back(w0);
-        L->tile_of_elem[e] = (uint32_t) (L->tile_off.size() - 1);
+        if (w1 - G.tile_off.back() > XTB_TILE_WORDS) G.tile_off.push_back(w0);
+        w0 = w1;
     }
-    L->tile_of_elem[n_elements] = (uint32_t) (L->tile_off.size() - 1);
-    L->tile_off.push_back((uint32_t) n_words);
-    L->n_tiles = L->tile_off.size() - 1;
+    G.tile_off.push_back((uint32_t) n_words);
+    G.n_tiles = G.tile_off.size() - 1;
+    return XTB_OK;
+}
 
+static cudaError_t program_upload(xtb_program& G, const uint64_t* words) {
+    cudaError_t e = cudaMalloc(&G.d_prog, (G.n_words + 2) * sizeof(uint64_t));
+    if (e == cudaSuccess && G.n_words)
+        e = cudaMemcpy(G.d_prog, words, G.n_words * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&G.d_tile_off, G.tile_off.size() * sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(G.d_tile_off, G.tile_off.data(), G.tile_off.size() * sizeof(uint32_t),
+                       cudaMemcpyHostToDevice);
+    return e;
+}
+
+static void program_free(xtb_program& G) {
+    if (G.d_prog) cudaFree(G.d_prog);
+    if (G.d_tile_off) cudaFree(G.d_tile_off);
+    G.d_prog = nullptr;
+    G.d_tile_off = nullptr;
+}
+
+extern "C" int xtb_lattice_create(const uint64_t* fused_words, size_t n_fused_words,
+                                  const uint32_t* fused_elem_offset,
+                                  const uint64_t* plain_words, size_t n_plain_words,
+                                  const uint32_t* plain_elem_offset, size_t n_elements,
+                                  double line_length, int device, xtb_lattice_handle* out) {
+    if (!out || (!plain_words && n_plain_words) || !plain_elem_offset)
+        return fail(XTB_E_INVALID, "null argument");
+    if (fused_words && !fused_elem_offset) return fail(XTB_E_INVALID, "null argument");
+    xtb_lattice* L = new (std::nothrow) xtb_lattice();
+    if (!L) return fail(XTB_E_NOMEM, "out of host memory");
+    L->device = device;
+    L->n_elements = n_elements;
+    L->line_length = line_length;
+    L->d_mon = nullptr;
+    L->d_ltm = nullptr;
+    int rc = program_prepare(L->plain, plain_words, n_plain_words, plain_elem_offset, n_elements);
+    if (rc == XTB_OK) {
+        for (size_t e = 0; e <= n_elements; ++e)
+            if (plain_elem_offset[e] == XTB_NOT_ADDRESSABLE)
+                rc = fail(XTB_E_INVALID, "every element of the plain program must be addressable");
+    }
+    if (rc == XTB_OK && fused_words)
+        rc = program_prepare(L->fused, fused_words, n_fused_words, fused_elem_offset, n_elements);
+    if (rc != XTB_OK) {
+        delete L;
+        return rc;
+    }
     int prev = 0;
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&L->d_prog, (n_words + 2) * sizeof(uint64_t));
-    if (e == cudaSuccess && n_words)
-        e = cudaMemcpy(L->d_prog, words, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&L->d_tile_off, L->tile_off.size() * sizeof(uint32_t));
-    if (e == cudaSuccess)
-        e = cudaMemcpy(L->d_tile_off, L->tile_off.data(), L->tile_off.size() * sizeof(uint32_t),
-                       cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = program_upload(L->plain, plain_words);
+    if (e == cudaSuccess && fused_words) e = program_upload(L->fused, fused_words);
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "lattice upload: %s", cudaGetErrorString(e));
-        if (L->d_prog) cudaFree(L->d_prog);
-        if (L->d_tile_off) cudaFree(L->d_tile_off);
+        program_free(L->plain);
+        program_free(L->fused);
         delete L;
         return XTB_E_CUDA;
     }
@@ -130,8 +156,8 @@ extern "C" int xtb_lattice_destroy(xtb_lattice_handle L) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(L->device);
-    if (L->d_prog) cudaFree(L->d_prog);
-    if (L->d_tile_off) cudaFree(L->d_tile_off);
+    program_free(L->plain);
+    program_free(L->fused);
     if (L->d_mon) cudaFree(L->d_mon);
     if (L->d_ltm) cudaFree(L->d_ltm);
     cudaSetDevice(prev);
@@ -182,19 +208,34 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
         if (!particles->field[f]) return fail(XTB_E_INVALID, "null particle field pointer");
     if (num_turns == 0) return XTB_OK;
 
+    // the fused program serves every launch whose element range falls on its op boundaries;
+    // the element-by-element monitor needs the per-element hooks of the plain program
+    const xtb_program* G = &L->plain;
+    if (L->fused.d_prog && flag_monitor != 2 && !(variant_flags & XTB_VARIANT_PLAIN_PROGRAM)
+        && L->fused.elem_offset[ele_start] != XTB_NOT_ADDRESSABLE
+        && L->fused.elem_offset[ele_start + num_ele_track] != XTB_NOT_ADDRESSABLE)
+        G = &L->fused;
+
     XtbTrackArgs a;
     memset(&a, 0, sizeof(a));
-    a.prog = L->d_prog;
-    a.tile_off = L->d_tile_off;
+    a.prog = G->d_prog;
+    a.tile_off = G->d_tile_off;
     a.inline_mon = L->d_mon;
     a.inline_ltm = L->d_ltm;
     a.part = *particles;
     if (tbt_monitor) a.mon = *tbt_monitor;
-    a.pc_start = L->elem_offset[ele_start];
-    a.pc_stop = L->elem_offset[ele_start + num_ele_track];
-    a.tile_first = (int32_t) L->tile_of_elem[ele_start];
-    a.tile_last = num_ele_track > 0 ? (int32_t) L->tile_of_elem[ele_start + num_ele_track - 1]
-                                    : a.tile_first;
+    a.pc_start = G->elem_offset[ele_start];
+    a.pc_stop = G->elem_offset[ele_start + num_ele_track];
+    {   // tiles covering [pc_start, pc_stop)
+        const std::vector<uint32_t>& t = G->tile_off;
+        auto tile_of = [&](uint32_t w) {
+            size_t k = (size_t) (std::upper_bound(t.begin(), t.end(), w) - t.begin());
+            k = k ? k - 1 : 0;
+            return (int32_t) std::min(k, G->n_tiles ? G->n_tiles - 1 : 0);
+        };
+        a.tile_first = tile_of(a.pc_start);
+        a.tile_last = a.pc_stop > a.pc_start ? tile_of(a.pc_stop - 1) : a.tile_first;
+    }
     a.num_turns = (int32_t) num_turns;
     a.flag_end_turn_actions = flag_end_turn_actions;
     a.flag_reset_s = flag_reset_s_at_end_turn;
@@ -206,17 +247,16 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     a.global_xy_limit = global_xy_limit;
 
     unsigned variant = 0;
-    if (L->has_heavy || (variant_flags & XTB_VARIANT_SYNRAD)) variant |= 1u;
+    if (G->has_heavy || (variant_flags & XTB_VARIANT_SYNRAD)) variant |= 1u;
     if (variant_flags & XTB_VARIANT_SYNRAD) variant |= 2u;
     if (variant_flags & XTB_VARIANT_FREEZE_LONG) variant |= 4u;
 
     int prev = 0;
     cudaGetDevice(&prev);
     if (prev != L->device) CUDA_TRY(cudaSetDevice(L->device));
-    const unsigned grid = (unsigned) ((particles->capacity + XTB_THREADS - 1) / XTB_THREADS);
     cudaError_t e = (variant_flags & XTB_VARIANT_EXACT)
-                        ? xtb_launch_track_exact(variant, &a, grid, (cudaStream_t) cuda_stream)
-                        : xtb_launch_track_fast(variant, &a, grid, (cudaStream_t) cuda_stream);
+                        ? xtb_launch_track_exact(variant, &a, (cudaStream_t) cuda_stream)
+                        : xtb_launch_track_fast(variant, &a, (cudaStream_t) cuda_stream);
     if (prev != L->device) cudaSetDevice(prev);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "track kernel launch: %s", cudaGetErrorString(e));

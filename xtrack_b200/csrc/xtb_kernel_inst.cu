@@ -12,23 +12,34 @@
 #define XTB_LAUNCH_NAME xtb_launch_track_fast
 #endif
 
+// particle slots per thread: 2 in the thin kernels, 1 in the (register-hungry) thick ones
+#ifndef XTB_NPT_THIN
+#define XTB_NPT_THIN 2
+#endif
+#ifndef XTB_NPT_HEAVY
+#define XTB_NPT_HEAVY 1
+#endif
+
 template <bool HEAVY, bool SYNRAD, bool FRZ>
-static cudaError_t launch(const XtbTrackArgs& a, unsigned grid, cudaStream_t stream) {
-    xtb_track_kernel<HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0)><<<grid, XTB_THREADS, 0, stream>>>(a);
+static cudaError_t launch(const XtbTrackArgs& a, cudaStream_t stream) {
+    constexpr int NPT = HEAVY ? XTB_NPT_HEAVY : XTB_NPT_THIN;
+    const int64_t per_block = (int64_t) XTB_THREADS * NPT;
+    const unsigned grid = (unsigned) ((a.part.capacity + per_block - 1) / per_block);
+    xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0)><<<grid, XTB_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 // variant bits: 1 = heavy ops present, 2 = synrad, 4 = freeze longitudinal
-extern "C" cudaError_t XTB_LAUNCH_NAME(unsigned variant, const XtbTrackArgs* a, unsigned grid,
+extern "C" cudaError_t XTB_LAUNCH_NAME(unsigned variant, const XtbTrackArgs* a,
                                        cudaStream_t stream) {
     switch (variant & 7u) {
-    case 0: return launch<false, false, false>(*a, grid, stream);
-    case 4: return launch<false, false, true>(*a, grid, stream);
+    case 0: return launch<false, false, false>(*a, stream);
+    case 4: return launch<false, false, true>(*a, stream);
 #ifdef XTB_WITH_HEAVY
-    case 1: return launch<true, false, false>(*a, grid, stream);
-    case 5: return launch<true, false, true>(*a, grid, stream);
-    case 2: case 3: return launch<true, true, false>(*a, grid, stream);
-    case 6: case 7: return launch<true, true, true>(*a, grid, stream);
+    case 1: return launch<true, false, false>(*a, stream);
+    case 5: return launch<true, false, true>(*a, stream);
+    case 2: case 3: return launch<true, true, false>(*a, stream);
+    case 6: case 7: return launch<true, true, true>(*a, stream);
 #endif
     default: return cudaErrorNotSupported;
     }

@@ -306,3 +306,44 @@ __device__ __forceinline__ void global_aperture_check(PState& P, const double li
     const bool inside = (P.x >= -lim) && (P.x <= lim) && (P.y >= -lim) && (P.y <= lim);
     if (P.state > 0 && !inside) P.state = -1;
 }
+
+// ---- order-specialised forms used by the fast opcodes (xtb_ops.h) ----------
+// Same arithmetic and operation order as horner_kick / mult_kick above, with the
+// coefficients already in registers (loaded once per op, shared by the particles
+// a thread carries) and the loop unrolled.
+template <int ORDER>
+__device__ __forceinline__ void mult_kick_c(PState& P, const double (&c)[2 * (ORDER + 1)]) {
+    const double x = P.x, y = P.y, chi = P.chi;
+    double dpx_mul = chi * c[0];
+    double dpy_mul = chi * c[1];
+#pragma unroll
+    for (int i = 1; i <= ORDER; ++i) {
+        const double zre = dpx_mul * x - dpy_mul * y;
+        const double zim = dpx_mul * y + dpy_mul * x;
+        dpx_mul = chi * c[2 * i] + zre;
+        dpy_mul = chi * c[2 * i + 1] + zim;
+    }
+    P.px += -dpx_mul;
+    P.py += dpy_mul;
+}
+
+// mult_kick_h with order 0 and no k1 term: q = [hl, B0], c = [cn_0, cs_0]
+template <bool FRZ>
+__device__ __forceinline__ void mult_kick_h0(PState& P, const double hl, const double b0,
+                                             const double cn0, const double cs0) {
+    const double x = P.x, chi = P.chi;
+    const double dpx_mul = chi * cn0;
+    const double dpy_mul = chi * cs0;
+    P.px += -dpx_mul;
+    P.py += dpy_mul;
+    double dpx = hl * (1. + P.delta);
+    const double dzeta = -P.rv0v * hl * x;
+    dpx += chi * b0 * x;
+    P.px += dpx;
+    if (!FRZ) P.zeta += dzeta;
+}
+
+// outside the global aperture?  (negation of the test in global_aperture_check, NaN -> outside)
+__device__ __forceinline__ bool outside_global(const PState& P, const double lim) {
+    return !((P.x >= -lim) && (P.x <= lim) && (P.y >= -lim) && (P.y <= lim));
+}

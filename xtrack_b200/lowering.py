@@ -27,34 +27,47 @@ import math
 import numpy as np
 
 # ---- opcodes / flags: mirror of csrc/xtb_ops.h ----------------------------
-F_START, F_END, F_GLOBAL = 0x01, 0x02, 0x04
+F_START, F_END, F_GLOBAL, F_DRIFT = 0x01, 0x02, 0x04, 0x08
 
-OP_NOP = 0
-OP_DRIFT = 1
-OP_DRIFT_EXACT = 2
-OP_MULT = 3
-OP_MULT_H = 4
-OP_CAVITY = 5
-OP_RFMULT = 6
-OP_EDGE_LIN = 7
-OP_SROT = 8
-OP_XYSHIFT = 9
-OP_SSHIFT = 10
-OP_YROT = 11
-OP_XROT = 12
-OP_LIMIT_RECT = 13
-OP_LIMIT_ELLIPSE = 14
-OP_LIMIT_POLYGON = 15
-OP_MONITOR = 16
-OP_LAST_TURNS = 17
-OP_KILL = 18
-OP_SET_STATE = 19
-OP_ADD_S_ZETA = 20
-OP_ADD_X = 21
-OP_MAGNET_BODY = 32
-OP_MAGNET_EDGE = 33
-OP_DIPEDGE_NL = 34
+# fast set (fused program only): one whole element per op
+FOP_NOP = 0
+FOP_MULT0 = 1          # .. FOP_MULT0 + order, order <= 3
+FOP_MULTH0 = 5
+FOP_EDGE = 6
+FOP_RECT = 7
+FOP_ELLIPSE = 8
+FOP_FDRIFT = 9
 
+# generic set
+OP_NOP = 32
+OP_DRIFT = 33
+OP_DRIFT_EXACT = 34
+OP_MULT = 35
+OP_MULT_H = 36
+OP_CAVITY = 37
+OP_RFMULT = 38
+OP_EDGE_LIN = 39
+OP_SROT = 40
+OP_XYSHIFT = 41
+OP_SSHIFT = 42
+OP_YROT = 43
+OP_XROT = 44
+OP_LIMIT_RECT = 45
+OP_LIMIT_ELLIPSE = 46
+OP_LIMIT_POLYGON = 47
+OP_MONITOR = 48
+OP_LAST_TURNS = 49
+OP_KILL = 50
+OP_SET_STATE = 51
+OP_ADD_S_ZETA = 52
+OP_ADD_X = 53
+# heavy set
+OP_MAGNET_BODY = 64
+OP_MAGNET_EDGE = 65
+OP_DIPEDGE_NL = 66
+HEAVY_FIRST = 64
+
+NOT_ADDRESSABLE = 0xffffffff
 TILE_WORDS = 1024
 
 ONE_OVER_FACT = [1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664,
@@ -94,12 +107,12 @@ FLOPS = {
 
 
 class Program:
-    """Accumulates ops; `finish()` returns the uint64 word array + element offsets."""
+    """Accumulates the ops of each element; `finish(fused)` returns the uint64 word
+    array + element offsets of the FUSED or the PLAIN program (csrc/xtb_ops.h)."""
 
     def __init__(self):
-        self.words = []
-        self.elem_offset = [0]
-        self._cur = []          # ops of the element being lowered: [op, flags, aux, params]
+        self.elements = []      # per element: (ops, static_thick); op = [opcode, aux, params]
+        self._cur = []
         self.flops = 0.0        # algorithmic flop per particle-turn (sum over elements)
         self.n_transc = 0.0
         self.op_hist = {}
@@ -108,46 +121,110 @@ class Program:
         self.last_turns_monitors = []
 
     def op(self, opcode, params=(), aux=0, flops=None, transc=0):
-        self._cur.append([int(opcode), 0, int(aux), [float(p) if not isinstance(p, _RawWord)
-                                                      else p for p in params]])
+        self._cur.append([int(opcode), int(aux), [float(p) if not isinstance(p, _RawWord)
+                                                   else p for p in params]])
         if flops is None:
             flops = FLOPS.get(opcode, 0)
         self.flops += flops
         self.n_transc += transc
         self.op_hist[opcode] = self.op_hist.get(opcode, 0) + 1
-        if opcode >= 32:
+        if opcode >= HEAVY_FIRST:
             self.has_heavy = True
 
     def end_element(self, static_thick):
         if not self._cur:
-            self._cur.append([OP_NOP, 0, 0, []])
+            self._cur.append([OP_NOP, 0, []])
             self.op_hist[OP_NOP] = self.op_hist.get(OP_NOP, 0) + 1
-        self._cur[0][1] |= F_START
-        self._cur[-1][1] |= F_END | (F_GLOBAL if static_thick else 0)
-        n_el_words = 0
-        for opcode, flags, aux, params in self._cur:
-            nw = 1 + len(params)
-            if nw & 1:
-                params = params + [0.0]
-                nw += 1
-            if nw > 0xffff:
-                raise ValueError('op too long')
-            hdr = opcode | (flags << 8) | (nw << 16) | ((aux & 0xffffffff) << 32)
-            self.words.append(np.uint64(hdr))
-            for pp in params:
-                if isinstance(pp, _RawWord):
-                    self.words.append(np.uint64(pp.value))
-                else:
-                    self.words.append(np.float64(pp).view(np.uint64))
-            n_el_words += nw
-        if n_el_words > TILE_WORDS:
-            raise ValueError(f'element lowers to {n_el_words} words > tile of {TILE_WORDS}')
+        self.elements.append((self._cur, bool(static_thick)))
         self._cur = []
-        self.elem_offset.append(len(self.words))
 
-    def finish(self):
-        words = np.array(self.words, dtype=np.uint64)
-        return words, np.array(self.elem_offset, dtype=np.uint32)
+    # -- emission -------------------------------------------------------------
+    @staticmethod
+    def _emit(words, opcode, flags, aux, params, prefix_length=None):
+        params = list(params)
+        if len(params) & 1:
+            params.append(0.0)
+        nw = 2 + len(params)
+        if nw > TILE_WORDS:
+            raise ValueError(f'op of {nw} words > tile of {TILE_WORDS}')
+        if prefix_length is not None:
+            flags |= F_DRIFT
+        hdr = opcode | (flags << 8) | (nw << 16) | ((aux & 0xffffffff) << 32)
+        words.append(np.uint64(hdr))
+        words.append(np.float64(0.0 if prefix_length is None else prefix_length).view(np.uint64))
+        for pp in params:
+            if isinstance(pp, _RawWord):
+                words.append(np.uint64(pp.value))
+            else:
+                words.append(np.float64(pp).view(np.uint64))
+
+    @staticmethod
+    def _fast_form(ops, static_thick):
+        """(fast opcode, params) of a single-op element that has a fast equivalent."""
+        if len(ops) != 1 or static_thick:
+            return None
+        opcode, aux, params = ops[0]
+        if opcode == OP_NOP:
+            return FOP_NOP, []
+        if opcode == OP_MULT and aux <= 3:
+            return FOP_MULT0 + aux, params
+        if opcode == OP_MULT_H and (aux & 0xff) == 0 and not ((aux >> 8) & 1):
+            return FOP_MULTH0, [params[0], params[1], params[4], params[5]]
+        if opcode == OP_EDGE_LIN:
+            return FOP_EDGE, params[:2]
+        if opcode == OP_LIMIT_RECT:
+            return FOP_RECT, params[:4]
+        if opcode == OP_LIMIT_ELLIPSE:
+            return FOP_ELLIPSE, params[:3]
+        return None
+
+    def finish(self, fused=False):
+        words = []
+        offsets = []
+        if not fused:
+            for ops, static_thick in self.elements:
+                offsets.append(len(words))
+                for ii, (opcode, aux, params) in enumerate(ops):
+                    flags = (F_START if ii == 0 else 0)
+                    if ii == len(ops) - 1:
+                        flags |= F_END | (F_GLOBAL if static_thick else 0)
+                    self._emit(words, opcode, flags, aux, params)
+                if len(words) - offsets[-1] > TILE_WORDS:
+                    raise ValueError('element larger than a program tile')
+        else:
+            pending = None          # (length, element index) of a Drift waiting for its host op
+            for ie, (ops, static_thick) in enumerate(self.elements):
+                is_drift = (len(ops) == 1 and ops[0][0] == OP_DRIFT and static_thick)
+                if is_drift and pending is None:
+                    pending = (ops[0][2][0], ie)
+                    offsets.append(None)            # filled when the host op is emitted
+                    continue
+                start = len(words)
+                plen = None
+                if pending is not None:
+                    plen = pending[0]
+                    offsets[pending[1]] = start
+                    offsets.append(NOT_ADDRESSABLE)
+                    pending = None
+                else:
+                    offsets.append(start)
+                fast = (FOP_FDRIFT, [ops[0][2][0]]) if is_drift else self._fast_form(ops, static_thick)
+                if fast is not None:
+                    self._emit(words, fast[0], 0, 0, fast[1], prefix_length=plen)
+                else:
+                    for ii, (opcode, aux, params) in enumerate(ops):
+                        flags = (F_START if ii == 0 else 0)
+                        if ii == len(ops) - 1:
+                            flags |= F_END | (F_GLOBAL if static_thick else 0)
+                        self._emit(words, opcode, flags, aux, params,
+                                   prefix_length=plen if ii == 0 else None)
+                if len(words) - start > TILE_WORDS:
+                    raise ValueError('element larger than a program tile')
+            if pending is not None:
+                offsets[pending[1]] = len(words)
+                self._emit(words, FOP_FDRIFT, 0, 0, [pending[0]])
+        offsets.append(len(words))
+        return (np.array(words, dtype=np.uint64), np.array(offsets, dtype=np.uint32))
 
 
 class _RawWord:

@@ -18,7 +18,7 @@ from .monitors import ParticlesMonitor
 
 class Tracker:
 
-    def __init__(self, line, device=None, exact_arithmetic=True, compact_every=None):
+    def __init__(self, line, device=None, exact_arithmetic=True, compact_every=None, fuse=True):
         self.line = line
         if device is None:
             device = 'cuda'
@@ -31,6 +31,9 @@ class Tracker:
         # False: FMA-contracted build, ~1e-11 relative from the reference after 10 LHC turns.
         self.exact_arithmetic = bool(exact_arithmetic)
         self.compact_every = compact_every
+        # fuse=True: full-turn launches run the FUSED program (drift-prefixed fast ops,
+        # csrc/xtb_ops.h); False: everything runs the PLAIN one-element-per-op program
+        self.fuse = bool(fuse)
         self.num_elements = len(line.element_names)
         self._config_key = None
         self._lattice = None
@@ -50,11 +53,12 @@ class Tracker:
             return
         synrad, exact_drifts = key
         prog = lowering.lower_line(self.line.elements, synrad=synrad, exact_drifts=exact_drifts)
-        words, elem_offset = prog.finish()
+        fused = prog.finish(fused=True) if self.fuse else (None, None)
+        plain = prog.finish(fused=False)
         self.line_length = self.line.get_length()
         if self._lattice is not None:
             self._lattice.close()
-        self._lattice = self._make_lattice(words, elem_offset)
+        self._lattice = self._make_lattice(fused, plain)
         for mm in prog.monitors + prog.last_turns_monitors:
             mm.allocate(self.device)
         if prog.monitors or prog.last_turns_monitors:
@@ -62,9 +66,9 @@ class Tracker:
         self.program = prog
         self._config_key = key
 
-    def _make_lattice(self, words, elem_offset):
+    def _make_lattice(self, fused, plain):
         # the C-ABI handle; raises unless `self.device` is a CUDA device (no CPU fallback)
-        return _cabi.Lattice(words, elem_offset, self.line_length, self.device)
+        return _cabi.Lattice(fused, plain, self.line_length, self.device)
 
     # -- monitor ------------------------------------------------------------
     def _get_monitor(self, particles, turn_by_turn_monitor, num_turns):
