@@ -6,7 +6,7 @@ through the generated shim into shared libraries under `oracle/_ref/`
 
   libxt_ref_serial.so       -DXO_CONTEXT_CPU_SERIAL              bit reference
   libxt_ref_omp.so          -DXO_CONTEXT_CPU_OPENMP -fopenmp     timing baseline
-  libxt_ref_serial_frozen.so  + FREEZE_VAR_* (freeze_longitudinal, line.py:4446)
+  libxt_ref_noise.so        serial + +-1 ulp noise on libm results  libm-sensitivity yardstick
 
 Flags mirror xobjects' CPU context as far as it is known (`-O3`, no
 `-march=native`, no `-ffast-math`): baseline x86-64 has no FMA, so the
@@ -27,6 +27,9 @@ FROZEN_VARS = ('zeta', 'delta', 'ptau', 'rpp', 'rvv', 's')   # set by build()
 VARIANTS = {
     'serial': ['-DXO_CONTEXT_CPU_SERIAL', '-DXTRACK_MULTIPOLE_NO_SYNRAD'],
     'omp': ['-DXO_CONTEXT_CPU_OPENMP', '-fopenmp', '-DXTRACK_MULTIPOLE_NO_SYNRAD'],
+    # the clean serial build with +-1 ulp noise on every transcendental libm result
+    # (shim/xobjects/headers/ulp_noise.h): measures the reference's sensitivity to its libm
+    'noise': ['-DXO_CONTEXT_CPU_SERIAL', '-DXTRACK_MULTIPOLE_NO_SYNRAD', '-DXTB_ORACLE_ULP_NOISE'],
 }
 
 
@@ -52,7 +55,9 @@ def build(variants=None, force=False, verbose=False):
     built = []
     for vv in (variants or VARIANTS):
         out = lib_path(vv)
-        deps = [gen_h, os.path.join(HERE, 'track_line.c'), __file__]
+        deps = [gen_h, os.path.join(HERE, 'track_line.c'), __file__,
+                os.path.join(HERE, 'shim', 'xobjects', 'headers', 'common.h'),
+                os.path.join(HERE, 'shim', 'xobjects', 'headers', 'ulp_noise.h')]
         if (not force and os.path.exists(out)
                 and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps)):
             continue

@@ -14,6 +14,9 @@
 #include <stddef.h>
 #include <stdlib.h>
 #include <math.h>
+#ifdef XTB_ORACLE_ULP_NOISE
+#include "ulp_noise.h"      /* +-1 ulp on every transcendental result: sensitivity yardstick */
+#endif
 
 #define XO_CONTEXT_CPU
 #if !defined(XO_CONTEXT_CPU_SERIAL) && !defined(XO_CONTEXT_CPU_OPENMP)

@@ -38,7 +38,7 @@ def load():
             ct.c_void_p, ct.c_void_p, ct.POINTER(_cabi.XtbParticles), ct.c_int64, ct.c_int32,
             ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.POINTER(_cabi.XtbMonitor),
             ct.c_uint64, ct.c_double, ct.c_uint32, ct.c_double, ct.c_void_p, ct.c_void_p,
-            ct.c_int32]
+            ct.c_int32, ct.c_int32]
     return _lib
 
 
@@ -84,7 +84,7 @@ class HostSimLattice:
             int(bool(flag_reset_s_at_end_turn)), int(flag_monitor), mst, int(track_flags),
             float(global_xy_limit), int(variant_flags), self.line_length,
             ct.cast(self._mons, ct.c_void_p) if self._mons is not None else None,
-            ct.cast(self._ltms, ct.c_void_p) if self._ltms is not None else None, self.npt)
+            ct.cast(self._ltms, ct.c_void_p) if self._ltms is not None else None, self.npt, 0)
         assert rc == 0
 
     def close(self):

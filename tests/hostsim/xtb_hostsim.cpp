@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <cstring>
 #include <algorithm>
+#include <type_traits>
+#include <vector>
 
 #define __device__
 #define __host__
@@ -20,6 +22,8 @@
 static inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, 8); return r; }
 static inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 static inline int __double2hiint(double v) { long long r; std::memcpy(&r, &v, 8); return (int) (r >> 32); }
+#define __reduce_max_sync(m, v) (v)
+#define __any_sync(m, v) (v)
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 using std::max;
@@ -30,60 +34,59 @@ using std::min;
 
 // Serial restatement of the turn loop of xtb_kernel.cuh around the SHARED op
 // interpreter (xtb_interp.cuh); NPT slots are carried together as in the kernel.
-template <int NPT, bool SYNRAD, bool FRZ>
+// `a.prog` is the image of the element range: its ops + the XTB_OP_END sentinel.
+template <int NPT, bool SYNRAD, bool FRZ, class S>
 static void run(const XtbTrackArgs& a) {
     for (int64_t base = 0; base < a.part.capacity; base += NPT) {
-        PSlot G[NPT];
-        PState P[NPT];
-        bool live[NPT];
-        bool any_live = false;
+        XtbLanes<NPT, S> lanes;
+        PSlot (&G)[NPT] = lanes.G;
+        S (&P)[NPT] = lanes.P;
+        bool (&live)[NPT] = lanes.live;
+        bool any_live = false, chi_one = true;
         for (int k = 0; k < NPT; ++k) {
             G[k].p = &a.part;
             G[k].i = base + k;
-            live[k] = false;
-            if (base + k < a.part.capacity) {
-                P[k].state = (int32_t) G[k].ldi(F_STATE);
-                live[k] = P[k].state > 0;
-            }
+            live[k] = (base + k < a.part.capacity) && G[k].ldi(F_STATE) > 0;
             if (live[k]) {
                 pstate_load(P[k], G[k]);
+                P[k].state = 1;
+                chi_one = chi_one && (P[k].chi == 1.0);
             } else {
                 pstate_benign(P[k]);
-                P[k].at_turn = 0;
-                P[k].at_element = 0;
             }
             any_live = any_live || live[k];
         }
         if (!any_live) continue;
+        const bool chi1 = chi_one && std::is_same<S, PHot>::value;
+        XtbPass ps;
+        ps.turn_inc = 0;  ps.el_off = 0;  ps.el_reset = 0;
         for (int turn = 0; turn < a.num_turns; ++turn) {
             any_live = false;
             for (int k = 0; k < NPT; ++k) any_live = any_live || live[k];
             if (!any_live) break;
             if (a.flag_monitor == 1)
                 for (int k = 0; k < NPT; ++k)
-                    if (live[k]) monitor_record(a.mon, P[k], G[k]);
-            uint32_t eidx = 0;
-            xtb_interp<NPT, true, SYNRAD, FRZ>(a.prog + a.pc_start, a.prog + a.pc_stop, P, G, live,
-                                               eidx, a);
+                    if (live[k]) {
+                        const PState T = pstate_full(P[k], G[k], ps, 0u);
+                        monitor_record(a.mon, T, G[k]);
+                    }
+            lanes.eidx = 0;
+            if (chi1) xtb_run_tile<NPT, true, SYNRAD, FRZ, true>(a.prog, 0u, &lanes, ps, a);
+            else xtb_run_tile<NPT, true, SYNRAD, FRZ, false>(a.prog, 0u, &lanes, ps, a);
+            const uint32_t eidx = a.num_ele_track;
             if (a.flag_monitor == 2)
                 for (int k = 0; k < NPT; ++k)
                     if (live[k]) {
-                        PState T = P[k];
-                        T.at_element += (int32_t) eidx;
+                        const PState T = pstate_full(P[k], G[k], ps, eidx);
                         monitor_record(a.mon, T, G[k]);
                     }
-            for (int k = 0; k < NPT; ++k) {
-                if (a.flag_end_turn_actions > 0) {
-                    P[k].at_turn += 1;
-                    P[k].at_element = 0;
-                    if (a.flag_reset_s > 0 && !FRZ) P[k].s = 0.;
-                } else {
-                    P[k].at_element += (int32_t) eidx;
-                }
-            }
+            xtb_end_pass<NPT, FRZ>(P, ps, eidx, a);
         }
         for (int k = 0; k < NPT; ++k)
-            if (live[k]) pstate_store(P[k], G[k]);
+            if (live[k]) {
+                const PState T = pstate_full(P[k], G[k], ps, 0u);
+                pstate_store(T, G[k]);
+            }
     }
 }
 
@@ -93,17 +96,22 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
                                   int32_t flag_reset_s, int32_t flag_monitor, const xtb_monitor_t* mon,
                                   uint64_t track_flags, double global_xy_limit, uint32_t variant,
                                   double line_length, const xtb_monitor_t* inline_mon,
-                                  const xtb_last_turns_monitor_t* inline_ltm, int32_t npt) {
+                                  const xtb_last_turns_monitor_t* inline_ltm, int32_t npt, int32_t force_full) {
     XtbTrackArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.prog = words;
+    if (elem_offset[ele_start] == XTB_NOT_ADDRESSABLE
+        || elem_offset[ele_start + num_ele_track] == XTB_NOT_ADDRESSABLE) return -1;
+    // image of the element range: its ops, the END sentinel, slack for the prefetches
+    std::vector<uint64_t> image(words + elem_offset[ele_start],
+                                words + elem_offset[ele_start + num_ele_track]);
+    image.push_back(XTB_HDR(XTB_OP_END, 0, 2, 0));
+    image.resize(image.size() + 9, 0);
+    a.prog = image.data();
+    a.num_ele_track = (uint32_t) num_ele_track;
     a.part = *p;
     if (mon) a.mon = *mon;
     a.inline_mon = inline_mon;
     a.inline_ltm = inline_ltm;
-    a.pc_start = elem_offset[ele_start];
-    a.pc_stop = elem_offset[ele_start + num_ele_track];
-    if (a.pc_start == XTB_NOT_ADDRESSABLE || a.pc_stop == XTB_NOT_ADDRESSABLE) return -1;
     a.num_turns = (int32_t) num_turns;
     a.flag_end_turn_actions = flag_end_turn_actions;
     a.flag_reset_s = flag_reset_s;
@@ -114,16 +122,25 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
     a.line_length = line_length;
     a.global_xy_limit = global_xy_limit;
     const bool synrad = variant & XTB_VARIANT_SYNRAD, frz = variant & XTB_VARIANT_FREEZE_LONG;
-    if (npt == 2) {
-        if (synrad && frz) run<2, true, true>(a);
-        else if (synrad) run<2, true, false>(a);
-        else if (frz) run<2, false, true>(a);
-        else run<2, false, false>(a);
+    // has_heavy mirrors the kernel choice: thick programs run on the full state, NPT = 1
+    bool heavy = synrad;
+    for (size_t pc = 0; pc + 2 < image.size() && !heavy;) {
+        const uint32_t hx = (uint32_t) image[pc];
+        if ((hx & 0xffu) == XTB_OP_END) break;
+        if ((hx & 0xffu) >= XTB_HEAVY_FIRST) heavy = true;
+        pc += hx >> 16;
+    }
+    if (heavy || force_full) {
+        if (synrad && frz) run<1, true, true, PState>(a);
+        else if (synrad) run<1, true, false, PState>(a);
+        else if (frz) run<1, false, true, PState>(a);
+        else run<1, false, false, PState>(a);
+    } else if (npt == 2) {
+        if (frz) run<2, false, true, PHot>(a);
+        else run<2, false, false, PHot>(a);
     } else {
-        if (synrad && frz) run<1, true, true>(a);
-        else if (synrad) run<1, true, false>(a);
-        else if (frz) run<1, false, true>(a);
-        else run<1, false, false>(a);
+        if (frz) run<1, false, true, PHot>(a);
+        else run<1, false, false, PHot>(a);
     }
     return 0;
 }

@@ -17,7 +17,6 @@
 extern "C" cudaError_t xtb_launch_track_fast(unsigned, const XtbTrackArgs*, cudaStream_t);
 extern "C" cudaError_t xtb_launch_track_exact(unsigned, const XtbTrackArgs*, cudaStream_t);
 
-#define XTB_THREADS 256
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -39,10 +38,16 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 struct xtb_program {
     size_t n_words = 0, n_tiles = 0;
     bool has_heavy = false;
-    uint64_t* d_prog = nullptr;
-    uint32_t* d_tile_off = nullptr;
+    uint64_t* d_prog = nullptr;          // IMAGE: tile k = its ops + one XTB_OP_END op (2 words)
+    uint32_t* d_tile_off = nullptr;      // image offsets [n_tiles + 1]
     std::vector<uint32_t> elem_offset;   // host copy [n_elements + 1], XTB_NOT_ADDRESSABLE allowed
-    std::vector<uint32_t> tile_off;      // host copy [n_tiles + 1]
+    std::vector<uint32_t> tile_off;      // host copy [n_tiles + 1], offsets in the op stream
+    // tile holding word w of the op stream
+    size_t tile_of(uint32_t w) const {
+        size_t k = (size_t) (std::upper_bound(tile_off.begin(), tile_off.end(), w) - tile_off.begin());
+        k = k ? k - 1 : 0;
+        return std::min(k, n_tiles ? n_tiles - 1 : 0);
+    }
 };
 
 struct xtb_lattice {
@@ -89,13 +94,26 @@ static int program_prepare(xtb_program& G, const uint64_t* words, size_t n_words
     return XTB_OK;
 }
 
+// Device image: the ops of each tile followed by the XTB_OP_END sentinel that ends the
+// interpreter loop (xtb_interp.cuh), so tile k starts at image word tile_off[k] + 2 k.
 static cudaError_t program_upload(xtb_program& G, const uint64_t* words) {
-    cudaError_t e = cudaMalloc(&G.d_prog, (G.n_words + 2) * sizeof(uint64_t));
-    if (e == cudaSuccess && G.n_words)
-        e = cudaMemcpy(G.d_prog, words, G.n_words * sizeof(uint64_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&G.d_tile_off, G.tile_off.size() * sizeof(uint32_t));
+    std::vector<uint64_t> image;
+    std::vector<uint32_t> image_off;
+    image.reserve(G.n_words + 2 * G.n_tiles + 8);
+    for (size_t k = 0; k < G.n_tiles; ++k) {
+        image_off.push_back((uint32_t) image.size());
+        image.insert(image.end(), words + G.tile_off[k], words + G.tile_off[k + 1]);
+        image.push_back(XTB_HDR(XTB_OP_END, 0, 2, 0));
+        image.push_back(0);
+    }
+    image_off.push_back((uint32_t) image.size());
+    image.resize(image.size() + 8, 0);
+    cudaError_t e = cudaMalloc(&G.d_prog, image.size() * sizeof(uint64_t));
     if (e == cudaSuccess)
-        e = cudaMemcpy(G.d_tile_off, G.tile_off.data(), G.tile_off.size() * sizeof(uint32_t),
+        e = cudaMemcpy(G.d_prog, image.data(), image.size() * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&G.d_tile_off, image_off.size() * sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(G.d_tile_off, image_off.data(), image_off.size() * sizeof(uint32_t),
                        cudaMemcpyHostToDevice);
     return e;
 }
@@ -224,19 +242,18 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     a.inline_ltm = L->d_ltm;
     a.part = *particles;
     if (tbt_monitor) a.mon = *tbt_monitor;
-    a.pc_start = G->elem_offset[ele_start];
-    a.pc_stop = G->elem_offset[ele_start + num_ele_track];
-    {   // tiles covering [pc_start, pc_stop)
-        const std::vector<uint32_t>& t = G->tile_off;
-        auto tile_of = [&](uint32_t w) {
-            size_t k = (size_t) (std::upper_bound(t.begin(), t.end(), w) - t.begin());
-            k = k ? k - 1 : 0;
-            return (int32_t) std::min(k, G->n_tiles ? G->n_tiles - 1 : 0);
-        };
-        a.tile_first = tile_of(a.pc_start);
-        a.tile_last = a.pc_stop > a.pc_start ? tile_of(a.pc_stop - 1) : a.tile_first;
+    {   // op-stream range -> tiles and image offsets (every tile before adds 2 sentinel words)
+        const uint32_t w_start = G->elem_offset[ele_start];
+        const uint32_t w_stop = G->elem_offset[ele_start + num_ele_track];
+        const size_t t_first = G->tile_of(w_start);
+        const size_t t_last = w_stop > w_start ? G->tile_of(w_stop - 1) : t_first;
+        a.tile_first = (int32_t) t_first;
+        a.tile_last = (int32_t) t_last;
+        a.pc_start = w_start + 2u * (uint32_t) t_first;
+        a.pc_stop = (w_stop > w_start ? w_stop : w_start) + 2u * (uint32_t) t_last;
     }
     a.num_turns = (int32_t) num_turns;
+    a.num_ele_track = (uint32_t) num_ele_track;
     a.flag_end_turn_actions = flag_end_turn_actions;
     a.flag_reset_s = flag_reset_s_at_end_turn;
     a.flag_monitor = flag_monitor;

@@ -173,10 +173,46 @@ static __device__ __noinline__ void generic_op(const uint32_t op, const int32_t 
 
 // A lane without a particle to track executes the ops on this benign on-axis state
 // (no per-op predication in the hot loop); nothing of it is ever written back.
+template <class S>
+__device__ __forceinline__ void pstate_benign(S& P) {
+    P.x = P.px = P.y = P.py = P.zeta = P.delta = P.s = 0.;
+    P.rpp = P.rv0v = P.chi = 1.;
+    P.state = 1;
+}
 __device__ __forceinline__ void pstate_benign(PState& P) {
     P.x = P.px = P.y = P.py = P.zeta = P.delta = P.s = 0.;
     P.rpp = P.rvv = P.rv0v = P.chi = 1.;
     P.state = 1;
+    P.at_turn = 0;
+    P.at_element = 0;
+}
+
+// ---- cold paths, out of line: their register needs must not weigh on the hot loop ----
+// one generic / heavy op on one lane; returns false when the particle was lost and stored
+template <bool HEAVY, bool SYNRAD, bool FRZ, class S>
+static __device__ __noinline__ bool xtb_slow_op(S& Pk, const PSlot Gk, const XtbPass ps,
+                                                const uint32_t eidx, const uint32_t h,
+                                                const int32_t aux, const double* __restrict__ q,
+                                                const XtbTrackArgs& a) {
+    const uint32_t op = h & 0xffu;
+    bool alive = true;
+    PState T = pstate_full(Pk, Gk, ps, eidx);
+    if ((a.flag_monitor == 2) && (h & (XTB_F_START << 8))) monitor_record(a.mon, T, Gk);
+#ifdef XTB_WITH_HEAVY
+    if (HEAVY && op >= XTB_HEAVY_FIRST) heavy_op<SYNRAD, FRZ>(op, aux, q, T, Gk, a);
+    else
+#endif
+        generic_op<FRZ>(op, aux, q, T, Gk, a, true);
+    if ((h & (XTB_F_GLOBAL << 8)) && !a.ignore_global) global_aperture_check(T, a.global_xy_limit);
+    if ((h & (XTB_F_END << 8)) && T.state <= 0) {
+        // tracker.py:702-711: a lost particle stops here, at_element stays on the
+        // element where it was lost
+        pstate_store(T, Gk);
+        alive = false;
+        T.state = 1;
+    }
+    pstate_back(Pk, T, Gk);
+    return alive;
 }
 
 struct __align__(16) xtb_w128 { uint64_t x, y; };
@@ -189,31 +225,57 @@ struct __align__(16) xtb_d2 { double x, y; };
 #define XTB_UNLIKELY(c) __builtin_expect(!!(c), 0)
 #endif
 
-// Executes the ops in [pc, pend) on the NPT particles of this thread.
-//   P[k].at_element  element index at the START of this pass over the lattice;
-//   eidx             elements completed so far in this pass (identical for all
-//                    threads), so the current element is P[k].at_element + eidx;
-//   live[k]          lane k still tracks a real, active particle.
-// A particle found lost at the end of an element is written back to the caller's SoA
-// at once (pstate_store) and its lane goes on as a dead lane: its registers keep
-// evolving but are never stored again.  The fast path never writes `state`: the loss
-// tests branch to cold code that stores the particle and clears live[k] -- nothing
-// else, so that no register of the hot loop is redefined on a cold path.  The caller
-// resets dead lanes to the benign state between tiles.
-template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ>
-__device__ __forceinline__ void xtb_interp(const uint64_t* __restrict__ pc,
-                                           const uint64_t* const pend, PState (&P)[NPT],
-                                           const PSlot (&G)[NPT], bool (&live)[NPT],
-                                           uint32_t& eidx, const XtbTrackArgs& a) {
+// The particles one thread carries, as they sit in (thread-local) memory between tiles.
+template <int NPT, class S>
+struct XtbLanes {
+    S P[NPT];
+    PSlot G[NPT];
+    bool live[NPT];      // lane k still tracks a real, active particle
+    uint32_t eidx;       // elements completed so far in this pass (identical for all threads)
+};
+
+// Executes the ops of one tile, from word `off` of `tb` up to the XTB_OP_END sentinel,
+// on the NPT particles of this thread.
+//
+// Deliberately NOT inlined into the kernel: the function loads the lanes from `lb` into
+// registers, runs the whole tile on registers and writes them back, so that the register
+// allocation of the hot loop is not disturbed by the variables of the turn / tile loops
+// around it (with it inlined, ptxas spilled the loop's own offset and header words).
+// The round trip through local memory costs ~50 instructions per tile of ~10^4.
+//
+// A particle found lost at the end of an element is written back to the caller's SoA at
+// once (pstate_store) and its lane goes on as a dead lane: its registers keep evolving
+// but are never stored again.  The fast path never writes `state`: the loss tests branch
+// to cold code that stores the particle and clears live[k] -- nothing else, so that no
+// register of the hot loop is redefined on a cold path.  Dead lanes are reset to the
+// benign state at the end of the tile.
+//
+// Hot-loop shape: the header of the NEXT op and the first four parameter words of THIS
+// op are loaded before any arithmetic (their shared-memory latency is covered by it);
+// the drift prefix is one bit test, the main op one switch; the loss test is one
+// not-taken branch; no per-op bounds test (the tile ends at a sentinel op).
+template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool CHI1, class S>
+static __device__ __noinline__ void xtb_run_tile(const uint64_t* __restrict__ tb, uint32_t off,
+                                                 XtbLanes<NPT, S>* __restrict__ lb,
+                                                 const XtbPass ps, const XtbTrackArgs& a) {
+    S P[NPT];
+    PSlot G[NPT];
+    bool live[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        P[k] = lb->P[k];
+        G[k] = lb->G[k];
+        live[k] = lb->live[k];
+    }
+    uint32_t eidx = lb->eidx;
     const double lim = a.global_xy_limit;
     // high word of the limit for the integer pre-filter (0: always take the exact test)
     const uint32_t lim_hi = (lim > 0.) ? (uint32_t) __double2hiint(lim) : 0u;
 
-    // lane k lost in element `e_rel` (relative index) with state code `code`
-    auto retire = [&](const int k, const uint32_t e_rel, const int32_t code) {
-        PState T = P[k];
+    // lane k lost in the current element with state code `code`
+    auto retire = [&](const int k, const int32_t code) {
+        PState T = pstate_full(P[k], G[k], ps, eidx);
         T.state = code;
-        T.at_element += (int32_t) e_rel;
         pstate_store(T, G[k]);
         live[k] = false;
     };
@@ -224,7 +286,7 @@ __device__ __forceinline__ void xtb_interp(const uint64_t* __restrict__ pc,
     //   2  integer pre-filter on the high words: |x| > lim implies hi32(|x|) >= hi32(lim),
     //      so lanes whose high words are all below hi32(lim) are inside for sure; no FP64
     //      instruction at all, the exact test runs on the cold path only.
-    auto global_check = [&](const uint32_t e_rel) {
+    auto global_check = [&]() {
 #if XTB_GLOBAL_FILTER == 2
         uint32_t m = 0;
 #pragma unroll
@@ -248,114 +310,121 @@ __device__ __forceinline__ void xtb_interp(const uint64_t* __restrict__ pc,
             if (!a.ignore_global) {
 #pragma unroll
                 for (int k = 0; k < NPT; ++k)
-                    if (outside_global(P[k], lim) && live[k]) retire(k, e_rel, -1);
+                    if (outside_global(P[k], lim) && live[k]) retire(k, -1);
             }
         }
     };
+    // the Drift element in front of an op: track, global check, loss check, at_element++
+    auto prefix = [&](const double L) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], L);
+        global_check();
+        eidx += 1;
+    };
 
-    while (pc < pend) {
-        // header + drift-prefix length in one 16-byte broadcast load
-        const xtb_w128 hw = *reinterpret_cast<const xtb_w128*>(pc);
+    xtb_w128 hw = *reinterpret_cast<const xtb_w128*>(tb + off);
+    for (;;) {
         const uint32_t h = (uint32_t) hw.x;
         const uint32_t op = h & 0xffu;
-        const xtb_d2* __restrict__ q2 = reinterpret_cast<const xtb_d2*>(pc + 2);
-        const double* __restrict__ q = reinterpret_cast<const double*>(pc + 2);
-        pc += (h >> 16);
+        const double L = __longlong_as_double((long long) hw.y);
+        const uint64_t* __restrict__ cur = tb + off;
+        off += (h >> 16);
+        // first four parameter words of this op and the header of the next one
+        const xtb_d2 c0 = *reinterpret_cast<const xtb_d2*>(cur + 2);
+        const xtb_d2 c1 = *reinterpret_cast<const xtb_d2*>(cur + 4);
+        hw = *reinterpret_cast<const xtb_w128*>(tb + off);
 
-        if (h & (XTB_F_DRIFT << 8)) {
-            // the Drift element in front of this op: track, global check, loss check, at_element++
-            const double L = __longlong_as_double((long long) hw.y);
-#pragma unroll
-            for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], L);
-            global_check(eidx);
-            eidx += 1;
-        }
-
-        if (op < XTB_GENERIC_FIRST) {
-            // ---- fast set: one whole element; never writes `state` in registers ----
-            switch (op) {
+        if (op < XTB_OP_END) {
+            // ---------------- fast ops ----------------
+            if (op & XTB_OPBIT_DRIFT) prefix(L);
+            switch (op & (XTB_OPBIT_DRIFT - 1)) {
             case XTB_OP_MULT0: {
-                const xtb_d2 c0 = q2[0];
                 const double c[2] = {c0.x, c0.y};
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_c<0>(P[k], c);
+                for (int k = 0; k < NPT; ++k) mult_kick_c<0, CHI1>(P[k], c);
                 break;
             }
             case XTB_OP_MULT1: {
-                const xtb_d2 c0 = q2[0], c1 = q2[1];
                 const double c[4] = {c0.x, c0.y, c1.x, c1.y};
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_c<1>(P[k], c);
+                for (int k = 0; k < NPT; ++k) mult_kick_c<1, CHI1>(P[k], c);
                 break;
             }
-            case XTB_OP_MULT2: {
-                const xtb_d2 c0 = q2[0], c1 = q2[1], c2 = q2[2];
-                const double c[6] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y};
+            case XTB_OP_MULTN: {
+                // order >= 2: Horner loop, one coefficient pair per step from shared memory
+                // (same arithmetic as mult_kick_c, not unrolled: small register footprint)
+                const uint32_t order = (uint32_t) (cur[0] >> 32);
+                double dpx[NPT], dpy[NPT];
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_c<2>(P[k], c);
-                break;
-            }
-            case XTB_OP_MULT3: {
-                const xtb_d2 c0 = q2[0], c1 = q2[1], c2 = q2[2], c3 = q2[3];
-                const double c[8] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y};
+                for (int k = 0; k < NPT; ++k) {
+                    dpx[k] = CHI1 ? c0.x : P[k].chi * c0.x;
+                    dpy[k] = CHI1 ? c0.y : P[k].chi * c0.y;
+                }
+                xtb_d2 cc = c1;
+                for (uint32_t i = 1; i <= order; ++i) {
+                    const xtb_d2 cn = *reinterpret_cast<const xtb_d2*>(cur + 4 + 2 * i);
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_c<3>(P[k], c);
+                    for (int k = 0; k < NPT; ++k) {
+                        const double zre = dpx[k] * P[k].x - dpy[k] * P[k].y;
+                        const double zim = dpx[k] * P[k].y + dpy[k] * P[k].x;
+                        dpx[k] = (CHI1 ? cc.x : P[k].chi * cc.x) + zre;
+                        dpy[k] = (CHI1 ? cc.y : P[k].chi * cc.y) + zim;
+                    }
+                    cc = cn;
+                }
+#pragma unroll
+                for (int k = 0; k < NPT; ++k) {
+                    P[k].px += -dpx[k];
+                    P[k].py += dpy[k];
+                }
                 break;
             }
             case XTB_OP_MULTH0: {
-                const xtb_d2 c0 = q2[0], c1 = q2[1];
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_h0<FRZ>(P[k], c0.x, c0.y, c1.x, c1.y);
+                for (int k = 0; k < NPT; ++k) mult_kick_h0<FRZ, CHI1>(P[k], c0.x, c0.y, c1.x, c1.y);
                 break;
             }
             case XTB_OP_EDGE: {
-                const xtb_d2 c0 = q2[0];
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) edge_linear(P[k], c0.x, c0.y);
+                for (int k = 0; k < NPT; ++k) edge_linear_c<CHI1>(P[k], c0.x, c0.y);
                 break;
             }
             case XTB_OP_RECT: {
-                const xtb_d2 c0 = q2[0], c1 = q2[1];
-                bool out[NPT];
                 bool any = false;
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) {
-                    out[k] = !((P[k].x >= c0.x) && (P[k].x <= c0.y) && (P[k].y >= c1.x)
-                               && (P[k].y <= c1.y));
-                    any = any | out[k];
-                }
+                for (int k = 0; k < NPT; ++k)
+                    any = any | !((P[k].x >= c0.x) && (P[k].x <= c0.y) && (P[k].y >= c1.x)
+                                  && (P[k].y <= c1.y));
                 if (XTB_UNLIKELY(any)) {
                     if (!a.ignore_local) {
 #pragma unroll
                         for (int k = 0; k < NPT; ++k)
-                            if (out[k] && live[k]) retire(k, eidx, 0);
+                            if (!((P[k].x >= c0.x) && (P[k].x <= c0.y) && (P[k].y >= c1.x)
+                                  && (P[k].y <= c1.y)) && live[k])
+                                retire(k, 0);
                     }
                 }
                 break;
             }
             case XTB_OP_ELLIPSE: {
-                const xtb_d2 c0 = q2[0], c1 = q2[1];
-                bool out[NPT];
                 bool any = false;
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) {
-                    out[k] = !(P[k].x * P[k].x * c0.y + P[k].y * P[k].y * c0.x <= c1.x);
-                    any = any | out[k];
-                }
+                for (int k = 0; k < NPT; ++k)
+                    any = any | !(P[k].x * P[k].x * c0.y + P[k].y * P[k].y * c0.x <= c1.x);
                 if (XTB_UNLIKELY(any)) {
                     if (!a.ignore_local) {
 #pragma unroll
                         for (int k = 0; k < NPT; ++k)
-                            if (out[k] && live[k]) retire(k, eidx, 0);
+                            if (!(P[k].x * P[k].x * c0.y + P[k].y * P[k].y * c0.x <= c1.x) && live[k])
+                                retire(k, 0);
                     }
                 }
                 break;
             }
             case XTB_OP_FDRIFT: {
-                const double L2 = q[0];
 #pragma unroll
-                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], L2);
-                global_check(eidx);
+                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], c0.x);
+                global_check();
                 break;
             }
             default:      // XTB_OP_NOP
@@ -363,32 +432,44 @@ __device__ __forceinline__ void xtb_interp(const uint64_t* __restrict__ pc,
             }
             eidx += 1;
         } else {
-            // ---- generic / heavy ops: flags honoured, out-of-line bodies ----
-            const int32_t aux = (int32_t) (hw.x >> 32);
-            const bool ebe = (a.flag_monitor == 2) && (h & (XTB_F_START << 8));
+            // ---------------- sentinel, generic and heavy ops ----------------
+            if (op == XTB_OP_END) break;
+            if (h & (XTB_F_DRIFT << 8)) prefix(L);
+            const int32_t aux = (int32_t) (cur[0] >> 32);
+            const double* __restrict__ q = reinterpret_cast<const double*>(cur + 2);
 #pragma unroll
             for (int k = 0; k < NPT; ++k) {
                 if (!live[k]) continue;      // these bodies touch the caller's SoA
-                PState T = P[k];
-                T.at_element += (int32_t) eidx;
-                if (ebe) monitor_record(a.mon, T, G[k]);
-#ifdef XTB_WITH_HEAVY
-                if (HEAVY && op >= XTB_HEAVY_FIRST) heavy_op<SYNRAD, FRZ>(op, aux, q, T, G[k], a);
-                else
-#endif
-                    generic_op<FRZ>(op, aux, q, T, G[k], a, true);
-                if ((h & (XTB_F_GLOBAL << 8)) && !a.ignore_global) global_aperture_check(T, lim);
-                if ((h & (XTB_F_END << 8)) && T.state <= 0) {
-                    // tracker.py:702-711: a lost particle stops here, at_element stays
-                    // on the element where it was lost
-                    pstate_store(T, G[k]);
-                    live[k] = false;
-                    T.state = 1;
-                }
-                T.at_element = P[k].at_element;
-                P[k] = T;
+                S Pc = P[k];                 // (copy: P itself must never have its address taken)
+                live[k] = xtb_slow_op<HEAVY, SYNRAD, FRZ>(Pc, G[k], ps, eidx, h, aux, q, a);
+                P[k] = Pc;
             }
             if (h & (XTB_F_END << 8)) eidx += 1;
         }
+    }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        if (!live[k]) pstate_benign(P[k]);      // lanes that died in this tile
+        lb->P[k] = P[k];
+        lb->live[k] = live[k];
+    }
+    lb->eidx = eidx;
+}
+
+// End of a pass over the element range: increment_at_turn (local_particle_custom_api.h:
+// 76-84) expressed on the block-uniform counters, s reset on the lanes.
+template <int NPT, bool FRZ, class S>
+__device__ __forceinline__ void xtb_end_pass(S (&P)[NPT], XtbPass& ps, const uint32_t eidx,
+                                             const XtbTrackArgs& a) {
+    if (a.flag_end_turn_actions > 0) {
+        ps.turn_inc += 1;
+        ps.el_off = 0;
+        ps.el_reset = 1;
+        if (a.flag_reset_s > 0 && !FRZ) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) P[k].s = 0.;
+        }
+    } else {
+        ps.el_off += eidx;
     }
 }

@@ -19,9 +19,15 @@
 //     compiled twice, with and without FMA contraction (xtb_kernel_inst.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include "xtb_interp.cuh"
 
+#ifndef XTB_THREADS
 #define XTB_THREADS 256
+#endif
+#ifndef XTB_THIN_BLOCKS_PER_SM
+#define XTB_THIN_BLOCKS_PER_SM 2
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t) __cvta_generic_to_shared(p);
@@ -54,18 +60,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+#define XTB_TILE_BUF_WORDS (XTB_TILE_WORDS + 8)   // tile image + END sentinel + prefetch slack
+
 // EXACT only distinguishes the symbols of the two builds of this translation unit
 // (template instantiations are COMDAT: identical names would be merged at link time).
 template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT>
-__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? 1 : (NPT >= 2 ? 2 : 3))
+__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? 1 : XTB_THIN_BLOCKS_PER_SM)
 xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
-    __shared__ __align__(128) uint64_t tile[XTB_NUM_BUF][XTB_TILE_WORDS];
+    using S = typename std::conditional<HEAVY, PState, PHot>::type;
+    __shared__ __align__(128) uint64_t tile[XTB_NUM_BUF][XTB_TILE_BUF_WORDS];
     __shared__ __align__(8) uint64_t full_bar[XTB_NUM_BUF];
 
-    PSlot G[NPT];
-    PState P[NPT];
-    bool live[NPT];             // this lane still tracks a real, active particle
+    XtbLanes<NPT, S> lanes;      // home of the particles between tiles (thread-local memory)
+    PSlot (&G)[NPT] = lanes.G;
+    S (&P)[NPT] = lanes.P;
+    bool (&live)[NPT] = lanes.live;
     bool any_live = false;
+    bool chi_one = true;
 #pragma unroll
     for (int k = 0; k < NPT; ++k) {
         const int64_t slot = ((int64_t) blockIdx.x * NPT + k) * XTB_THREADS + threadIdx.x;
@@ -73,19 +84,22 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
         G[k].i = slot;
         live[k] = false;
         if (slot < a.part.capacity) {
-            P[k].state = (int32_t) G[k].ldi(F_STATE);
-            live[k] = P[k].state > 0;     // check_is_active (GPU), local_particle_custom_api.h:188
+            // check_is_active (GPU), local_particle_custom_api.h:188
+            live[k] = G[k].ldi(F_STATE) > 0;
         }
         if (live[k]) {
             pstate_load(P[k], G[k]);
+            P[k].state = 1;
+            chi_one = chi_one && (P[k].chi == 1.0);
         } else {
             pstate_benign(P[k]);
-            P[k].at_turn = 0;
-            P[k].at_element = 0;
         }
         any_live = any_live || live[k];
     }
     if (!__syncthreads_or(any_live)) return;     // nothing to track in this block
+    // chi == 1 for every particle of the block (any beam of one species): the products
+    // chi * coefficient are then exact copies and are left out (CHI1 code path)
+    const bool chi1 = __syncthreads_and(chi_one) && !HEAVY;
 
     const int n_tiles = a.tile_last - a.tile_first + 1;
     const bool resident = (n_tiles == 1);     // whole range fits one tile: load once
@@ -109,6 +123,10 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
         for (int64_t st = 0; st < XTB_NUM_BUF && st < total_steps; ++st) issue(st);
     }
 
+    XtbPass ps;
+    ps.turn_inc = 0;
+    ps.el_off = 0;
+    ps.el_reset = 0;
     int64_t step = 0;
     for (int turn = 0; turn < a.num_turns; ++turn) {
         // every particle of this block lost: drain the copies in flight and stop
@@ -129,55 +147,60 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
         if (a.flag_monitor == 1) {
 #pragma unroll
             for (int k = 0; k < NPT; ++k)
-                if (live[k]) { const PState T = P[k];  monitor_record(a.mon, T, G[k]); }
+                if (live[k]) {
+                    const PState T = pstate_full(P[k], G[k], ps, 0u);
+                    monitor_record(a.mon, T, G[k]);
+                }
         }
 
         uint32_t eidx = 0;      // elements completed in this pass (uniform over the block)
         for (int j = 0; j < n_tiles; ++j, ++step) {
             const int kt = a.tile_first + j;
             const int b = resident ? 0 : (int) (step % XTB_NUM_BUF);
+            const uint32_t w0 = a.tile_off[kt], w1 = a.tile_off[kt + 1];
+            const uint32_t lo = max(w0, a.pc_start), hi = min(w1 - 2u, a.pc_stop);
             if (!resident || turn == 0) {
                 mbar_wait(&full_bar[b], (uint32_t) ((step / XTB_NUM_BUF) & 1));
+                if (hi < w1 - 2u) {
+                    // the range stops inside this tile: plant the sentinel there
+                    if (threadIdx.x == 0) {
+                        tile[b][hi - w0] = XTB_HDR(XTB_OP_END, 0, 2, 0);
+                        tile[b][hi - w0 + 1] = 0;
+                    }
+                    __syncthreads();
+                }
             }
-            const uint32_t w0 = a.tile_off[kt], w1 = a.tile_off[kt + 1];
-            const uint32_t lo = max(w0, a.pc_start), hi = min(w1, a.pc_stop);
             any_live = false;
 #pragma unroll
             for (int k = 0; k < NPT; ++k) any_live = any_live || live[k];
             if (__any_sync(0xffffffffu, any_live)) {
-                xtb_interp<NPT, HEAVY, SYNRAD, FRZ>(&tile[b][0] + (lo - w0), &tile[b][0] + (hi - w0),
-                                                    P, G, live, eidx, a);
-#pragma unroll
-                for (int k = 0; k < NPT; ++k)
-                    if (!live[k]) pstate_benign(P[k]);      // lanes that died in this tile
+                lanes.eidx = eidx;
+                if (chi1)
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, !HEAVY>(&tile[b][0], lo - w0, &lanes, ps, a);
+                else
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, false>(&tile[b][0], lo - w0, &lanes, ps, a);
+                eidx = lanes.eidx;
             }
             if (!resident) {
                 __syncthreads();       // every warp is done with buffer b
                 if (threadIdx.x == 0 && step + XTB_NUM_BUF < total_steps) issue(step + XTB_NUM_BUF);
             }
         }
+        eidx = a.num_ele_track;        // (warps that skipped dead tiles did not count)
         if (a.flag_monitor == 2) {
 #pragma unroll
             for (int k = 0; k < NPT; ++k)
                 if (live[k]) {
-                    PState T = P[k];
-                    T.at_element += (int32_t) eidx;
+                    const PState T = pstate_full(P[k], G[k], ps, eidx);
                     monitor_record(a.mon, T, G[k]);
                 }
         }
-        // increment_at_turn, local_particle_custom_api.h:76-84
-#pragma unroll
-        for (int k = 0; k < NPT; ++k) {
-            if (a.flag_end_turn_actions > 0) {
-                P[k].at_turn += 1;
-                P[k].at_element = 0;
-                if (a.flag_reset_s > 0 && !FRZ) P[k].s = 0.;
-            } else {
-                P[k].at_element += (int32_t) eidx;
-            }
-        }
+        xtb_end_pass<NPT, FRZ>(P, ps, eidx, a);
     }
 #pragma unroll
     for (int k = 0; k < NPT; ++k)
-        if (live[k]) pstate_store(P[k], G[k]);
+        if (live[k]) {
+            const PState T = pstate_full(P[k], G[k], ps, 0u);
+            pstate_store(T, G[k]);
+        }
 }

@@ -15,7 +15,8 @@
  * 16-byte boundary (bulk-copy granularity, 128-bit shared-memory loads).
  *
  * Drift prefix.  In a thin lattice every other element is a Drift; an op whose
- * header carries XTB_F_DRIFT first performs the expanded drift of the Drift
+ * header carries XTB_F_DRIFT (fast ops: also opcode bit XTB_OPBIT_DRIFT, so that one
+ * indirect branch dispatches both) first performs the expanded drift of the Drift
  * ELEMENT that precedes it (track_drift.h:11-22), with that element's own
  * end-of-element actions (global aperture check, loss check, at_element + 1;
  * xtrack/tracker.py:681-711), and then its own work: two elements per
@@ -44,14 +45,15 @@
 #define XTB_OP_NOP            0   /* Marker, inactive elements, plain Drift (prefix only)    */
 #define XTB_OP_MULT0          1   /* [cn_0, cs_0]                                            */
 #define XTB_OP_MULT1          2   /* [cn_1, cs_1, cn_0, cs_0]                                */
-#define XTB_OP_MULT2          3   /* [cn_2, cs_2, ..., cn_0, cs_0]                           */
-#define XTB_OP_MULT3          4   /* [cn_3, cs_3, ..., cn_0, cs_0]                           */
+#define XTB_OP_MULTN          3   /* aux=order>=2; [cn_o, cs_o, ..., cn_0, cs_0]             */
 #define XTB_OP_MULTH0         5   /* [hl, B0, cn_0, cs_0]  order 0 with curvature, no k1     */
 #define XTB_OP_EDGE           6   /* [r21, r43]            track_dipole_edge_linear.h:30-39  */
 #define XTB_OP_RECT           7   /* [min_x, max_x, min_y, max_y]        limitrect.h:10-38   */
 #define XTB_OP_ELLIPSE        8   /* [a_squ, b_squ, a_b_squ, 0]          limitellipse.h:13   */
 #define XTB_OP_FDRIFT         9   /* [L, 0]  a Drift element as main op (+ global check)    */
 #define XTB_NUM_FAST         10
+#define XTB_OPBIT_DRIFT      16   /* fast opcode | 16: the same op with a drift prefix      */
+#define XTB_OP_END           31   /* tile sentinel (appended by xtb_lattice_create)         */
 
 /* -- generic set (flags honoured; thin, always compiled) -------------------- */
 #define XTB_GENERIC_FIRST    32

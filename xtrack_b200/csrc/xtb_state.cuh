@@ -23,26 +23,44 @@ enum XtbField {
 #define XTB_N_I64 6
 
 struct XtbTrackArgs {
-    const uint64_t* prog;        // device program (words)
-    const uint32_t* tile_off;    // [n_tiles+1] word offsets of the tile boundaries
+    const uint64_t* prog;        // device program image: tiles, each closed by an XTB_OP_END op
+    const uint32_t* tile_off;    // [n_tiles+1] word offsets of the tile images
     const xtb_monitor_t* inline_mon;             // device tables for OP_MONITOR / OP_LAST_TURNS
     const xtb_last_turns_monitor_t* inline_ltm;
     xtb_particles_t part;
     xtb_monitor_t mon;           // turn-by-turn monitor (flag_monitor != 0)
-    uint32_t pc_start, pc_stop;  // word range to execute each turn
+    uint32_t pc_start, pc_stop;  // word range (image offsets) to execute each turn
     int32_t tile_first, tile_last;   // tiles covering [pc_start, pc_stop)
     int32_t num_turns;
+    uint32_t num_ele_track;          // elements per pass
     int32_t flag_end_turn_actions, flag_reset_s, flag_monitor;
     int32_t ignore_global, ignore_local, kill_cavity_kick;
     double line_length;
     double global_xy_limit;
 };
 
+// Full per-particle state: what the generic / thick-magnet op bodies work on.
 struct PState {
     double x, px, y, py, zeta, delta, rpp, rvv, rv0v, chi, s;
     int64_t at_turn;
     int32_t at_element;
     int32_t state;
+};
+
+// Slim state of the thin kernels' hot loop: only what the fast ops touch.  rvv stays in
+// the caller's SoA (written through whenever the energy changes, like ptau); at_turn and
+// at_element are reconstructed from the SoA's entry values plus block-uniform counters
+// (XtbPass) whenever a full PState is needed (loss, monitor record, generic op, exit).
+struct PHot {
+    double x, px, y, py, zeta, delta, rpp, rv0v, chi, s;
+    int32_t state;
+};
+
+// Block-uniform bookkeeping of the turn loop (identical for all threads of a launch).
+struct XtbPass {
+    int32_t turn_inc;     // end-of-turn increments of at_turn so far in this launch
+    uint32_t el_off;      // elements completed in earlier passes since the last at_element reset
+    int32_t el_reset;     // at_element was reset to 0 by an end-of-turn action of this launch
 };
 
 // In-place access to the caller's SoA for one slot.
@@ -76,6 +94,39 @@ __device__ __forceinline__ void pstate_load(PState& P, const PSlot& G) {
     P.rv0v = 1. / P.rvv;
     P.at_turn = G.ldi(F_AT_TURN);
     P.at_element = (int32_t) G.ldi(F_AT_ELEMENT);
+}
+__device__ __forceinline__ void pstate_load(PHot& P, const PSlot& G) {
+    P.x = G.ld(F_X);  P.px = G.ld(F_PX);  P.y = G.ld(F_Y);  P.py = G.ld(F_PY);
+    P.zeta = G.ld(F_ZETA);  P.delta = G.ld(F_DELTA);  P.rpp = G.ld(F_RPP);
+    P.chi = G.ld(F_CHI);  P.s = G.ld(F_S);
+    P.rv0v = 1. / G.ld(F_RVV);
+}
+
+// hot state -> full state.  The SoA still holds the launch-entry at_turn / at_element
+// of a particle that has not been stored yet, and the current rvv.
+__device__ __forceinline__ PState pstate_full(const PState& P, const PSlot& G, const XtbPass& ps,
+                                              const uint32_t eidx) {
+    PState T = P;
+    T.at_turn = G.ldi(F_AT_TURN) + ps.turn_inc;
+    T.at_element = (ps.el_reset ? 0 : (int32_t) G.ldi(F_AT_ELEMENT)) + (int32_t) (ps.el_off + eidx);
+    return T;
+}
+__device__ __forceinline__ PState pstate_full(const PHot& P, const PSlot& G, const XtbPass& ps,
+                                              const uint32_t eidx) {
+    PState T;
+    T.x = P.x;  T.px = P.px;  T.y = P.y;  T.py = P.py;  T.zeta = P.zeta;  T.delta = P.delta;
+    T.rpp = P.rpp;  T.rv0v = P.rv0v;  T.chi = P.chi;  T.s = P.s;  T.state = P.state;
+    T.rvv = G.ld(F_RVV);
+    T.at_turn = G.ldi(F_AT_TURN) + ps.turn_inc;
+    T.at_element = (ps.el_reset ? 0 : (int32_t) G.ldi(F_AT_ELEMENT)) + (int32_t) (ps.el_off + eidx);
+    return T;
+}
+// full state -> hot state after a generic op (rvv is written through to the SoA)
+__device__ __forceinline__ void pstate_back(PState& P, const PState& T, const PSlot& G) { P = T; }
+__device__ __forceinline__ void pstate_back(PHot& P, const PState& T, const PSlot& G) {
+    P.x = T.x;  P.px = T.px;  P.y = T.y;  P.py = T.py;  P.zeta = T.zeta;  P.delta = T.delta;
+    P.rpp = T.rpp;  P.rv0v = T.rv0v;  P.chi = T.chi;  P.s = T.s;  P.state = T.state;
+    G.st(F_RVV, T.rvv);
 }
 
 // Write the register-resident fields back (exit, loss, monitor snapshots read

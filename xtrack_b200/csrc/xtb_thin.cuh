@@ -17,8 +17,8 @@
 // suppressed (FREEZE_VAR_*, xtrack/particles/particles.py:193-227, line.py:4446-4508).
 
 // xtrack/beam_elements/elements_src/track_drift.h:11-22
-template <bool FRZ>
-__device__ __forceinline__ void drift_expanded(PState& P, const double length) {
+template <bool FRZ, class S>
+__device__ __forceinline__ void drift_expanded(S& P, const double length) {
     const double xp = P.px * P.rpp;
     const double yp = P.py * P.rpp;
     const double dzeta = 1 - P.rv0v * (1. + (xp * xp + yp * yp) / 2.);
@@ -311,39 +311,49 @@ __device__ __forceinline__ void global_aperture_check(PState& P, const double li
 // Same arithmetic and operation order as horner_kick / mult_kick above, with the
 // coefficients already in registers (loaded once per op, shared by the particles
 // a thread carries) and the loop unrolled.
-template <int ORDER>
-__device__ __forceinline__ void mult_kick_c(PState& P, const double (&c)[2 * (ORDER + 1)]) {
+// CHI1: every particle of the block has chi == 1.0, so `chi * c` is `c` bit for bit and
+// the multiplication is left out.
+template <int ORDER, bool CHI1, class S>
+__device__ __forceinline__ void mult_kick_c(S& P, const double (&c)[2 * (ORDER + 1)]) {
     const double x = P.x, y = P.y, chi = P.chi;
-    double dpx_mul = chi * c[0];
-    double dpy_mul = chi * c[1];
+    double dpx_mul = CHI1 ? c[0] : chi * c[0];
+    double dpy_mul = CHI1 ? c[1] : chi * c[1];
 #pragma unroll
     for (int i = 1; i <= ORDER; ++i) {
         const double zre = dpx_mul * x - dpy_mul * y;
         const double zim = dpx_mul * y + dpy_mul * x;
-        dpx_mul = chi * c[2 * i] + zre;
-        dpy_mul = chi * c[2 * i + 1] + zim;
+        dpx_mul = (CHI1 ? c[2 * i] : chi * c[2 * i]) + zre;
+        dpy_mul = (CHI1 ? c[2 * i + 1] : chi * c[2 * i + 1]) + zim;
     }
     P.px += -dpx_mul;
     P.py += dpy_mul;
 }
 
 // mult_kick_h with order 0 and no k1 term: q = [hl, B0], c = [cn_0, cs_0]
-template <bool FRZ>
-__device__ __forceinline__ void mult_kick_h0(PState& P, const double hl, const double b0,
+template <bool FRZ, bool CHI1, class S>
+__device__ __forceinline__ void mult_kick_h0(S& P, const double hl, const double b0,
                                              const double cn0, const double cs0) {
     const double x = P.x, chi = P.chi;
-    const double dpx_mul = chi * cn0;
-    const double dpy_mul = chi * cs0;
+    const double dpx_mul = CHI1 ? cn0 : chi * cn0;
+    const double dpy_mul = CHI1 ? cs0 : chi * cs0;
     P.px += -dpx_mul;
     P.py += dpy_mul;
     double dpx = hl * (1. + P.delta);
     const double dzeta = -P.rv0v * hl * x;
-    dpx += chi * b0 * x;
+    dpx += (CHI1 ? b0 : chi * b0) * x;
     P.px += dpx;
     if (!FRZ) P.zeta += dzeta;
 }
 
+// DipoleEdgeLinear_single_particle (track_dipole_edge_linear.h:30-39), fast-op form
+template <bool CHI1, class S>
+__device__ __forceinline__ void edge_linear_c(S& P, const double r21, const double r43) {
+    P.px += (CHI1 ? r21 : P.chi * r21) * P.x;
+    P.py += (CHI1 ? r43 : P.chi * r43) * P.y;
+}
+
 // outside the global aperture?  (negation of the test in global_aperture_check, NaN -> outside)
-__device__ __forceinline__ bool outside_global(const PState& P, const double lim) {
+template <class S>
+__device__ __forceinline__ bool outside_global(const S& P, const double lim) {
     return !((P.x >= -lim) && (P.x <= lim) && (P.y >= -lim) && (P.y <= lim));
 }

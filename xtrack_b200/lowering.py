@@ -31,12 +31,17 @@ F_START, F_END, F_GLOBAL, F_DRIFT = 0x01, 0x02, 0x04, 0x08
 
 # fast set (fused program only): one whole element per op
 FOP_NOP = 0
-FOP_MULT0 = 1          # .. FOP_MULT0 + order, order <= 3
+FOP_MULT0 = 1
+FOP_MULT1 = 2
+FOP_MULTN = 3          # aux = order >= 2
 FOP_MULTH0 = 5
 FOP_EDGE = 6
 FOP_RECT = 7
 FOP_ELLIPSE = 8
 FOP_FDRIFT = 9
+
+OPBIT_DRIFT = 16
+GENERIC_FIRST = 32
 
 # generic set
 OP_NOP = 32
@@ -149,6 +154,8 @@ class Program:
             raise ValueError(f'op of {nw} words > tile of {TILE_WORDS}')
         if prefix_length is not None:
             flags |= F_DRIFT
+            if opcode < GENERIC_FIRST:
+                opcode |= OPBIT_DRIFT       # fast ops: the prefixed form is its own opcode
         hdr = opcode | (flags << 8) | (nw << 16) | ((aux & 0xffffffff) << 32)
         words.append(np.uint64(hdr))
         words.append(np.float64(0.0 if prefix_length is None else prefix_length).view(np.uint64))
@@ -165,17 +172,19 @@ class Program:
             return None
         opcode, aux, params = ops[0]
         if opcode == OP_NOP:
-            return FOP_NOP, []
-        if opcode == OP_MULT and aux <= 3:
-            return FOP_MULT0 + aux, params
+            return FOP_NOP, [], 0
+        if opcode == OP_MULT and aux <= 1:
+            return FOP_MULT0 + aux, params, 0
+        if opcode == OP_MULT and 2 * (aux + 1) + 2 <= 64:
+            return FOP_MULTN, params, aux
         if opcode == OP_MULT_H and (aux & 0xff) == 0 and not ((aux >> 8) & 1):
-            return FOP_MULTH0, [params[0], params[1], params[4], params[5]]
+            return FOP_MULTH0, [params[0], params[1], params[4], params[5]], 0
         if opcode == OP_EDGE_LIN:
-            return FOP_EDGE, params[:2]
+            return FOP_EDGE, params[:2], 0
         if opcode == OP_LIMIT_RECT:
-            return FOP_RECT, params[:4]
+            return FOP_RECT, params[:4], 0
         if opcode == OP_LIMIT_ELLIPSE:
-            return FOP_ELLIPSE, params[:3]
+            return FOP_ELLIPSE, params[:3], 0
         return None
 
     def finish(self, fused=False):
@@ -208,9 +217,10 @@ class Program:
                     pending = None
                 else:
                     offsets.append(start)
-                fast = (FOP_FDRIFT, [ops[0][2][0]]) if is_drift else self._fast_form(ops, static_thick)
+                fast = ((FOP_FDRIFT, [ops[0][2][0]], 0) if is_drift
+                        else self._fast_form(ops, static_thick))
                 if fast is not None:
-                    self._emit(words, fast[0], 0, 0, fast[1], prefix_length=plen)
+                    self._emit(words, fast[0], 0, fast[2], fast[1], prefix_length=plen)
                 else:
                     for ii, (opcode, aux, params) in enumerate(ops):
                         flags = (F_START if ii == 0 else 0)
