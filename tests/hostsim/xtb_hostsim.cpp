@@ -21,6 +21,7 @@
 #define __global__
 static inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, 8); return r; }
 static inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
+static inline double __hiloint2double(int hi, int lo) { long long r = ((long long) hi << 32) | (unsigned) lo; double d; std::memcpy(&d, &r, 8); return d; }
 static inline int __double2hiint(double v) { long long r; std::memcpy(&r, &v, 8); return (int) (r >> 32); }
 #define __reduce_max_sync(m, v) (v)
 #define __any_sync(m, v) (v)
@@ -39,13 +40,14 @@ template <int NPT, bool SYNRAD, bool FRZ, class S>
 static void run(const XtbTrackArgs& a) {
     for (int64_t base = 0; base < a.part.capacity; base += NPT) {
         XtbLanes<NPT, S> lanes;
-        PSlot (&G)[NPT] = lanes.G;
+        PSlot G[NPT];
         S (&P)[NPT] = lanes.P;
         bool (&live)[NPT] = lanes.live;
         bool any_live = false, chi_one = true;
         for (int k = 0; k < NPT; ++k) {
             G[k].p = &a.part;
-            G[k].i = base + k;
+            G[k].i = (uint32_t) (base + k);
+            lanes.slot[k] = (uint32_t) (base + k);
             live[k] = (base + k < a.part.capacity) && G[k].ldi(F_STATE) > 0;
             if (live[k]) {
                 pstate_load(P[k], G[k]);
@@ -71,8 +73,9 @@ static void run(const XtbTrackArgs& a) {
                         monitor_record(a.mon, T, G[k]);
                     }
             lanes.eidx = 0;
-            if (chi1) xtb_run_tile<NPT, true, SYNRAD, FRZ, true>(a.prog, 0u, &lanes, ps, a);
-            else xtb_run_tile<NPT, true, SYNRAD, FRZ, false>(a.prog, 0u, &lanes, ps, a);
+            lanes.off = 0;
+            if (chi1) xtb_run_tile<NPT, true, SYNRAD, FRZ, true>(a.prog, lanes, ps, a);
+            else xtb_run_tile<NPT, true, SYNRAD, FRZ, false>(a.prog, lanes, ps, a);
             const uint32_t eidx = a.num_ele_track;
             if (a.flag_monitor == 2)
                 for (int k = 0; k < NPT; ++k)

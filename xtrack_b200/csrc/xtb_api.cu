@@ -222,6 +222,7 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     if (num_turns < 0 || num_turns > 0x7fffffff) return fail(XTB_E_INVALID, "bad num_turns");
     if (flag_monitor != 0 && !tbt_monitor) return fail(XTB_E_INVALID, "flag_monitor without monitor");
     if (particles->capacity <= 0) return fail(XTB_E_INVALID, "empty particles");
+    if (particles->capacity >= (1ll << 31)) return fail(XTB_E_INVALID, "capacity >= 2^31 slots per launch");
     for (int f = 0; f < XTB_NUM_FIELDS; ++f)
         if (!particles->field[f]) return fail(XTB_E_INVALID, "null particle field pointer");
     if (num_turns == 0) return XTB_OK;

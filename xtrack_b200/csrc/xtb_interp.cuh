@@ -218,6 +218,39 @@ static __device__ __noinline__ bool xtb_slow_op(S& Pk, const PSlot Gk, const Xtb
 struct __align__(16) xtb_w128 { uint64_t x, y; };
 struct __align__(16) xtb_d2 { double x, y; };
 
+// Tile access.  On the device a tile is addressed by its 32-bit shared-window address
+// and read with explicit ld.shared (no 64-bit generic pointer arithmetic in the hot
+// loop); the host build of this file reads through an ordinary pointer.
+#ifdef __CUDA_ARCH__
+typedef uint32_t xtb_tile_t;
+__device__ __forceinline__ xtb_tile_t xtb_tile_of(const uint64_t* p) {
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ xtb_w128 xtb_ld_w(const xtb_tile_t tb, const uint32_t off) {
+    xtb_w128 r;
+    asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"(tb + off * 8u));
+    return r;
+}
+__device__ __forceinline__ xtb_d2 xtb_ld_d(const xtb_tile_t tb, const uint32_t off) {
+    xtb_d2 r;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(tb + off * 8u));
+    return r;
+}
+__device__ __forceinline__ const uint64_t* xtb_tile_ptr(const xtb_tile_t tb, const uint32_t off) {
+    return reinterpret_cast<const uint64_t*>(__cvta_shared_to_generic(tb + off * 8u));
+}
+#else
+typedef const uint64_t* xtb_tile_t;
+static inline xtb_tile_t xtb_tile_of(const uint64_t* p) { return p; }
+static inline xtb_w128 xtb_ld_w(const xtb_tile_t tb, const uint32_t off) {
+    return *reinterpret_cast<const xtb_w128*>(tb + off);
+}
+static inline xtb_d2 xtb_ld_d(const xtb_tile_t tb, const uint32_t off) {
+    return *reinterpret_cast<const xtb_d2*>(tb + off);
+}
+static inline const uint64_t* xtb_tile_ptr(const xtb_tile_t tb, const uint32_t off) { return tb + off; }
+#endif
+
 #ifndef XTB_GLOBAL_FILTER
 #define XTB_GLOBAL_FILTER 2
 #endif
@@ -229,231 +262,309 @@ struct __align__(16) xtb_d2 { double x, y; };
 template <int NPT, class S>
 struct XtbLanes {
     S P[NPT];
-    PSlot G[NPT];
+    uint32_t slot[NPT];  // index of lane k's particle in the caller's SoA
     bool live[NPT];      // lane k still tracks a real, active particle
     uint32_t eidx;       // elements completed so far in this pass (identical for all threads)
+    uint32_t off;        // word offset in the tile of the op to execute next
 };
 
-// Executes the ops of one tile, from word `off` of `tb` up to the XTB_OP_END sentinel,
-// on the NPT particles of this thread.
-//
-// Deliberately NOT inlined into the kernel: the function loads the lanes from `lb` into
-// registers, runs the whole tile on registers and writes them back, so that the register
-// allocation of the hot loop is not disturbed by the variables of the turn / tile loops
-// around it (with it inlined, ptxas spilled the loop's own offset and header words).
-// The round trip through local memory costs ~50 instructions per tile of ~10^4.
-//
-// A particle found lost at the end of an element is written back to the caller's SoA at
-// once (pstate_store) and its lane goes on as a dead lane: its registers keep evolving
-// but are never stored again.  The fast path never writes `state`: the loss tests branch
-// to cold code that stores the particle and clears live[k] -- nothing else, so that no
-// register of the hot loop is redefined on a cold path.  Dead lanes are reset to the
-// benign state at the end of the tile.
-//
-// Hot-loop shape: the header of the NEXT op and the first four parameter words of THIS
-// op are loaded before any arithmetic (their shared-memory latency is covered by it);
-// the drift prefix is one bit test, the main op one switch; the loss test is one
-// not-taken branch; no per-op bounds test (the tile ends at a sentinel op).
-template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool CHI1, class S>
-static __device__ __noinline__ void xtb_run_tile(const uint64_t* __restrict__ tb, uint32_t off,
-                                                 XtbLanes<NPT, S>* __restrict__ lb,
-                                                 const XtbPass ps, const XtbTrackArgs& a) {
+// why xtb_run_fast came back
+enum XtbStop {
+    XTB_STOP_END = 0,        // sentinel reached: tile done
+    XTB_STOP_SLOW,           // the op at `off` is a generic / heavy op (not executed)
+    XTB_STOP_GLOBAL_PREFIX,  // drift prefix of the op at `off` done; some lane is outside the global limit
+    XTB_STOP_GLOBAL_MAIN,    // XTB_OP_FDRIFT at `off` done; some lane is outside the global limit
+    XTB_STOP_RECT,           // XTB_OP_RECT at `off`: some lane is outside the aperture
+    XTB_STOP_ELLIPSE         // XTB_OP_ELLIPSE at `off`: some lane is outside the aperture
+};
+
+// The hot loop.  Executes fast ops from `lb->off` on until something happens that is
+// not fast-path work (XtbStop) and returns what; the caller (xtb_run_tile) deals with
+// it and calls again.  The function
+//   * is deliberately NOT inlined and contains nothing but the fast handlers -- no global
+//     memory access, no call, no cold code -- so that ptxas allocates registers for the
+//     hot handlers alone (with the cold paths in the same function it kept spilling the
+//     tile address and offset, the two values every handler needs first);
+//   * loads the lanes from `lb` into registers at entry and writes them back at exit
+//     (~50 instructions per call, against ~10^4 per tile);
+//   * is threaded code: each handler fetches its parameters and the header of the NEXT op
+//     first (XTB_FETCH: their shared-memory latency is covered by the arithmetic), then
+//     branches straight to the handler of the next op (XTB_NEXT).  One taken branch per op,
+//     no loop back-edge, no bounds test (the tile ends at a sentinel op), no second
+//     dispatch for the drift prefix (prefixed forms have their own handlers).
+// The loss tests are single not-taken branches; the exact test and the bookkeeping are
+// redone by the caller.  `skip_prefix`: the drift prefix of the first op was already done.
+template <int NPT, bool FRZ, bool CHI1, class S>
+static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NPT, S>* __restrict__ lb,
+                                                const uint32_t lim_hi, const int skip_prefix) {
     S P[NPT];
-    PSlot G[NPT];
-    bool live[NPT];
 #pragma unroll
     for (int k = 0; k < NPT; ++k) {
         P[k] = lb->P[k];
-        G[k] = lb->G[k];
-        live[k] = lb->live[k];
+        if (CHI1) P[k].chi = 1.0;      // known constant on this path: no register for it
     }
     uint32_t eidx = lb->eidx;
+    uint32_t off = lb->off;
+    int stop;
+
+    uint32_t h, op, cur;
+    xtb_d2 c0, c1;
+    xtb_w128 hw, hwn;
+    double L;
+
+    // "is any lane outside the global aperture?" (XTB_GLOBAL_FILTER, see xtb_run_tile)
+#if XTB_GLOBAL_FILTER == 2
+#define XTB_ANY_OUTSIDE(any)                                                 \
+    {                                                                        \
+        uint32_t m_ = 0;                                                     \
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) {                    \
+            m_ = max(m_, (uint32_t) __double2hiint(P[k].x) & 0x7fffffffu);   \
+            m_ = max(m_, (uint32_t) __double2hiint(P[k].y) & 0x7fffffffu);   \
+        }                                                                    \
+        any = m_ >= lim_hi;                                                  \
+    }
+#else
+#define XTB_ANY_OUTSIDE(any)                                                 \
+    {                                                                        \
+        const double lim_ = __hiloint2double((int) lim_hi, 0);              \
+        any = false;                                                         \
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k)                      \
+            any = any | !((fabs(P[k].x) < lim_) && (fabs(P[k].y) < lim_));   \
+    }
+#endif
+#define XTB_FETCH()                                                          \
+    h = (uint32_t) hw.x;                                                     \
+    L = __longlong_as_double((long long) hw.y);                              \
+    cur = off;                                                               \
+    off += (h >> 16);                                                        \
+    c0 = xtb_ld_d(tb, cur + 2);                                              \
+    c1 = xtb_ld_d(tb, cur + 4);                                              \
+    hwn = xtb_ld_w(tb, off);
+#define XTB_D(OPC) ((OPC) | XTB_OPBIT_DRIFT)
+#define XTB_NEXT()                                                           \
+    hw = hwn;                                                                \
+    op = (uint32_t) hw.x & 0xffu;                                            \
+    if (op == XTB_D(XTB_OP_MULTH0)) goto H_D_MULTH0;                         \
+    if (op == XTB_D(XTB_OP_MULT1)) goto H_D_MULT1;                           \
+    if (op == XTB_D(XTB_OP_EDGE)) goto H_D_EDGE;                             \
+    if (op == XTB_D(XTB_OP_RECT)) goto H_D_RECT;                             \
+    if (op == XTB_D(XTB_OP_MULTN)) goto H_D_MULTN;                           \
+    if (op == XTB_OP_MULTH0) goto H_MULTH0;                                  \
+    goto L_SWITCH;
+    // the Drift element in front of an op: track, global check (-> caller), at_element++
+#define XTB_PREFIX()                                                         \
+    {                                                                        \
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], L); \
+        bool any_;                                                           \
+        XTB_ANY_OUTSIDE(any_)                                                \
+        if (XTB_UNLIKELY(any_)) { stop = XTB_STOP_GLOBAL_PREFIX;  off = cur;  goto L_STOP; } \
+        eidx += 1;                                                           \
+    }
+#define XTB_HANDLER(NAME, ...)                                               \
+    H_##NAME: { XTB_FETCH(); { __VA_ARGS__ } eidx += 1; XTB_NEXT(); }        \
+    H_D_##NAME: { XTB_FETCH(); XTB_PREFIX(); { __VA_ARGS__ } eidx += 1; XTB_NEXT(); }
+
+    hwn = xtb_ld_w(tb, off);
+    hw = hwn;
+    op = (uint32_t) hw.x & 0xffu;
+    if (skip_prefix) op &= ~(uint32_t) XTB_OPBIT_DRIFT;     // (fast ops only: see xtb_run_tile)
+    goto L_SWITCH;
+
+    XTB_HANDLER(NOP, )
+    XTB_HANDLER(MULT0, {
+        const double c[2] = {c0.x, c0.y};
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_c<0, CHI1>(P[k], c);
+    })
+    XTB_HANDLER(MULT1, {
+        const double c[4] = {c0.x, c0.y, c1.x, c1.y};
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_c<1, CHI1>(P[k], c);
+    })
+    XTB_HANDLER(MULTN, {
+        // order >= 2: Horner loop, one coefficient pair per step from shared memory
+        // (same arithmetic as mult_kick_c, not unrolled: small register footprint)
+        const uint32_t order = (uint32_t) (hw.x >> 32);
+        double dpx[NPT], dpy[NPT];
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) {
+            dpx[k] = CHI1 ? c0.x : P[k].chi * c0.x;
+            dpy[k] = CHI1 ? c0.y : P[k].chi * c0.y;
+        }
+        xtb_d2 cc = c1;
+        for (uint32_t i = 1; i <= order; ++i) {
+            const xtb_d2 cn = xtb_ld_d(tb, cur + 4 + 2 * i);
+            _Pragma("unroll") for (int k = 0; k < NPT; ++k) {
+                const double zre = dpx[k] * P[k].x - dpy[k] * P[k].y;
+                const double zim = dpx[k] * P[k].y + dpy[k] * P[k].x;
+                dpx[k] = (CHI1 ? cc.x : P[k].chi * cc.x) + zre;
+                dpy[k] = (CHI1 ? cc.y : P[k].chi * cc.y) + zim;
+            }
+            cc = cn;
+        }
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) {
+            P[k].px += -dpx[k];
+            P[k].py += dpy[k];
+        }
+    })
+    XTB_HANDLER(MULTH0, {
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k)
+            mult_kick_h0<FRZ, CHI1>(P[k], c0.x, c0.y, c1.x, c1.y);
+    })
+    XTB_HANDLER(EDGE, {
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) edge_linear_c<CHI1>(P[k], c0.x, c0.y);
+    })
+    XTB_HANDLER(RECT, {
+        bool any = false;
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k)
+            any = any | !((P[k].x >= c0.x) && (P[k].x <= c0.y) && (P[k].y >= c1.x)
+                          && (P[k].y <= c1.y));
+        if (XTB_UNLIKELY(any)) { stop = XTB_STOP_RECT;  off = cur;  goto L_STOP; }
+    })
+    XTB_HANDLER(ELLIPSE, {
+        bool any = false;
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k)
+            any = any | !(P[k].x * P[k].x * c0.y + P[k].y * P[k].y * c0.x <= c1.x);
+        if (XTB_UNLIKELY(any)) { stop = XTB_STOP_ELLIPSE;  off = cur;  goto L_STOP; }
+    })
+    XTB_HANDLER(FDRIFT, {
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], c0.x);
+        bool any;
+        XTB_ANY_OUTSIDE(any)
+        if (XTB_UNLIKELY(any)) { stop = XTB_STOP_GLOBAL_MAIN;  off = cur;  goto L_STOP; }
+    })
+
+L_SWITCH:
+    switch (op) {
+#define XTB_ROUTE(NAME)                                  \
+    case XTB_OP_##NAME: goto H_##NAME;                   \
+    case XTB_D(XTB_OP_##NAME): goto H_D_##NAME;
+    XTB_ROUTE(NOP) XTB_ROUTE(MULT0) XTB_ROUTE(MULT1) XTB_ROUTE(MULTN) XTB_ROUTE(MULTH0)
+    XTB_ROUTE(EDGE) XTB_ROUTE(RECT) XTB_ROUTE(ELLIPSE) XTB_ROUTE(FDRIFT)
+#undef XTB_ROUTE
+    case XTB_OP_END:
+        stop = XTB_STOP_END;
+        break;
+    default:
+        stop = XTB_STOP_SLOW;
+        break;
+    }
+#undef XTB_FETCH
+#undef XTB_NEXT
+#undef XTB_PREFIX
+#undef XTB_HANDLER
+#undef XTB_ANY_OUTSIDE
+#undef XTB_D
+L_STOP:
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) lb->P[k] = P[k];
+    lb->eidx = eidx;
+    lb->off = off;
+    return stop;
+}
+
+// Executes the ops of one tile, from word `lb->off` of the tile up to the XTB_OP_END
+// sentinel, on the NPT particles of this thread: the fast ops in xtb_run_fast, everything
+// else here --
+//   * generic and heavy ops through their out-of-line bodies (xtb_slow_op);
+//   * the loss bookkeeping when a fast-path test fired: the exact test of the reference
+//     (global_aperture_check, local_particle_custom_api.h:262-289 -> state -1; LimitRect /
+//     LimitEllipse -> state 0) on every lane, then for a lost particle the write-back to
+//     the caller's SoA at once (pstate_store; at_element stays on the element where it was
+//     lost, tracker.py:702-711).  The lane goes on as a dead lane on the benign state.
+// XTB_GLOBAL_FILTER selects the fast path's "is any lane outside the global limit?":
+//   2  integer pre-filter on the high words: |x| > lim implies hi32(|x|) >= hi32(lim), so
+//      lanes whose high words are all below hi32(lim) are inside for sure -- no FP64
+//      instruction, no false negative; the exact test here sorts out the false positives;
+//   1  |x| < 2^e(lim) (2 DSETP per particle) as the pre-filter.
+template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool CHI1, class S>
+__device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, S>& lanes,
+                                             const XtbPass& ps, const XtbTrackArgs& a) {
     const double lim = a.global_xy_limit;
-    // high word of the limit for the integer pre-filter (0: always take the exact test)
+    // high word of the limit for the pre-filter (0: every check goes to the exact test)
     const uint32_t lim_hi = (lim > 0.) ? (uint32_t) __double2hiint(lim) : 0u;
+    int skip_prefix = 0;
 
     // lane k lost in the current element with state code `code`
     auto retire = [&](const int k, const int32_t code) {
-        PState T = pstate_full(P[k], G[k], ps, eidx);
+        const PSlot Gk{&a.part, lanes.slot[k]};
+        PState T = pstate_full(lanes.P[k], Gk, ps, lanes.eidx);
         T.state = code;
-        pstate_store(T, G[k]);
-        live[k] = false;
+        pstate_store(T, Gk);
+        lanes.live[k] = false;
+        pstate_benign(lanes.P[k]);
     };
-    // global_aperture_check (local_particle_custom_api.h:262-289) + is-active check.
-    // The hot path only needs "is any lane outside?"; XTB_GLOBAL_FILTER selects how:
-    //   0  the reference's four comparisons per particle (FP64 pipe: 4 DSETP)
-    //   1  |x| <= lim && |y| <= lim (2 DSETP; same truth table, NaN -> outside)
-    //   2  integer pre-filter on the high words: |x| > lim implies hi32(|x|) >= hi32(lim),
-    //      so lanes whose high words are all below hi32(lim) are inside for sure; no FP64
-    //      instruction at all, the exact test runs on the cold path only.
     auto global_check = [&]() {
-#if XTB_GLOBAL_FILTER == 2
-        uint32_t m = 0;
-#pragma unroll
-        for (int k = 0; k < NPT; ++k) {
-            m = max(m, (uint32_t) __double2hiint(P[k].x) & 0x7fffffffu);
-            m = max(m, (uint32_t) __double2hiint(P[k].y) & 0x7fffffffu);
-        }
-        const bool any = m >= lim_hi;
-#else
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < NPT; ++k) {
-#if XTB_GLOBAL_FILTER == 1
-            any = any | !((fabs(P[k].x) <= lim) && (fabs(P[k].y) <= lim));
-#else
-            any = any | outside_global(P[k], lim);
-#endif
-        }
-#endif
-        if (XTB_UNLIKELY(any)) {
-            if (!a.ignore_global) {
-#pragma unroll
-                for (int k = 0; k < NPT; ++k)
-                    if (outside_global(P[k], lim) && live[k]) retire(k, -1);
-            }
-        }
-    };
-    // the Drift element in front of an op: track, global check, loss check, at_element++
-    auto prefix = [&](const double L) {
-#pragma unroll
-        for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], L);
-        global_check();
-        eidx += 1;
+        if (a.ignore_global) return;
+        for (int k = 0; k < NPT; ++k)
+            if (lanes.live[k] && outside_global(lanes.P[k], lim)) retire(k, -1);
     };
 
-    xtb_w128 hw = *reinterpret_cast<const xtb_w128*>(tb + off);
     for (;;) {
+        const int stop = xtb_run_fast<NPT, FRZ, CHI1>(tb, &lanes, lim_hi, skip_prefix);
+        skip_prefix = 0;
+        if (stop == XTB_STOP_END) break;
+        const xtb_w128 hw = xtb_ld_w(tb, lanes.off);
         const uint32_t h = (uint32_t) hw.x;
         const uint32_t op = h & 0xffu;
         const double L = __longlong_as_double((long long) hw.y);
-        const uint64_t* __restrict__ cur = tb + off;
-        off += (h >> 16);
-        // first four parameter words of this op and the header of the next one
-        const xtb_d2 c0 = *reinterpret_cast<const xtb_d2*>(cur + 2);
-        const xtb_d2 c1 = *reinterpret_cast<const xtb_d2*>(cur + 4);
-        hw = *reinterpret_cast<const xtb_w128*>(tb + off);
-
-        if (op < XTB_OP_END) {
-            // ---------------- fast ops ----------------
-            if (op & XTB_OPBIT_DRIFT) prefix(L);
-            switch (op & (XTB_OPBIT_DRIFT - 1)) {
-            case XTB_OP_MULT0: {
-                const double c[2] = {c0.x, c0.y};
-#pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_c<0, CHI1>(P[k], c);
-                break;
-            }
-            case XTB_OP_MULT1: {
-                const double c[4] = {c0.x, c0.y, c1.x, c1.y};
-#pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_c<1, CHI1>(P[k], c);
-                break;
-            }
-            case XTB_OP_MULTN: {
-                // order >= 2: Horner loop, one coefficient pair per step from shared memory
-                // (same arithmetic as mult_kick_c, not unrolled: small register footprint)
-                const uint32_t order = (uint32_t) (cur[0] >> 32);
-                double dpx[NPT], dpy[NPT];
-#pragma unroll
+        const uint32_t cur = lanes.off;
+        switch (stop) {
+        case XTB_STOP_GLOBAL_PREFIX:
+            // the drift prefix is done: finish its element, then redo the op without it
+            global_check();
+            lanes.eidx += 1;
+            skip_prefix = 1;
+            if (op >= XTB_GENERIC_FIRST) goto slow_main;
+            break;
+        case XTB_STOP_GLOBAL_MAIN:
+            global_check();
+            lanes.eidx += 1;
+            lanes.off = cur + (h >> 16);
+            break;
+        case XTB_STOP_RECT: {
+            const xtb_d2 c0 = xtb_ld_d(tb, cur + 2), c1 = xtb_ld_d(tb, cur + 4);
+            if (!a.ignore_local)
                 for (int k = 0; k < NPT; ++k) {
-                    dpx[k] = CHI1 ? c0.x : P[k].chi * c0.x;
-                    dpy[k] = CHI1 ? c0.y : P[k].chi * c0.y;
+                    const S& Q = lanes.P[k];
+                    if (lanes.live[k]
+                        && !((Q.x >= c0.x) && (Q.x <= c0.y) && (Q.y >= c1.x) && (Q.y <= c1.y)))
+                        retire(k, 0);
                 }
-                xtb_d2 cc = c1;
-                for (uint32_t i = 1; i <= order; ++i) {
-                    const xtb_d2 cn = *reinterpret_cast<const xtb_d2*>(cur + 4 + 2 * i);
-#pragma unroll
-                    for (int k = 0; k < NPT; ++k) {
-                        const double zre = dpx[k] * P[k].x - dpy[k] * P[k].y;
-                        const double zim = dpx[k] * P[k].y + dpy[k] * P[k].x;
-                        dpx[k] = (CHI1 ? cc.x : P[k].chi * cc.x) + zre;
-                        dpy[k] = (CHI1 ? cc.y : P[k].chi * cc.y) + zim;
-                    }
-                    cc = cn;
-                }
-#pragma unroll
+            lanes.eidx += 1;
+            lanes.off = cur + (h >> 16);
+            break;
+        }
+        case XTB_STOP_ELLIPSE: {
+            const xtb_d2 c0 = xtb_ld_d(tb, cur + 2), c1 = xtb_ld_d(tb, cur + 4);
+            if (!a.ignore_local)
                 for (int k = 0; k < NPT; ++k) {
-                    P[k].px += -dpx[k];
-                    P[k].py += dpy[k];
+                    const S& Q = lanes.P[k];
+                    if (lanes.live[k] && !(Q.x * Q.x * c0.y + Q.y * Q.y * c0.x <= c1.x)) retire(k, 0);
                 }
-                break;
-            }
-            case XTB_OP_MULTH0: {
-#pragma unroll
-                for (int k = 0; k < NPT; ++k) mult_kick_h0<FRZ, CHI1>(P[k], c0.x, c0.y, c1.x, c1.y);
-                break;
-            }
-            case XTB_OP_EDGE: {
-#pragma unroll
-                for (int k = 0; k < NPT; ++k) edge_linear_c<CHI1>(P[k], c0.x, c0.y);
-                break;
-            }
-            case XTB_OP_RECT: {
-                bool any = false;
-#pragma unroll
-                for (int k = 0; k < NPT; ++k)
-                    any = any | !((P[k].x >= c0.x) && (P[k].x <= c0.y) && (P[k].y >= c1.x)
-                                  && (P[k].y <= c1.y));
-                if (XTB_UNLIKELY(any)) {
-                    if (!a.ignore_local) {
-#pragma unroll
-                        for (int k = 0; k < NPT; ++k)
-                            if (!((P[k].x >= c0.x) && (P[k].x <= c0.y) && (P[k].y >= c1.x)
-                                  && (P[k].y <= c1.y)) && live[k])
-                                retire(k, 0);
-                    }
-                }
-                break;
-            }
-            case XTB_OP_ELLIPSE: {
-                bool any = false;
-#pragma unroll
-                for (int k = 0; k < NPT; ++k)
-                    any = any | !(P[k].x * P[k].x * c0.y + P[k].y * P[k].y * c0.x <= c1.x);
-                if (XTB_UNLIKELY(any)) {
-                    if (!a.ignore_local) {
-#pragma unroll
-                        for (int k = 0; k < NPT; ++k)
-                            if (!(P[k].x * P[k].x * c0.y + P[k].y * P[k].y * c0.x <= c1.x) && live[k])
-                                retire(k, 0);
-                    }
-                }
-                break;
-            }
-            case XTB_OP_FDRIFT: {
-#pragma unroll
-                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], c0.x);
+            lanes.eidx += 1;
+            lanes.off = cur + (h >> 16);
+            break;
+        }
+        default: {      // XTB_STOP_SLOW: generic / heavy op, flags honoured
+            if (h & (XTB_F_DRIFT << 8)) {
+                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(lanes.P[k], L);
                 global_check();
-                break;
+                lanes.eidx += 1;
             }
-            default:      // XTB_OP_NOP
-                break;
-            }
-            eidx += 1;
-        } else {
-            // ---------------- sentinel, generic and heavy ops ----------------
-            if (op == XTB_OP_END) break;
-            if (h & (XTB_F_DRIFT << 8)) prefix(L);
-            const int32_t aux = (int32_t) (cur[0] >> 32);
-            const double* __restrict__ q = reinterpret_cast<const double*>(cur + 2);
-#pragma unroll
+        slow_main:
+            const int32_t aux = (int32_t) (hw.x >> 32);
+            const double* __restrict__ q = reinterpret_cast<const double*>(xtb_tile_ptr(tb, cur + 2));
             for (int k = 0; k < NPT; ++k) {
-                if (!live[k]) continue;      // these bodies touch the caller's SoA
-                S Pc = P[k];                 // (copy: P itself must never have its address taken)
-                live[k] = xtb_slow_op<HEAVY, SYNRAD, FRZ>(Pc, G[k], ps, eidx, h, aux, q, a);
-                P[k] = Pc;
+                if (!lanes.live[k]) continue;      // these bodies touch the caller's SoA
+                const PSlot Gk{&a.part, lanes.slot[k]};
+                lanes.live[k] = xtb_slow_op<HEAVY, SYNRAD, FRZ>(lanes.P[k], Gk, ps, lanes.eidx, h, aux, q, a);
+                if (!lanes.live[k]) pstate_benign(lanes.P[k]);
             }
-            if (h & (XTB_F_END << 8)) eidx += 1;
+            if (h & (XTB_F_END << 8)) lanes.eidx += 1;
+            lanes.off = cur + (h >> 16);
+            skip_prefix = 0;
+            break;
+        }
         }
     }
-#pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        if (!live[k]) pstate_benign(P[k]);      // lanes that died in this tile
-        lb->P[k] = P[k];
-        lb->live[k] = live[k];
-    }
-    lb->eidx = eidx;
 }
 
 // End of a pass over the element range: increment_at_turn (local_particle_custom_api.h:

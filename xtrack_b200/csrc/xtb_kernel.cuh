@@ -72,7 +72,7 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     __shared__ __align__(8) uint64_t full_bar[XTB_NUM_BUF];
 
     XtbLanes<NPT, S> lanes;      // home of the particles between tiles (thread-local memory)
-    PSlot (&G)[NPT] = lanes.G;
+    PSlot G[NPT];
     S (&P)[NPT] = lanes.P;
     bool (&live)[NPT] = lanes.live;
     bool any_live = false;
@@ -81,7 +81,8 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     for (int k = 0; k < NPT; ++k) {
         const int64_t slot = ((int64_t) blockIdx.x * NPT + k) * XTB_THREADS + threadIdx.x;
         G[k].p = &a.part;
-        G[k].i = slot;
+        G[k].i = (uint32_t) slot;
+        lanes.slot[k] = (uint32_t) slot;
         live[k] = false;
         if (slot < a.part.capacity) {
             // check_is_active (GPU), local_particle_custom_api.h:188
@@ -175,10 +176,11 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
             for (int k = 0; k < NPT; ++k) any_live = any_live || live[k];
             if (__any_sync(0xffffffffu, any_live)) {
                 lanes.eidx = eidx;
+                lanes.off = lo - w0;
                 if (chi1)
-                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, !HEAVY>(&tile[b][0], lo - w0, &lanes, ps, a);
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, !HEAVY>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
                 else
-                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, false>(&tile[b][0], lo - w0, &lanes, ps, a);
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, false>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
                 eidx = lanes.eidx;
             }
             if (!resident) {

@@ -12,9 +12,10 @@
 #define XTB_LAUNCH_NAME xtb_launch_track_fast
 #endif
 
-// particle slots per thread: 2 in the thin kernels, 1 in the (register-hungry) thick ones
+// particle slots per thread: 3 in the thin kernels (measured best of 1..4 on B200, see
+// profiles/), 1 in the (register-hungry) thick ones
 #ifndef XTB_NPT_THIN
-#define XTB_NPT_THIN 2
+#define XTB_NPT_THIN 3
 #endif
 #ifndef XTB_NPT_HEAVY
 #define XTB_NPT_HEAVY 1

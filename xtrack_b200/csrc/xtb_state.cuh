@@ -66,7 +66,7 @@ struct XtbPass {
 // In-place access to the caller's SoA for one slot.
 struct PSlot {
     const xtb_particles_t* p;
-    int64_t i;
+    uint32_t i;              // slot index (xtb_track rejects capacities >= 2^31)
     __device__ __forceinline__ double ld(int f) const {
         return reinterpret_cast<const double*>(p->field[f])[i];
     }
