@@ -45,7 +45,7 @@ def load():
 class HostSimLattice:
     """Mirrors the program selection of `xtb_track` (csrc/xtb_api.cu): the FUSED program
     when the element range falls on its op boundaries, else the PLAIN one."""
-    npt = 2          # particle slots carried together, as in the thin CUDA kernels
+    npt = 3          # particle slots carried together, as in the thin CUDA kernels
 
     def __init__(self, fused, plain, line_length):
         self.plain = (np.ascontiguousarray(plain[0], dtype=np.uint64),

@@ -138,6 +138,9 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
         else if (synrad) run<1, true, false, PState>(a);
         else if (frz) run<1, false, true, PState>(a);
         else run<1, false, false, PState>(a);
+    } else if (npt == 3) {
+        if (frz) run<3, false, true, PHot>(a);
+        else run<3, false, false, PHot>(a);
     } else if (npt == 2) {
         if (frz) run<2, false, true, PHot>(a);
         else run<2, false, false, PHot>(a);
