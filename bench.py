@@ -234,11 +234,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from xtrack_b200 import sharding
+
     def final_reduction(p):
         stats = _cabi.reduce_stats(p)               # per-GPU partial sums (K5)
-        if world > 1:
-            dist.all_reduce(stats)                  # NCCL: 29 doubles, end of run only
-        return stats
+        return sharding.all_reduce_stats(stats)     # NCCL: 29 doubles, end of run only
 
     # ---- resident-in-HBM measurement ("value") -----------------------------------------
     p = p_host.copy(_device=dev)
@@ -356,9 +356,17 @@ def main():
     peak_sustained, peak_burst = _cabi.measure_dfma_peak(local_rank, 2.0)
     pet_rank0 = pet
     achieved = (pet_rank0 / n_el) * flop_per_turn / (float(np.sum(kernel_ms)) * 1e-3)
+    # DRAM traffic of one tracking launch from the committed ncu --set full capture (this is
+    # an FP64-bound kernel: the figure only shows that HBM is idle, 5e-7 B per element-turn)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_summary.json')) as fid:
+            traffic = json.load(fid).get('dram_bytes_per_launch')
+    except Exception:
+        pass
     roofline = {
         'bound': 'fp64', 'achieved': achieved / 1e12, 'peak': peak_sustained / 1e12,
-        'unit': 'TFLOP/s', 'frac': achieved / peak_sustained, 'traffic': None,
+        'unit': 'TFLOP/s', 'frac': achieved / peak_sustained, 'traffic': traffic,
         'peak_source': 'measured in this run: register-resident DFMA chains on all SMs '
                        '(xtb_measure_dfma_peak, sustained); burst %.2f TFLOP/s; '
                        'MEASURED_PEAKS.json holds no FP64 figure' % (peak_burst / 1e12),

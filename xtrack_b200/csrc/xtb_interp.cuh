@@ -228,12 +228,14 @@ __device__ __forceinline__ xtb_tile_t xtb_tile_of(const uint64_t* p) {
 }
 __device__ __forceinline__ xtb_w128 xtb_ld_w(const xtb_tile_t tb, const uint32_t off) {
     xtb_w128 r;
-    asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"(tb + off * 8u));
+    // (volatile: keeps the load where it is written -- ahead of the arithmetic that covers
+    // its latency; otherwise it is sunk to its first use)
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"(tb + off * 8u));
     return r;
 }
 __device__ __forceinline__ xtb_d2 xtb_ld_d(const xtb_tile_t tb, const uint32_t off) {
     xtb_d2 r;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(tb + off * 8u));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(tb + off * 8u));
     return r;
 }
 __device__ __forceinline__ const uint64_t* xtb_tile_ptr(const xtb_tile_t tb, const uint32_t off) {
