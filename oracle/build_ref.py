@@ -7,6 +7,8 @@ through the generated shim into shared libraries under `oracle/_ref/`
   libxt_ref_serial.so       -DXO_CONTEXT_CPU_SERIAL              bit reference
   libxt_ref_omp.so          -DXO_CONTEXT_CPU_OPENMP -fopenmp     timing baseline
   libxt_ref_noise.so        serial + +-1 ulp noise on libm results  libm-sensitivity yardstick
+  libxt_ref_synrad*.so      the same three without -DXTRACK_MULTIPOLE_NO_SYNRAD: synchrotron
+                            radiation compiled in (mean / quantum models)
 
 Flags mirror xobjects' CPU context as far as it is known (`-O3`, no
 `-march=native`, no `-ffast-math`): baseline x86-64 has no FMA, so the
@@ -30,6 +32,11 @@ VARIANTS = {
     # the clean serial build with +-1 ulp noise on every transcendental libm result
     # (shim/xobjects/headers/ulp_noise.h): measures the reference's sensitivity to its libm
     'noise': ['-DXO_CONTEXT_CPU_SERIAL', '-DXTRACK_MULTIPOLE_NO_SYNRAD', '-DXTB_ORACLE_ULP_NOISE'],
+    # radiation compiled in (line.config XTRACK_MULTIPOLE_NO_SYNRAD = False after
+    # configure_radiation, line.py:4744-4837): mean / quantum models, per-particle RNG
+    'synrad': ['-DXO_CONTEXT_CPU_SERIAL'],
+    'synrad_omp': ['-DXO_CONTEXT_CPU_OPENMP', '-fopenmp'],
+    'synrad_noise': ['-DXO_CONTEXT_CPU_SERIAL', '-DXTB_ORACLE_ULP_NOISE'],
 }
 
 
@@ -57,7 +64,8 @@ def build(variants=None, force=False, verbose=False):
         out = lib_path(vv)
         deps = [gen_h, os.path.join(HERE, 'track_line.c'), __file__,
                 os.path.join(HERE, 'shim', 'xobjects', 'headers', 'common.h'),
-                os.path.join(HERE, 'shim', 'xobjects', 'headers', 'ulp_noise.h')]
+                os.path.join(HERE, 'shim', 'xobjects', 'headers', 'ulp_noise.h'),
+                os.path.join(HERE, 'shim', 'xtrack', 'headers', 'synrad_total_energy_tables.h')]
         if (not force and os.path.exists(out)
                 and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps)):
             continue

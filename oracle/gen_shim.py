@@ -202,6 +202,9 @@ def generate():
     out.append('#include "xtrack/headers/particle_states.h"')
     out.append(RECORD_STUBS)
     out.append('#ifndef XTRACK_MULTIPOLE_NO_SYNRAD')
+    # handles of the (field-less) random generator elements, random/random_generators.py
+    out.append('typedef void* RandomUniformData;\ntypedef void* RandomUniformAccurateData;\n'
+               'typedef void* RandomExponentialData;')
     out.append('#include "xtrack/random/random_src/uniform.h"')
     out.append('#include "xtrack/random/random_src/uniform_accurate.h"')
     out.append('#include "xtrack/random/random_src/exponential.h"')

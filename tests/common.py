@@ -112,7 +112,7 @@ def max_rel_dev(got, ref, fields=COORDS, mask=None):
     return out
 
 
-def libm_yardstick(line, particles, num_turns, ref=None, fields=COORDS, **kw):
+def libm_yardstick(line, particles, num_turns, ref=None, fields=COORDS, variant='serial', **kw):
     """The reference's OWN sensitivity to the libm it links: max_rel_dev between the clean
     oracle and the oracle rebuilt with +-1 ulp noise on every transcendental result
     (oracle variant `noise`, shim/xobjects/headers/ulp_noise.h).  Lattices with per-particle
@@ -121,8 +121,9 @@ def libm_yardstick(line, particles, num_turns, ref=None, fields=COORDS, **kw):
     device) differ at exactly that level, so this is the floor below which agreement with
     the CPU reference cannot be demanded of ANY device implementation."""
     if ref is None:
-        ref = oracle_track(line, particles, num_turns, **kw)
-    noisy = oracle_track(line, particles, num_turns, variant='noise', **kw)
+        ref = oracle_track(line, particles, num_turns, variant=variant, **kw)
+    noisy = oracle_track(line, particles, num_turns,
+                         variant={'serial': 'noise', 'synrad': 'synrad_noise'}[variant], **kw)
     return max_rel_dev(noisy, ref, fields=fields, mask=ref['state'] > 0)
 
 
@@ -153,3 +154,16 @@ def assert_parity(got, ref, yard, exact, mask=None, fields=COORDS, label=''):
           'yardstick', {k: '%.1e' % v for k, v in yard.items()})
     assert not bad, f'{label}: deviation above tolerance (got, allowed): {bad}'
     return dev
+
+
+def seed_rng_host(particles, seeds):
+    """Seeds the per-particle generator of HOST particles with the reference's own
+    `Particles_initialize_rand_gen` (oracle build of particles/rng_src/particles_rng.h:12-28;
+    the product seeds on the device with `xtb_rng_init`)."""
+    hp = ro.HostParticles.from_particles(particles)
+    assert np.array_equal(hp.arrays['particle_id'], particles.get('particle_id')), \
+        'seed before any loss (slot order = id order)'
+    ro.init_rand_gen(hp, seeds)
+    for nn in ro.U32_VARS:
+        setattr(particles, nn, hp.arrays[nn])
+    return particles
