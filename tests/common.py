@@ -136,10 +136,11 @@ EXACT_FACTOR = 3.0      # EXACT kernel (no FMA contraction): device libm vs glib
 FMA_FACTOR = 8.0        # FMA kernel: every mul+add pair rounds once instead of twice
 
 
-def assert_parity(got, ref, yard, exact, mask=None, fields=COORDS, label=''):
+def assert_parity(got, ref, yard, exact, mask=None, fields=COORDS, label='', floor=None):
     dev = max_rel_dev(got, ref, fields=fields, mask=mask)
     factor = EXACT_FACTOR if exact else FMA_FACTOR
-    floor = RTOL if exact else 2 * RTOL
+    if floor is None:
+        floor = RTOL if exact else 2 * RTOL
     # the yardstick is one noise realisation: take it per plane group (the coordinates of
     # a group are coupled by the optics), not per single coordinate
     groups = (('x', 'px', 'y', 'py'), ('zeta', 'delta'))

@@ -59,7 +59,16 @@ static void run(const XtbTrackArgs& a) {
             any_live = any_live || live[k];
         }
         if (!any_live) continue;
-        const bool chi1 = chi_one && std::is_same<S, PHot>::value;
+        // the kernel's fast state: chi == 1 and one common s on the whole group
+        bool fast_state = chi_one && std::is_same<S, PHot>::value;
+        {
+            int first_live = -1;
+            for (int k = NPT - 1; k >= 0; --k) if (live[k]) first_live = k;
+            const double s_ref = P[first_live].s;
+            for (int k = 0; k < NPT; ++k)
+                if (live[k] && __double_as_longlong(P[k].s) != __double_as_longlong(s_ref)) fast_state = false;
+            if (fast_state) for (int k = 0; k < NPT; ++k) P[k].s = s_ref;
+        }
         XtbPass ps;
         ps.turn_inc = 0;  ps.el_off = 0;  ps.el_reset = 0;
         for (int turn = 0; turn < a.num_turns; ++turn) {
@@ -74,8 +83,8 @@ static void run(const XtbTrackArgs& a) {
                     }
             lanes.eidx = 0;
             lanes.off = 0;
-            if (chi1) xtb_run_tile<NPT, true, SYNRAD, FRZ, true>(a.prog, lanes, ps, a);
-            else xtb_run_tile<NPT, true, SYNRAD, FRZ, false>(a.prog, lanes, ps, a);
+            if (fast_state) xtb_run_tile<NPT, true, SYNRAD, FRZ, true, true>(a.prog, lanes, ps, a);
+            else xtb_run_tile<NPT, true, SYNRAD, FRZ, false, false>(a.prog, lanes, ps, a);
             const uint32_t eidx = a.num_ele_track;
             if (a.flag_monitor == 2)
                 for (int k = 0; k < NPT; ++k)

@@ -63,7 +63,12 @@ def test_mean_radiation_ten_turns(name, exact):
     yard = common.libm_yardstick(line, p_host, 10, ref=ref, variant='synrad')
     got = common.by_id(_track_gpu(line, p_host, 10, exact))
     assert ref['delta'].mean() < -1e-3
-    common.assert_parity(got, ref, yard, exact, mask=ref['state'] > 0, label=name + ' mean')
+    # EXACT (the parity-grade default): the 1e-12 / yardstick bar.  The opt-in FMA variant
+    # rounds every contracted mul+add once instead of twice; on the strongly damped ring
+    # that shows at a few 1e-12 of the beam size after 10 turns, where the libm yardstick
+    # (few transcendental calls on this thin lattice) is only 6e-14: its floor is 1e-11.
+    common.assert_parity(got, ref, yard, exact, mask=ref['state'] > 0, label=name + ' mean',
+                         floor=None if exact else 1e-11)
     for ff in ('state', 'at_turn', 'at_element'):
         assert np.array_equal(got[ff], ref[ff]), ff
 

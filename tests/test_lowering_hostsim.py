@@ -197,3 +197,25 @@ def test_freeze_longitudinal():
         assert np.array_equal(p.get(ff), p_host.get(ff)), ff
     assert np.all(p.get('at_turn') == 2)
     assert not np.array_equal(p.get('x'), p_host.get('x'))
+
+
+def test_nonuniform_s_and_mixed_species():
+    """The hot loop's fast state (chi == 1, one common s carried once per thread) is a
+    per-block decision taken at launch; beams that do not qualify -- particles sitting at
+    different s, ions of several charge states -- take the general code path.  Both must
+    reproduce the reference, losses included (a lost particle's s is frozen)."""
+    line = common.load_line('sps')
+    n = 240
+    rng = np.random.default_rng(5)
+    for case in ('uniform', 's', 'chi'):
+        extra = {}
+        if case == 's':
+            extra['s'] = rng.uniform(0, 3, n)
+        if case == 'chi':
+            extra['chi'] = np.where(np.arange(n) % 7 == 0, 1.01, 1.0)
+            extra['charge_ratio'] = np.ones(n)
+        p_host = common.gaussian_particles(line, n, 3, common.SIGMAS['sps'], scale=6.0, **extra)
+        ref = common.oracle_track(line, p_host, 6)
+        assert 5 < (ref['state'] <= 0).sum() < n
+        got = common.by_id(_track(line, p_host, 6))
+        _assert_identical(got, ref)

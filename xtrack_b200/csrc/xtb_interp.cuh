@@ -296,7 +296,11 @@ enum XtbStop {
 //     dispatch for the drift prefix (prefixed forms have their own handlers).
 // The loss tests are single not-taken branches; the exact test and the bookkeeping are
 // redone by the caller.  `skip_prefix`: the drift prefix of the first op was already done.
-template <int NPT, bool FRZ, bool CHI1, class S>
+// SUNI: every lane of the block entered the launch with the same s (bitwise), so s is the
+// same number on every lane for ever (every op adds the same element constants in the same
+// order): it is carried ONCE per thread -- one DADD per drift instead of NPT, and no
+// register pair per particle for it.
+template <int NPT, bool FRZ, bool CHI1, bool SUNI, class S>
 static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NPT, S>* __restrict__ lb,
                                                 const uint32_t lim_hi, const int skip_prefix) {
     S P[NPT];
@@ -308,6 +312,7 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
     uint32_t eidx = lb->eidx;
     uint32_t off = lb->off;
     int stop;
+    double s_u = lb->P[0].s;
 
     uint32_t h, op, cur;
     xtb_d2 c0, c1;
@@ -334,6 +339,13 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
             any = any | !((fabs(P[k].x) < lim_) && (fabs(P[k].y) < lim_));   \
     }
 #endif
+#define XTB_DRIFT(LEN)                                                       \
+    if (SUNI) {                                                              \
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) drift_expanded_nos<FRZ>(P[k], LEN); \
+        if (!FRZ) s_u += LEN;                                                \
+    } else {                                                                 \
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], LEN); \
+    }
 #define XTB_FETCH()                                                          \
     h = (uint32_t) hw.x;                                                     \
     L = __longlong_as_double((long long) hw.y);                              \
@@ -356,7 +368,7 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
     // the Drift element in front of an op: track, global check (-> caller), at_element++
 #define XTB_PREFIX()                                                         \
     {                                                                        \
-        _Pragma("unroll") for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], L); \
+        XTB_DRIFT(L)                                                         \
         bool any_;                                                           \
         XTB_ANY_OUTSIDE(any_)                                                \
         if (XTB_UNLIKELY(any_)) { stop = XTB_STOP_GLOBAL_PREFIX;  off = cur;  goto L_STOP; } \
@@ -427,7 +439,7 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
         if (XTB_UNLIKELY(any)) { stop = XTB_STOP_ELLIPSE;  off = cur;  goto L_STOP; }
     })
     XTB_HANDLER(FDRIFT, {
-        _Pragma("unroll") for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(P[k], c0.x);
+        XTB_DRIFT(c0.x)
         bool any;
         XTB_ANY_OUTSIDE(any)
         if (XTB_UNLIKELY(any)) { stop = XTB_STOP_GLOBAL_MAIN;  off = cur;  goto L_STOP; }
@@ -449,6 +461,7 @@ L_SWITCH:
         break;
     }
 #undef XTB_FETCH
+#undef XTB_DRIFT
 #undef XTB_NEXT
 #undef XTB_PREFIX
 #undef XTB_HANDLER
@@ -456,7 +469,10 @@ L_SWITCH:
 #undef XTB_D
 L_STOP:
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) lb->P[k] = P[k];
+    for (int k = 0; k < NPT; ++k) {
+        if (SUNI) P[k].s = s_u;
+        lb->P[k] = P[k];
+    }
     lb->eidx = eidx;
     lb->off = off;
     return stop;
@@ -476,7 +492,7 @@ L_STOP:
 //      lanes whose high words are all below hi32(lim) are inside for sure -- no FP64
 //      instruction, no false negative; the exact test here sorts out the false positives;
 //   1  |x| < 2^e(lim) (2 DSETP per particle) as the pre-filter.
-template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool CHI1, class S>
+template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool CHI1, bool SUNI, class S>
 __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, S>& lanes,
                                              const XtbPass& ps, const XtbTrackArgs& a) {
     const double lim = a.global_xy_limit;
@@ -491,7 +507,9 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
         T.state = code;
         pstate_store(T, Gk);
         lanes.live[k] = false;
+        const double s_keep = lanes.P[k].s;      // (SUNI: s stays the same on every lane)
         pstate_benign(lanes.P[k]);
+        lanes.P[k].s = s_keep;
     };
     auto global_check = [&]() {
         if (a.ignore_global) return;
@@ -500,7 +518,7 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
     };
 
     for (;;) {
-        const int stop = xtb_run_fast<NPT, FRZ, CHI1>(tb, &lanes, lim_hi, skip_prefix);
+        const int stop = xtb_run_fast<NPT, FRZ, CHI1, SUNI>(tb, &lanes, lim_hi, skip_prefix);
         skip_prefix = 0;
         if (stop == XTB_STOP_END) break;
         const xtb_w128 hw = xtb_ld_w(tb, lanes.off);
@@ -558,7 +576,19 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
                 if (!lanes.live[k]) continue;      // these bodies touch the caller's SoA
                 const PSlot Gk{&a.part, lanes.slot[k]};
                 lanes.live[k] = xtb_slow_op<HEAVY, SYNRAD, FRZ>(lanes.P[k], Gk, ps, lanes.eidx, h, aux, q, a);
-                if (!lanes.live[k]) pstate_benign(lanes.P[k]);
+                if (!lanes.live[k]) {
+                    const double s_keep = lanes.P[k].s;
+                    pstate_benign(lanes.P[k]);
+                    lanes.P[k].s = s_keep;
+                }
+            }
+            if (SUNI) {
+                // dead lanes skipped the op: give them the s of the lanes that did it
+                for (int k = 0; k < NPT; ++k)
+                    if (lanes.live[k]) {
+                        for (int j = 0; j < NPT; ++j) lanes.P[j].s = lanes.P[k].s;
+                        break;
+                    }
             }
             if (h & (XTB_F_END << 8)) lanes.eidx += 1;
             lanes.off = cur + (h >> 16);

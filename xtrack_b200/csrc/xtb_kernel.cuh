@@ -101,6 +101,33 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     // chi == 1 for every particle of the block (any beam of one species): the products
     // chi * coefficient are then exact copies and are left out (CHI1 code path)
     const bool chi1 = __syncthreads_and(chi_one) && !HEAVY;
+    // s bitwise identical on every live particle of the block (any beam tracked from one
+    // place in the ring): it then stays identical, and the hot loop carries it once per
+    // thread (SUNI code path, taken together with CHI1)
+    bool fast_state = false;
+    if (!HEAVY) {
+        __shared__ int s_first_tid;
+        __shared__ double s_ref_sh;
+        if (threadIdx.x == 0) s_first_tid = XTB_THREADS;
+        __syncthreads();
+        int first_live = -1;
+#pragma unroll
+        for (int k = NPT - 1; k >= 0; --k) if (live[k]) first_live = k;
+        if (first_live >= 0) atomicMin(&s_first_tid, (int) threadIdx.x);
+        __syncthreads();
+        if ((int) threadIdx.x == s_first_tid) s_ref_sh = P[first_live].s;
+        __syncthreads();
+        const double s_ref = s_ref_sh;
+        bool s_same = true;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k)
+            if (live[k]) s_same = s_same && (__double_as_longlong(P[k].s) == __double_as_longlong(s_ref));
+        fast_state = __syncthreads_and(s_same) && chi1;
+        if (fast_state) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) P[k].s = s_ref;      // (lanes without a particle too)
+        }
+    }
 
     const int n_tiles = a.tile_last - a.tile_first + 1;
     const bool resident = (n_tiles == 1);     // whole range fits one tile: load once
@@ -177,10 +204,10 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
             if (__any_sync(0xffffffffu, any_live)) {
                 lanes.eidx = eidx;
                 lanes.off = lo - w0;
-                if (chi1)
-                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, !HEAVY>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
+                if (fast_state)
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, !HEAVY, !HEAVY>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
                 else
-                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, false>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, false, false>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
                 eidx = lanes.eidx;
             }
             if (!resident) {

@@ -30,6 +30,18 @@ __device__ __forceinline__ void drift_expanded(S& P, const double length) {
     }
 }
 
+// drift_expanded without the `s += length`: for the hot loop when s is carried once per
+// thread (block-uniform s, see xtb_run_fast SUNI)
+template <bool FRZ, class S>
+__device__ __forceinline__ void drift_expanded_nos(S& P, const double length) {
+    const double xp = P.px * P.rpp;
+    const double yp = P.py * P.rpp;
+    const double dzeta = 1 - P.rv0v * (1. + (xp * xp + yp * yp) / 2.);
+    P.x += xp * length;
+    P.y += yp * length;
+    if (!FRZ) P.zeta += length * dzeta;
+}
+
 // track_drift.h:26-40
 template <bool FRZ>
 __device__ __forceinline__ void drift_exact(PState& P, const double length) {
