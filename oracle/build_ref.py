@@ -37,6 +37,11 @@ VARIANTS = {
     'synrad': ['-DXO_CONTEXT_CPU_SERIAL'],
     'synrad_omp': ['-DXO_CONTEXT_CPU_OPENMP', '-fopenmp'],
     'synrad_noise': ['-DXO_CONTEXT_CPU_SERIAL', '-DXTB_ORACLE_ULP_NOISE'],
+    # OpenMP builds of the noise variants (the noise is a hash of the argument: stateless),
+    # so that the GPU tests do not spend the GPU box's time on a serial CPU run
+    'noise_omp': ['-DXO_CONTEXT_CPU_OPENMP', '-fopenmp', '-DXTRACK_MULTIPOLE_NO_SYNRAD',
+                  '-DXTB_ORACLE_ULP_NOISE'],
+    'synrad_noise_omp': ['-DXO_CONTEXT_CPU_OPENMP', '-fopenmp', '-DXTB_ORACLE_ULP_NOISE'],
 }
 
 

@@ -75,11 +75,33 @@ def toy_ring(thin=False):
     return line
 
 
+_OMP_VARIANT = {'serial': 'omp', 'noise': 'noise_omp', 'synrad': 'synrad_omp',
+                'synrad_noise': 'synrad_noise_omp'}
+
+
 def oracle_track(line, particles, num_turns, *, ele_start=0, num_ele_track=None,
                  flag_end_turn_actions=True, monitor=None, flag_monitor=0, variant='serial',
-                 track_flags=0):
+                 track_flags=0, parallel=False):
     """Runs the reference-header oracle on a copy of `particles`; returns the fields
-    ordered by particle_id."""
+    ordered by particle_id.  `parallel`: the OpenMP build of the same variant -- particles
+    are independent, so surviving particles come out bit-identical to the serial build.
+    Lost ones need not: the reference's OpenMP context skips lost particles in every
+    per-particle block (headers/track.h:43), including the EXIT transformation of a
+    misaligned element, so a particle lost inside a shifted aperture keeps the element-frame
+    coordinates there, while the serial and the GPU contexts (no state test, track.h:20-31,
+    51-55) transform it back.  The product follows the GPU context; whenever the run lost
+    particles the result is therefore recomputed with the serial build."""
+    if parallel:
+        out = oracle_track(line, particles, num_turns, ele_start=ele_start,
+                           num_ele_track=num_ele_track,
+                           flag_end_turn_actions=flag_end_turn_actions, monitor=monitor,
+                           flag_monitor=flag_monitor, variant=_OMP_VARIANT.get(variant, variant),
+                           track_flags=track_flags)
+        if (out['state'] > 0).all():
+            return out
+        if monitor is not None:
+            for vv in monitor.arrays.values():
+                vv[:] = 0
     hp = ro.HostParticles.from_particles(particles)
     re = ro.RefElements(line.elements)
     ro.track_line(hp, re, num_turns=num_turns, ele_start=ele_start,

@@ -59,8 +59,8 @@ def test_mean_radiation_ten_turns(name, exact):
     line.configure_radiation(model='mean')
     n = 2000 if name == 'clic_dr' else 600
     p_host = common.gaussian_particles(line, n, 11, common.SIGMAS[name])
-    ref = common.oracle_track(line, p_host, 10, variant='synrad')
-    yard = common.libm_yardstick(line, p_host, 10, ref=ref, variant='synrad')
+    ref = common.oracle_track(line, p_host, 10, variant='synrad', parallel=True)
+    yard = common.libm_yardstick(line, p_host, 10, ref=ref, variant='synrad', parallel=True)
     got = common.by_id(_track_gpu(line, p_host, 10, exact))
     assert ref['delta'].mean() < -1e-3
     # EXACT (the parity-grade default): the 1e-12 / yardstick bar.  The opt-in FMA variant
@@ -87,8 +87,8 @@ def test_quantum_radiation_stream_and_statistics(name):
     p_dev._init_random_number_generator(seeds=seeds)
     for nn in ro.U32_VARS:
         assert np.array_equal(p_dev.get(nn), p_host.get(nn)), nn
-    ref = common.oracle_track(line, p_host, turns, variant='synrad')
-    yard = common.libm_yardstick(line, p_host, turns, ref=ref, variant='synrad')
+    ref = common.oracle_track(line, p_host, turns, variant='synrad', parallel=True)
+    yard = common.libm_yardstick(line, p_host, turns, ref=ref, variant='synrad', parallel=True)
     line.build_tracker(_device='cuda:0', exact_arithmetic=True)
     line.track(p_dev, num_turns=turns)
     got = common.by_id(p_dev)

@@ -219,3 +219,61 @@ def test_nonuniform_s_and_mixed_species():
         assert 5 < (ref['state'] <= 0).sum() < n
         got = common.by_id(_track(line, p_host, 6))
         _assert_identical(got, ref)
+
+
+def test_zero_coefficient_specialisations():
+    """Ops that leave out the reference's operations on literal-zero coefficients
+    (csrc/xtb_ops.h: MULTP1 / MULTPN / MULTH0N; trimmed RF-multipole orders, zero-voltage
+    RF elements) against the reference, which computes them all.  np.array_equal treats the
+    only admissible difference, the sign of an exact zero, as equal."""
+    D = xb.Drift
+    els = [D(length=0.7), xb.Multipole(knl=[0, 0.3]),                       # MULTP1 (+prefix)
+           xb.Multipole(knl=[0, 0, 2.0]),                                   # MULTPN order 2, no prefix
+           D(length=0.4), xb.Multipole(knl=[0, 0, 0, 30.0, 0, 0]),          # order 3, trailing zeros
+           D(length=0.4), xb.Multipole(knl=[0, 0, 0, 0, 4e3]),              # order 4
+           D(length=0.3), xb.Multipole(knl=[0, 0.2], ksl=[0, 0.1]),         # general order 1
+           D(length=0.3), xb.Multipole(ksl=[0, 0.1]),                       # skew only: general
+           D(length=0.3), xb.Multipole(knl=[0.0], ksl=[0.0]),               # all zero
+           D(length=0.5), xb.Multipole(knl=[0.02], hxl=0.02, length=0.5),   # MULTH0N
+           D(length=0.5), xb.Multipole(knl=[0.02], ksl=[1e-3], hxl=0.02, length=0.5),   # MULTH0
+           D(length=0.2), xb.RFMultipole(voltage=0., frequency=4e8, knl=[0, 0, 0, 0, 0, 0],
+                                         ksl=[0, 0, 0, 0, 0, 0]),           # no strength at all
+           D(length=0.2), xb.RFMultipole(voltage=0., frequency=4e8, knl=[0, 0, 0, 0, 0, 0],
+                                         ksl=[-4.8e-7, 0, 0, 0, 0, 0]),     # crab placeholder
+           D(length=0.2), xb.RFMultipole(voltage=0., frequency=4e8, knl=[4.8e-7, 0, 0, 0, 0, 0],
+                                         ksl=[0, 0, 0, 0, 0, 0], pn=[90., 0, 0, 0, 0, 0]),
+           D(length=0.2), xb.RFMultipole(voltage=2e3, frequency=4e8, knl=[0, 0, 1e-1, 0],
+                                         ksl=[1e-4, 0, 0, 0], pn=[0, 0, 20., 0], ps=[5., 0, 0, 0]),
+           D(length=0.2), xb.Cavity(voltage=0., frequency=4e8, lag=30.),
+           D(length=0.2), xb.Cavity(voltage=1e5, frequency=4e8, lag=30.)]
+    line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=3e9)
+    p_host = common.gaussian_particles(line, 300, 4, common.SIGMAS['toy'], scale=5.)
+    # particles exactly on axis / on one axis: the zero-sign cases
+    x = p_host.get('x').copy();  y = p_host.get('y').copy()
+    px = p_host.get('px').copy();  py = p_host.get('py').copy()
+    x[:10] = 0.;  y[5:20] = 0.;  px[:3] = 0.;  py[:8] = 0.
+    p_host.x = x;  p_host.y = y;  p_host.px = px;  p_host.py = py
+    ref = common.oracle_track(line, p_host, 3)
+    got = common.by_id(_track(line, p_host, 3))
+    _assert_identical(got, ref)
+
+
+def test_oracle_openmp_builds_equal_serial():
+    """The OpenMP builds of the oracle (used by the GPU tests and as the CPU baseline of
+    bench.py) give the serial build's results particle by particle: bit-identical for
+    survivors, identical loss records for lost ones (whose coordinates may stay in the frame
+    of a misaligned aperture in the reference's OpenMP context, see common.oracle_track)."""
+    line = common.load_line('sps')
+    p_host = common.gaussian_particles(line, 500, 3, common.SIGMAS['sps'], scale=6.0)
+    for variant in ('serial', 'noise'):
+        a = common.oracle_track(line, p_host, 4, variant=variant)
+        b = common.oracle_track(line, p_host, 4, variant=common._OMP_VARIANT[variant])
+        assert 5 < (a['state'] <= 0).sum() < 495
+        alive = a['state'] > 0
+        for ff in common.ALL_F64:
+            assert np.array_equal(a[ff][alive], b[ff][alive]), ff
+        for ff in ('state', 'at_turn', 'at_element'):
+            assert np.array_equal(a[ff], b[ff]), ff
+        # with losses, parallel=True falls back to the serial build
+        _assert_identical(common.oracle_track(line, p_host, 4, variant=variant, parallel=True), a)

@@ -215,6 +215,10 @@ static __device__ __noinline__ bool xtb_slow_op(S& Pk, const PSlot Gk, const Xtb
     return alive;
 }
 
+#ifndef XTB_VOLATILE_PARAMS
+#define XTB_VOLATILE_PARAMS 0
+#endif
+
 struct __align__(16) xtb_w128 { uint64_t x, y; };
 struct __align__(16) xtb_d2 { double x, y; };
 
@@ -235,7 +239,13 @@ __device__ __forceinline__ xtb_w128 xtb_ld_w(const xtb_tile_t tb, const uint32_t
 }
 __device__ __forceinline__ xtb_d2 xtb_ld_d(const xtb_tile_t tb, const uint32_t off) {
     xtb_d2 r;
+#if XTB_VOLATILE_PARAMS
+    // ld.volatile: ptxas may not sink the load below the (never taken) loss branch that ends
+    // the drift prefix, so the parameters of the main op are fetched while the prefix computes
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(tb + off * 8u));
+#else
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(tb + off * 8u));
+#endif
     return r;
 }
 __device__ __forceinline__ const uint64_t* xtb_tile_ptr(const xtb_tile_t tb, const uint32_t off) {
@@ -358,12 +368,12 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
 #define XTB_NEXT()                                                           \
     hw = hwn;                                                                \
     op = (uint32_t) hw.x & 0xffu;                                            \
-    if (op == XTB_D(XTB_OP_MULTH0)) goto H_D_MULTH0;                         \
-    if (op == XTB_D(XTB_OP_MULT1)) goto H_D_MULT1;                           \
+    if (op == XTB_D(XTB_OP_MULTH0N)) goto H_D_MULTH0N;                       \
+    if (op == XTB_D(XTB_OP_MULTP1)) goto H_D_MULTP1;                         \
     if (op == XTB_D(XTB_OP_EDGE)) goto H_D_EDGE;                             \
     if (op == XTB_D(XTB_OP_RECT)) goto H_D_RECT;                             \
-    if (op == XTB_D(XTB_OP_MULTN)) goto H_D_MULTN;                           \
-    if (op == XTB_OP_MULTH0) goto H_MULTH0;                                  \
+    if (op == XTB_D(XTB_OP_MULTPN)) goto H_D_MULTPN;                         \
+    if (op == XTB_OP_MULTH0N) goto H_MULTH0N;                                \
     goto L_SWITCH;
     // the Drift element in front of an op: track, global check (-> caller), at_element++
 #define XTB_PREFIX()                                                         \
@@ -422,6 +432,22 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
         _Pragma("unroll") for (int k = 0; k < NPT; ++k)
             mult_kick_h0<FRZ, CHI1>(P[k], c0.x, c0.y, c1.x, c1.y);
     })
+    XTB_HANDLER(MULTH0N, {
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k)
+            mult_kick_h0n<FRZ, CHI1>(P[k], c0.x, c0.y, c1.x);
+    })
+    XTB_HANDLER(MULTH1N, {
+        const xtb_d2 c2 = xtb_ld_d(tb, cur + 6);
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k)
+            mult_kick_h1n<FRZ, CHI1>(P[k], c0.x, c0.y, c1.x, c1.y, c2.x);
+    })
+    XTB_HANDLER(MULTP1, {
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_p1<CHI1>(P[k], c0.x);
+    })
+    XTB_HANDLER(MULTPN, {
+        const uint32_t order = (uint32_t) (hw.x >> 32);
+        _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn<CHI1>(P[k], c0.x, order);
+    })
     XTB_HANDLER(EDGE, {
         _Pragma("unroll") for (int k = 0; k < NPT; ++k) edge_linear_c<CHI1>(P[k], c0.x, c0.y);
     })
@@ -452,6 +478,7 @@ L_SWITCH:
     case XTB_D(XTB_OP_##NAME): goto H_D_##NAME;
     XTB_ROUTE(NOP) XTB_ROUTE(MULT0) XTB_ROUTE(MULT1) XTB_ROUTE(MULTN) XTB_ROUTE(MULTH0)
     XTB_ROUTE(EDGE) XTB_ROUTE(RECT) XTB_ROUTE(ELLIPSE) XTB_ROUTE(FDRIFT)
+    XTB_ROUTE(MULTPN) XTB_ROUTE(MULTP1) XTB_ROUTE(MULTH0N) XTB_ROUTE(MULTH1N)
 #undef XTB_ROUTE
     case XTB_OP_END:
         stop = XTB_STOP_END;

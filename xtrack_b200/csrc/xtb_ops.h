@@ -29,6 +29,16 @@
  *   PLAIN  one element = one or more generic ops, never fused: used for
  *          launches whose element range does not fall on op boundaries of the
  *          fused program and for the element-by-element monitor.
+ * Zero-coefficient specialisation (MULTP1, MULTPN, MULTH0N).  Real lattices are made of
+ * plain normal magnets: one non-zero coefficient.  The reference's Horner loop
+ * (track_magnet_kick.h:183-228) still multiplies and adds the zeros; the specialised ops
+ * leave out exactly the operations whose operand is a literal zero coefficient
+ * (0*y, z - 0, 0 + z, p + 0).  For finite coordinates these are IEEE identities, so the
+ * results are the reference's bit for bit, except that a result that is exactly zero may
+ * come out as -0.0 where the reference has +0.0 (or vice versa).  The same specialisation
+ * exists in the reference as `SimpleThinQuadrupole` / `SimpleThinBend`
+ * (simplethinquadrupole.h:13-33), which `optimize_for_tracking` swaps in (line.py:4951).
+ *
  * An element that lowers to several ops carries XTB_F_START on the first and
  * XTB_F_END (loss check + at_element++) on the last, plus XTB_F_GLOBAL for
  * classes that are statically thick (global aperture check, tracker.py:681-689).
@@ -46,12 +56,18 @@
 #define XTB_OP_MULT0          1   /* [cn_0, cs_0]                                            */
 #define XTB_OP_MULT1          2   /* [cn_1, cs_1, cn_0, cs_0]                                */
 #define XTB_OP_MULTN          3   /* aux=order>=2; [cn_o, cs_o, ..., cn_0, cs_0]             */
+#define XTB_OP_MULTPN         4   /* aux=order>=2; [cn_o, 0]  ONLY the top normal coefficient  */
+                                  /* is non-zero (plain sextupole, octupole ...)             */
 #define XTB_OP_MULTH0         5   /* [hl, B0, cn_0, cs_0]  order 0 with curvature, no k1     */
 #define XTB_OP_EDGE           6   /* [r21, r43]            track_dipole_edge_linear.h:30-39  */
 #define XTB_OP_RECT           7   /* [min_x, max_x, min_y, max_y]        limitrect.h:10-38   */
 #define XTB_OP_ELLIPSE        8   /* [a_squ, b_squ, a_b_squ, 0]          limitellipse.h:13   */
 #define XTB_OP_FDRIFT         9   /* [L, 0]  a Drift element as main op (+ global check)    */
-#define XTB_NUM_FAST         10
+#define XTB_OP_MULTP1        10   /* [cn_1, 0]  plain normal quadrupole kick (cs_1 = c_0 = 0)  */
+#define XTB_OP_MULTH0N       11   /* [hl, B0, cn_0, 0]     MULTH0 with cs_0 == 0               */
+#define XTB_OP_MULTH1N       12   /* [hl, B0, B1, cn_1, cn_0, 0]  order 1 with curvature and   */
+                                  /* the k1*h term, normal components only (cs_1 = cs_0 = 0)  */
+#define XTB_NUM_FAST         13
 #define XTB_OPBIT_DRIFT      16   /* fast opcode | 16: the same op with a drift prefix      */
 #define XTB_OP_END           31   /* tile sentinel (appended by xtb_lattice_create)         */
 

@@ -9,6 +9,15 @@
 #pragma once
 #include "xtb_state.cuh"
 
+// 1 + t/2 as the reference writes it (track_drift.h:19).  t/2 is exact, so the fused
+// multiply-add rounds the same real number once: bit-identical, one FP64 instruction less.
+// (Host build: plain arithmetic, same value.)
+#ifdef __CUDA_ARCH__
+#define XTB_ONE_PLUS_HALF(t) __fma_rn((t), 0.5, 1.)
+#else
+#define XTB_ONE_PLUS_HALF(t) (1. + (t) / 2.)
+#endif
+
 #define XTB_C_LIGHT 299792458.0
 #define XTB_PI 3.1415926535897932384626433832795028841971693993751
 #define XTB_DEG2RAD 0.0174532925199432957692369076848861271344287188854
@@ -21,7 +30,7 @@ template <bool FRZ, class S>
 __device__ __forceinline__ void drift_expanded(S& P, const double length) {
     const double xp = P.px * P.rpp;
     const double yp = P.py * P.rpp;
-    const double dzeta = 1 - P.rv0v * (1. + (xp * xp + yp * yp) / 2.);
+    const double dzeta = 1 - P.rv0v * XTB_ONE_PLUS_HALF(xp * xp + yp * yp);
     P.x += xp * length;
     P.y += yp * length;
     if (!FRZ) {
@@ -36,7 +45,7 @@ template <bool FRZ, class S>
 __device__ __forceinline__ void drift_expanded_nos(S& P, const double length) {
     const double xp = P.px * P.rpp;
     const double yp = P.py * P.rpp;
-    const double dzeta = 1 - P.rv0v * (1. + (xp * xp + yp * yp) / 2.);
+    const double dzeta = 1 - P.rv0v * XTB_ONE_PLUS_HALF(xp * xp + yp * yp);
     P.x += xp * length;
     P.y += yp * length;
     if (!FRZ) P.zeta += length * dzeta;
@@ -191,7 +200,8 @@ __device__ __forceinline__ void cavity_kick(PState& P, const PSlot& G, const Xtb
     }
     const double q = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
     const double tau = P.zeta / beta0;
-    const double energy_kick = q * voltage
+    // voltage == 0 (block-uniform): q*0*sin(.) is an exact zero, the sine is not evaluated
+    const double energy_kick = (voltage == 0.) ? 0. : q * voltage
         * sin(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
     if (!a.kill_cavity_kick) {
         add_to_energy<FRZ>(P, G, beta0, energy_kick + 0., 1);
@@ -199,8 +209,11 @@ __device__ __forceinline__ void cavity_kick(PState& P, const PSlot& G, const Xtb
 }
 
 // RF multipole kick: track_rf.h:18-167 with order >= 0 (RFMultipole, rfmultipole.h).
-// q = [V, f, lag, phase, 0], then (knl, ksl, pn, ps, phase_n, phase_s) per order;
-// factor_knl_ksl is folded into knl/ksl by the host.
+// q = [V, f, lag, phase, 0], then (bal_n, bal_s, pn, ps, phase_n, phase_s) per order, with
+// bal = factor_knl_ksl * k[kk] / kk! folded by the host; `order` is the highest order with a
+// non-zero strength (-1: none).  Terms whose strength is a literal zero are exact zeros in
+// the reference (cos * (0 * z)); they, and the sin/cos that only they use, are left out --
+// the branches are on element constants, hence uniform over the block.
 template <bool FRZ>
 __device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const XtbTrackArgs& a,
                                             const double* __restrict__ q, const int order) {
@@ -210,26 +223,41 @@ __device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const Xtb
     const double beta0 = G.ld(F_BETA0);
     const double qq = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
     const double tau = P.zeta / beta0;
-    const double energy_kick = qq * voltage
+    const double energy_kick = (voltage == 0.) ? 0. : qq * voltage
         * sin(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
 
-    double dpx = 0.0, dpy = 0.0, dptr = 0.0, zre = 1.0, zim = 0.0, factorial = 1.0;
+    double dpx = 0.0, dpy = 0.0, dptr = 0.0, zre = 1.0, zim = 0.0;
     const double x = P.x, y = P.y;
     const double p0c = G.ld(F_P0C);
     for (int kk = 0; kk <= order; kk++) {
-        if (kk > 0) factorial *= kk;
         const double* __restrict__ e = t + 6 * kk;
+        const double bal_n_kk = e[0];
+        const double bal_s_kk = e[1];
+        const bool has_n = (bal_n_kk != 0.), has_s = (bal_s_kk != 0.);
         const double pn_kk = phase0 + XTB_DEG2RAD * e[2] + e[4] - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau;
         const double ps_kk = phase0 + XTB_DEG2RAD * e[3] + e[5] - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau;
-        const double bal_n_kk = e[0] / factorial;
-        const double bal_s_kk = e[1] / factorial;
-        const double cn = cos(pn_kk), cs = cos(ps_kk), sn = sin(pn_kk), ss = sin(ps_kk);
-        dpx += cn * (bal_n_kk * zre) - cs * (bal_s_kk * zim);
-        dpy += cs * (bal_s_kk * zre) + cn * (bal_n_kk * zim);
+        double cn = 0., cs = 0., sn = 0., ss = 0.;
+        if (has_n) { cn = cos(pn_kk);  sn = sin(pn_kk); }
+        if (has_s) {
+            if (has_n && ps_kk == pn_kk) { cs = cn;  ss = sn; }
+            else { cs = cos(ps_kk);  ss = sin(ps_kk); }
+        }
+        if (has_n && has_s) {
+            dpx += cn * (bal_n_kk * zre) - cs * (bal_s_kk * zim);
+            dpy += cs * (bal_s_kk * zre) + cn * (bal_n_kk * zim);
+        } else if (has_n) {
+            dpx += cn * (bal_n_kk * zre);
+            dpy += cn * (bal_n_kk * zim);
+        } else if (has_s) {
+            dpx += -(cs * (bal_s_kk * zim));
+            dpy += cs * (bal_s_kk * zre);
+        }
         const double zret = zre * x - zim * y;
         zim = zim * x + zre * y;
         zre = zret;
-        dptr += sn * (bal_n_kk * zre) - ss * (bal_s_kk * zim);
+        if (has_n && has_s) dptr += sn * (bal_n_kk * zre) - ss * (bal_s_kk * zim);
+        else if (has_n) dptr += sn * (bal_n_kk * zre);
+        else if (has_s) dptr += -(ss * (bal_s_kk * zim));
     }
     const double rf_energy_kick = -qq * ((frequency * (2.0 * XTB_PI / XTB_C_LIGHT) * p0c) * dptr);
     P.px += -P.chi * dpx;
@@ -354,6 +382,66 @@ __device__ __forceinline__ void mult_kick_h0(S& P, const double hl, const double
     const double dzeta = -P.rv0v * hl * x;
     dpx += (CHI1 ? b0 : chi * b0) * x;
     P.px += dpx;
+    if (!FRZ) P.zeta += dzeta;
+}
+
+// Plain normal multipole of order ORDER >= 1: mult_kick_c with every coefficient but cn_ORDER
+// a literal zero, the zero operations left out (xtb_ops.h "Zero-coefficient specialisation"):
+//   Horner step 1:  zre = cn*x - 0*y = cn*x ;  zim = cn*y + 0*x = cn*y ;  then 0 + z = z
+template <bool CHI1, class S>
+__device__ __forceinline__ void mult_kick_p1(S& P, const double cn) {
+    const double a = CHI1 ? cn : P.chi * cn;
+    P.px += -(a * P.x);
+    P.py += a * P.y;
+}
+template <bool CHI1, class S>
+__device__ __forceinline__ void mult_kick_pn(S& P, const double cn, const uint32_t order) {
+    const double x = P.x, y = P.y;
+    const double a = CHI1 ? cn : P.chi * cn;
+    double dpx = a * x, dpy = a * y;
+    for (uint32_t i = 2; i <= order; ++i) {
+        const double zre = dpx * x - dpy * y;
+        const double zim = dpx * y + dpy * x;
+        dpx = zre;
+        dpy = zim;
+    }
+    P.px += -dpx;
+    P.py += dpy;
+}
+
+// mult_kick_h0 with cs_0 == 0: `py += 0` left out
+template <bool FRZ, bool CHI1, class S>
+__device__ __forceinline__ void mult_kick_h0n(S& P, const double hl, const double b0,
+                                              const double cn0) {
+    const double x = P.x, chi = P.chi;
+    const double dpx_mul = CHI1 ? cn0 : chi * cn0;
+    P.px += -dpx_mul;
+    double dpx = hl * (1. + P.delta);
+    const double dzeta = -P.rv0v * hl * x;
+    dpx += (CHI1 ? b0 : chi * b0) * x;
+    P.px += dpx;
+    if (!FRZ) P.zeta += dzeta;
+}
+
+// mult_kick_h with order 1, the k1*h term, and cs_1 = cs_0 = 0 (combined-function magnet):
+// Horner step with the zero operations left out, then track_magnet_kick.h:98-142
+template <bool FRZ, bool CHI1, class S>
+__device__ __forceinline__ void mult_kick_h1n(S& P, const double hl, const double b0,
+                                              const double b1c, const double cn1,
+                                              const double cn0) {
+    const double x = P.x, y = P.y, chi = P.chi;
+    const double a = CHI1 ? cn1 : chi * cn1;
+    const double dpx_mul = (CHI1 ? cn0 : chi * cn0) + a * x;
+    const double dpy_mul = a * y;
+    P.px += -dpx_mul;
+    P.py += dpy_mul;
+    double dpx = hl * (1. + P.delta);
+    const double dzeta = -P.rv0v * hl * x;
+    dpx += (CHI1 ? b0 : chi * b0) * x;
+    const double b1 = CHI1 ? b1c : chi * b1c;
+    dpx += b1 * (-x * x + 0.5 * y * y);
+    P.px += dpx;
+    P.py += b1 * x * y;
     if (!FRZ) P.zeta += dzeta;
 }
 

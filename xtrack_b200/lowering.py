@@ -34,11 +34,15 @@ FOP_NOP = 0
 FOP_MULT0 = 1
 FOP_MULT1 = 2
 FOP_MULTN = 3          # aux = order >= 2
+FOP_MULTPN = 4         # aux = order >= 2, only the top normal coefficient non-zero
 FOP_MULTH0 = 5
 FOP_EDGE = 6
 FOP_RECT = 7
 FOP_ELLIPSE = 8
 FOP_FDRIFT = 9
+FOP_MULTP1 = 10        # plain normal quadrupole kick
+FOP_MULTH0N = 11       # MULTH0 with cs_0 == 0
+FOP_MULTH1N = 12       # order 1 with curvature + k1*h term, normal components only
 
 OPBIT_DRIFT = 16
 GENERIC_FIRST = 32
@@ -173,12 +177,24 @@ class Program:
         opcode, aux, params = ops[0]
         if opcode == OP_NOP:
             return FOP_NOP, [], 0
+        if opcode == OP_MULT and aux >= 1 and all(v == 0.0 for v in params[1:2 * (aux + 1)]):
+            # plain normal magnet: every coefficient but the top normal one is a literal zero
+            # (csrc/xtb_ops.h "Zero-coefficient specialisation")
+            if aux == 1:
+                return FOP_MULTP1, [params[0], 0.0], 0
+            return FOP_MULTPN, [params[0], 0.0], aux
         if opcode == OP_MULT and aux <= 1:
             return FOP_MULT0 + aux, params, 0
         if opcode == OP_MULT and 2 * (aux + 1) + 2 <= 64:
             return FOP_MULTN, params, aux
         if opcode == OP_MULT_H and (aux & 0xff) == 0 and not ((aux >> 8) & 1):
+            if params[5] == 0.0:
+                return FOP_MULTH0N, [params[0], params[1], params[4], 0.0], 0
             return FOP_MULTH0, [params[0], params[1], params[4], params[5]], 0
+        if (opcode == OP_MULT_H and (aux & 0xff) == 1 and ((aux >> 8) & 1)
+                and params[5] == 0.0 and params[7] == 0.0):
+            # [hl, B0, B1, 0, cn_1, cs_1, cn_0, cs_0] -> [hl, B0, B1, cn_1, cn_0, 0]
+            return FOP_MULTH1N, [params[0], params[1], params[2], params[4], params[6], 0.0], 0
         if opcode == OP_EDGE_LIN:
             return FOP_EDGE, params[:2], 0
         if opcode == OP_LIMIT_RECT:
@@ -827,13 +843,29 @@ def _lower_rf(prog, cfg, *, weight, length, voltage, frequency, harmonic, lag, p
 
     def kick(kw):
         if order >= 0:
+            # track_rf.h:65-115.  `bal = factor_knl_ksl * knl[kk] / factorial` is element
+            # constant: folded here with the reference's operations (factorial accumulated
+            # as a double product).  Orders above the highest non-zero coefficient add
+            # cos*(0*z) - cos*(0*z) = +-0 to the kicks: exact identities, dropped (a crab
+            # cavity placeholder with order 5 and one or no strength set costs 24 sin/cos
+            # per particle in the reference for nothing).  order_eff = -1: only the energy
+            # bookkeeping of LocalParticle_add_to_energy remains.
             fk = ff * kw
-            params = [vv * kw, frequency, lag, phase, 0.0]
+            bal = []
+            factorial = 1.0
             for kk in range(order + 1):
-                params += [fk * float(knl[kk]), fk * float(ksl[kk]), float(pn[kk]), float(ps[kk]),
+                if kk > 0:
+                    factorial *= kk
+                bal.append((fk * float(knl[kk]) / factorial, fk * float(ksl[kk]) / factorial))
+            order_eff = order
+            while order_eff >= 0 and bal[order_eff][0] == 0.0 and bal[order_eff][1] == 0.0:
+                order_eff -= 1
+            params = [vv * kw, frequency, lag, phase, 0.0]
+            for kk in range(order_eff + 1):
+                params += [bal[kk][0], bal[kk][1], float(pn[kk]), float(ps[kk]),
                            float(phase_n[kk]), float(phase_s[kk])]
-            prog.op(OP_RFMULT, params, aux=order, flops=25 + 30 * (order + 1),
-                    transc=1 + 4 * (order + 1))
+            prog.op(OP_RFMULT, params, aux=order_eff, flops=25 + 30 * (order_eff + 1),
+                    transc=(1 if vv * kw != 0.0 else 0) + 4 * (order_eff + 1))
         else:
             prog.op(OP_CAVITY, [vv * kw, frequency, harmonic, lag, phase, 0.0, 0.0],
                     aux=int(absolute_time), transc=1)
