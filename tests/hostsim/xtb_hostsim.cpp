@@ -47,9 +47,11 @@ static void run(const XtbTrackArgs& a) {
         for (int k = 0; k < NPT; ++k) {
             G[k].p = &a.part;
             G[k].i = (uint32_t) (base + k);
+            G[k].c = &lanes.C[k];
             lanes.slot[k] = (uint32_t) (base + k);
             live[k] = (base + k < a.part.capacity) && G[k].ldi(F_STATE) > 0;
             if (live[k]) {
+                G[k].load_cold();
                 pstate_load(P[k], G[k]);
                 P[k].state = 1;
                 chi_one = chi_one && (P[k].chi == 1.0);

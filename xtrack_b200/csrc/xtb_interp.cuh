@@ -274,6 +274,7 @@ static inline const uint64_t* xtb_tile_ptr(const xtb_tile_t tb, const uint32_t o
 template <int NPT, class S>
 struct XtbLanes {
     S P[NPT];
+    PCold C[NPT];        // cached cold fields of lane k's particle (xtb_state.cuh)
     uint32_t slot[NPT];  // index of lane k's particle in the caller's SoA
     bool live[NPT];      // lane k still tracks a real, active particle
     uint32_t eidx;       // elements completed so far in this pass (identical for all threads)
@@ -529,7 +530,7 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
 
     // lane k lost in the current element with state code `code`
     auto retire = [&](const int k, const int32_t code) {
-        const PSlot Gk{&a.part, lanes.slot[k]};
+        const PSlot Gk{&a.part, lanes.slot[k], &lanes.C[k]};
         PState T = pstate_full(lanes.P[k], Gk, ps, lanes.eidx);
         T.state = code;
         pstate_store(T, Gk);
@@ -601,7 +602,7 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
             const double* __restrict__ q = reinterpret_cast<const double*>(xtb_tile_ptr(tb, cur + 2));
             for (int k = 0; k < NPT; ++k) {
                 if (!lanes.live[k]) continue;      // these bodies touch the caller's SoA
-                const PSlot Gk{&a.part, lanes.slot[k]};
+                const PSlot Gk{&a.part, lanes.slot[k], &lanes.C[k]};
                 lanes.live[k] = xtb_slow_op<HEAVY, SYNRAD, FRZ>(lanes.P[k], Gk, ps, lanes.eidx, h, aux, q, a);
                 if (!lanes.live[k]) {
                     const double s_keep = lanes.P[k].s;

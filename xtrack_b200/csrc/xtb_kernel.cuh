@@ -22,11 +22,18 @@
 #include <type_traits>
 #include "xtb_interp.cuh"
 
+// Launch shape (measured on B200, profiles/r01_history.md): 128 threads, 4 blocks per SM for
+// the thin kernels (128 registers per thread, 16 warps per SM; smaller blocks desynchronise
+// the warps of an SM sub-partition a little better than 256 x 2), 2 blocks per SM for the
+// register-hungry thick kernels (<= 255 registers per thread, 8 warps per SM).
 #ifndef XTB_THREADS
-#define XTB_THREADS 256
+#define XTB_THREADS 128
 #endif
 #ifndef XTB_THIN_BLOCKS_PER_SM
-#define XTB_THIN_BLOCKS_PER_SM 2
+#define XTB_THIN_BLOCKS_PER_SM 4
+#endif
+#ifndef XTB_HEAVY_BLOCKS_PER_SM
+#define XTB_HEAVY_BLOCKS_PER_SM 2
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -65,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // EXACT only distinguishes the symbols of the two builds of this translation unit
 // (template instantiations are COMDAT: identical names would be merged at link time).
 template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT>
-__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? 1 : XTB_THIN_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? XTB_HEAVY_BLOCKS_PER_SM : XTB_THIN_BLOCKS_PER_SM)
 xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     using S = typename std::conditional<HEAVY, PState, PHot>::type;
     __shared__ __align__(128) uint64_t tile[XTB_NUM_BUF][XTB_TILE_BUF_WORDS];
@@ -82,6 +89,7 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
         const int64_t slot = ((int64_t) blockIdx.x * NPT + k) * XTB_THREADS + threadIdx.x;
         G[k].p = &a.part;
         G[k].i = (uint32_t) slot;
+        G[k].c = &lanes.C[k];
         lanes.slot[k] = (uint32_t) slot;
         live[k] = false;
         if (slot < a.part.capacity) {
@@ -89,6 +97,7 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
             live[k] = G[k].ldi(F_STATE) > 0;
         }
         if (live[k]) {
+            G[k].load_cold();
             pstate_load(P[k], G[k]);
             P[k].state = 1;
             chi_one = chi_one && (P[k].chi == 1.0);

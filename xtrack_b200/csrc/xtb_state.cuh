@@ -63,18 +63,62 @@ struct XtbPass {
     int32_t el_reset;     // at_element was reset to 0 by an end-of-turn action of this launch
 };
 
-// In-place access to the caller's SoA for one slot.
+// The rarely used fields of one particle (energy bookkeeping of cavities / radiation, loss
+// bookkeeping), read from the caller's SoA ONCE at kernel entry and kept in thread-local
+// memory (L1-resident) for the launch: the out-of-line op bodies then never wait for HBM.
+// ptau and rvv are written back at exit and at loss (pstate_store).
+struct PCold {
+    double beta0, gamma0, p0c, charge_ratio, ptau, rvv;
+    int64_t at_turn0;        // at_turn / at_element at kernel entry
+    int32_t at_element0;
+};
+
+// Access to one particle slot: the cached cold fields through `c`, everything else in
+// place in the caller's SoA.  The field index is a compile-time constant at every call
+// site, so the selection below folds away.
 struct PSlot {
     const xtb_particles_t* p;
     uint32_t i;              // slot index (xtb_track rejects capacities >= 2^31)
-    __device__ __forceinline__ double ld(int f) const {
+    PCold* c;
+    __device__ __forceinline__ double ldg(int f) const {
         return reinterpret_cast<const double*>(p->field[f])[i];
     }
-    __device__ __forceinline__ void st(int f, double v) const {
+    __device__ __forceinline__ void stg(int f, double v) const {
         reinterpret_cast<double*>(p->field[f])[i] = v;
     }
-    __device__ __forceinline__ int64_t ldi(int f) const {
+    __device__ __forceinline__ int64_t ldgi(int f) const {
         return reinterpret_cast<const int64_t*>(p->field[f])[i];
+    }
+    __device__ __forceinline__ double ld(int f) const {
+        switch (f) {
+        case F_BETA0: return c->beta0;
+        case F_GAMMA0: return c->gamma0;
+        case F_P0C: return c->p0c;
+        case F_CHARGE_RATIO: return c->charge_ratio;
+        case F_PTAU: return c->ptau;
+        case F_RVV: return c->rvv;
+        default: return ldg(f);
+        }
+    }
+    __device__ __forceinline__ void st(int f, double v) const {
+        switch (f) {
+        case F_PTAU: c->ptau = v; break;
+        case F_RVV: c->rvv = v; break;
+        default: stg(f, v); break;
+        }
+    }
+    __device__ __forceinline__ int64_t ldi(int f) const {
+        switch (f) {
+        case F_AT_TURN: return c->at_turn0;
+        case F_AT_ELEMENT: return (int64_t) c->at_element0;
+        default: return ldgi(f);
+        }
+    }
+    // fill the cache from the SoA (kernel entry)
+    __device__ __forceinline__ void load_cold() const {
+        c->beta0 = ldg(F_BETA0);  c->gamma0 = ldg(F_GAMMA0);  c->p0c = ldg(F_P0C);
+        c->charge_ratio = ldg(F_CHARGE_RATIO);  c->ptau = ldg(F_PTAU);  c->rvv = ldg(F_RVV);
+        c->at_turn0 = ldgi(F_AT_TURN);  c->at_element0 = (int32_t) ldgi(F_AT_ELEMENT);
     }
     __device__ __forceinline__ void sti(int f, int64_t v) const {
         reinterpret_cast<int64_t*>(p->field[f])[i] = v;
@@ -134,7 +178,8 @@ __device__ __forceinline__ void pstate_back(PHot& P, const PState& T, const PSlo
 __device__ __forceinline__ void pstate_store(const PState& P, const PSlot& G) {
     G.st(F_X, P.x);  G.st(F_PX, P.px);  G.st(F_Y, P.y);  G.st(F_PY, P.py);
     G.st(F_ZETA, P.zeta);  G.st(F_DELTA, P.delta);  G.st(F_RPP, P.rpp);
-    G.st(F_RVV, P.rvv);  G.st(F_S, P.s);
+    G.stg(F_RVV, P.rvv);  G.st(F_S, P.s);
+    G.stg(F_PTAU, G.c->ptau);
     G.sti(F_AT_TURN, P.at_turn);
     G.sti(F_AT_ELEMENT, (int64_t) P.at_element);
     G.sti(F_STATE, (int64_t) P.state);
