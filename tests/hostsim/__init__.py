@@ -104,3 +104,11 @@ class HostSimTracker(Tracker):
 def build_hostsim_tracker(line):
     line.tracker = HostSimTracker(line)
     return line.tracker
+
+
+def trig_stats(reset=True):
+    """(lookups, misses) of the host-tabulated element trigonometry since the last reset."""
+    lib = load()
+    a, b = ct.c_longlong(0), ct.c_longlong(0)
+    lib.xtb_hostsim_trig_stats(ct.byref(a), ct.byref(b), int(reset))
+    return a.value, b.value

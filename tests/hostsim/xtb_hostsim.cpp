@@ -31,7 +31,15 @@ using std::max;
 using std::min;
 
 #define XTB_WITH_HEAVY
+#define XTB_COUNT_TRIG_MISS
 #include "../../xtrack_b200/csrc/xtb_interp.cuh"
+
+// (test hook) lookups / misses of the host-tabulated element trigonometry (xtb_thick.cuh)
+extern "C" void xtb_hostsim_trig_stats(long long* lookups, long long* misses, int reset) {
+    *lookups = xtb_trig_lookups;
+    *misses = xtb_trig_misses;
+    if (reset) { xtb_trig_lookups = 0;  xtb_trig_misses = 0; }
+}
 
 // Serial restatement of the turn loop of xtb_kernel.cuh around the SHARED op
 // interpreter (xtb_interp.cuh); NPT slots are carried together as in the kernel.

@@ -27,11 +27,16 @@ def _assert_identical(got, ref, fields=common.ALL_F64 + ('state', 'at_turn', 'at
 
 @pytest.mark.parametrize('name', ['hllhc_14', 'sps', 'clic_dr', 'lep'])
 def test_ten_turns_bit_identical(name):
+    hostsim.trig_stats(reset=True)
     line = common.load_line(name)
     p_host = common.gaussian_particles(line, 60, 11, common.SIGMAS[name])
     ref = common.oracle_track(line, p_host, 10 if name != 'lep' else 4)
     got = common.by_id(_track(line, p_host, 10 if name != 'lep' else 4))
     _assert_identical(got, ref)
+    lookups, misses = hostsim.trig_stats()
+    assert misses == 0, (lookups, misses)
+    if name == 'lep':       # 1696 bends x 32 polar drifts per particle-turn, all tabulated
+        assert lookups > 60 * 4 * 1696 * 30
 
 
 def test_ducktrack_golden_full_rings():
@@ -152,7 +157,14 @@ def test_bend_models_and_integrators(model, integrator):
     line.particle_ref = xb.Particles(p0c=3e9)
     p_host = common.gaussian_particles(line, 50, 4, common.SIGMAS['toy'])
     ref = common.oracle_track(line, p_host, 1)
+    hostsim.trig_stats(reset=True)
     _assert_identical(common.by_id(_track(line, p_host, 1)), ref)
+    # every sin/cos of element constants came from the table the lowering computed
+    lookups, misses = hostsim.trig_stats()
+    assert misses == 0, (lookups, misses)
+    if model in ('rot-kick-rot', 'bend-kick-bend', 'full', 'adaptive', 'rot-kick-rot-low-order',
+                 'rot-kick-rot-high-order'):
+        assert lookups > 0
 
 
 def test_rbend_models():

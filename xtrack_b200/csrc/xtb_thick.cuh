@@ -23,18 +23,55 @@
 #define XTB_POW4(X) ((X) * (X) * (X) * (X))
 
 // ---------------------------------------------------------------- drifts ----
+// Trigonometry of element constants.  cos(h*s), sin(h*s), sin(h*s/2) in the polar drift and
+// the curved exact bend depend on the element alone, yet the reference evaluates them per
+// particle and per integrator sub-step (a default bend: 32 polar drifts = 96 sin/cos per
+// particle).  The host lowering tabulates them for every sub-step length the integrator of
+// this op will ask for (lowering.py::_trig_table, computed with the host libm -- the one the
+// reference's CPU build uses), keyed by the bit pattern of the length; a length that is not
+// in the table (there should be none) is evaluated here.
+struct TrigTab {
+    const double* t;     // entries of 4 doubles: length, cos(h*s), sin(h*s), sin(0.5*h*s)
+    int n;
+    double rho;          // 1 / h (valid iff n > 0)
+};
+#ifdef XTB_COUNT_TRIG_MISS
+static long long xtb_trig_lookups = 0, xtb_trig_misses = 0;
+#endif
+__device__ __forceinline__ void trig_of(const TrigTab& tt, const double h, const double s,
+                                        double& ca, double& sa, double& sa2) {
+#ifdef XTB_COUNT_TRIG_MISS
+    xtb_trig_lookups++;
+#endif
+    const long long key = __double_as_longlong(s);
+    for (int i = 0; i < tt.n; ++i) {
+        if (__double_as_longlong(tt.t[4 * i]) == key) {
+            ca = tt.t[4 * i + 1];
+            sa = tt.t[4 * i + 2];
+            sa2 = tt.t[4 * i + 3];
+            return;
+        }
+    }
+#ifdef XTB_COUNT_TRIG_MISS
+    xtb_trig_misses++;
+#endif
+    ca = cos(h * s);
+    sa = sin(h * s);
+    sa2 = sin(0.5 * h * s);
+}
+
 // track_polar_drift_single_particle, track_magnet_drift.h:45-87
 template <bool FRZ>
-__device__ __noinline__ void polar_drift(PState& P, const double length, const double h) {
+__device__ __noinline__ void polar_drift(PState& P, const double length, const double h,
+                                         const TrigTab tt) {
     const double rvv = P.rvv;
     const double x = P.x, y = P.y, px = P.px, py = P.py;
     const double s = length;
     const double one_plus_delta = P.delta + 1.0;
     const double pz = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(px) - XTB_POW2(py));
-    const double rho = 1 / h;
-    const double ca = cos(h * s);
-    const double sa = sin(h * s);
-    const double sa2 = sin(0.5 * h * s);
+    const double rho = (tt.n > 0) ? tt.rho : 1 / h;
+    double ca, sa, sa2;
+    trig_of(tt, h, s, ca, sa, sa2);
     const double _pz = 1 / pz;
     const double pxt = px * _pz;
     const double _ptt = 1 / (ca - sa * pxt);
@@ -133,10 +170,10 @@ __device__ __noinline__ void combined_dipole_quad(PState& P, const double length
 // track_curved_exact_bend_single_particle, track_magnet_drift.h:272-345
 template <bool FRZ>
 __device__ __noinline__ void curved_exact_bend(PState& P, const double length, const double k0,
-                                               const double h) {
+                                               const double h, const TrigTab tt) {
     const double k0_chi = k0 * P.chi;
     if (fabs(k0_chi) < 1e-8) {
-        polar_drift<FRZ>(P, length, h);
+        polar_drift<FRZ>(P, length, h, tt);
         return;
     }
     const double rvv = P.rvv;
@@ -144,9 +181,9 @@ __device__ __noinline__ void curved_exact_bend(PState& P, const double length, c
     const double s = length;
     const double one_plus_delta = P.delta + 1.0;
     const double hs = h * s;
-    const double sin_hs = sin(hs);
-    const double cos_hs = cos(hs);
-    const double sin_hs_2 = sin(hs / 2);
+    // (sin(hs / 2) == sin(0.5 * h * s): halving is exact)
+    double cos_hs, sin_hs, sin_hs_2;
+    trig_of(tt, h, s, cos_hs, sin_hs, sin_hs_2);
     const double pz0 = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(px0) - XTB_POW2(py));
     const double C = pz0 - k0_chi * ((1.0 / h) + x0);
     const double pxs = px0 * cos_hs + C * sin_hs;
@@ -202,45 +239,46 @@ __device__ __noinline__ void straight_exact_bend(PState& P, const double length,
 // track_magnet_drift_single_particle, track_magnet_drift.h:468-555
 template <bool FRZ>
 __device__ __forceinline__ void magnet_drift(PState& P, const double length, const double k0,
-                                             const double k1, const double h, const int drift_model) {
+                                             const double k1, const double h, const int drift_model,
+                                             const TrigTab tt) {
     if (drift_model == -1) return;
     if (length == 0.0) return;
     switch (drift_model) {
     case 0: drift_expanded<FRZ>(P, length); break;
     case 1: drift_exact<FRZ>(P, length); break;
-    case 2: polar_drift<FRZ>(P, length, h); break;
+    case 2: polar_drift<FRZ>(P, length, h, tt); break;
     case 3: combined_dipole_quad<FRZ>(P, length, k0, k1, h); break;
-    case 4: curved_exact_bend<FRZ>(P, length, k0, h); break;
+    case 4: curved_exact_bend<FRZ>(P, length, k0, h, tt); break;
     case 5: straight_exact_bend<FRZ>(P, length, k0); break;
     case 7:
-        polar_drift<FRZ>(P, 0.6756035959798289 * length, h);
+        polar_drift<FRZ>(P, 0.6756035959798289 * length, h, tt);
         P.px = P.px - 1.3512071919596578 * k0 * P.chi * length;
-        polar_drift<FRZ>(P, -0.17560359597982889 * length, h);
+        polar_drift<FRZ>(P, -0.17560359597982889 * length, h, tt);
         P.px = P.px - (-1.7024143839193155) * k0 * P.chi * length;
-        polar_drift<FRZ>(P, -0.17560359597982889 * length, h);
+        polar_drift<FRZ>(P, -0.17560359597982889 * length, h, tt);
         P.px = P.px - 1.3512071919596578 * k0 * P.chi * length;
-        polar_drift<FRZ>(P, 0.6756035959798289 * length, h);
+        polar_drift<FRZ>(P, 0.6756035959798289 * length, h, tt);
         break;
     case 8: {
         const double d[4] = {3.922568052387799819591407413100e-01, 5.100434119184584780271052295575e-01,
                              -4.710533854097565531482416645304e-01, 6.875316825251809316199569366290e-02};
         const double k[4] = {7.845136104775599639182814826199e-01, 2.355732133593569921359289764951e-01,
                              -1.177679984178870098432412305556e+00, 1.315186320683906284756403692882e+00};
-        polar_drift<FRZ>(P, d[0] * length, h);
+        polar_drift<FRZ>(P, d[0] * length, h, tt);
         P.px = P.px - k[0] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[1] * length, h);
+        polar_drift<FRZ>(P, d[1] * length, h, tt);
         P.px = P.px - k[1] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[2] * length, h);
+        polar_drift<FRZ>(P, d[2] * length, h, tt);
         P.px = P.px - k[2] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[3] * length, h);
+        polar_drift<FRZ>(P, d[3] * length, h, tt);
         P.px = P.px - k[3] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[3] * length, h);
+        polar_drift<FRZ>(P, d[3] * length, h, tt);
         P.px = P.px - k[2] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[2] * length, h);
+        polar_drift<FRZ>(P, d[2] * length, h, tt);
         P.px = P.px - k[1] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[1] * length, h);
+        polar_drift<FRZ>(P, d[1] * length, h, tt);
         P.px = P.px - k[0] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[0] * length, h);
+        polar_drift<FRZ>(P, d[0] * length, h, tt);
         break;
     }
     default: break;
@@ -254,7 +292,8 @@ __device__ __forceinline__ void magnet_drift(PState& P, const double length, con
 //  q[8] htot    q[9] (int) order_user | order_rel << 32
 //  q[10..17] k0_tot k1_tot k2 k3 k0s k1s k2s k3s   (field evaluation for radiation)
 //  q[18..25] main coefficients (order 3, Horner order, pairs)
-//  then user coefficients (order_user+1 pairs), then rel coefficients (order_rel+1 pairs)
+//  then user coefficients (order_user+1 pairs), then rel coefficients (order_rel+1 pairs),
+//  then the trig table: (int) n, 1/h, n x [length, cos(h*s), sin(h*s), sin(h*s/2)]
 //  aux: integrator[0:2] drift_model+1[2:6] rot_frame[6] has_user[7] has_rel[8]
 //       has_main[9] radiation_flag[10:12] drift_only[12] num_kicks[13:32]
 struct BodyPar {
@@ -265,6 +304,7 @@ struct BodyPar {
     int order_user, order_rel;
     int integrator, drift_model, rot_frame, has_user, has_rel, has_main, radiation_flag, drift_only;
     int num_kicks;
+    TrigTab trig;
 };
 
 __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) {
@@ -276,6 +316,10 @@ __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) 
     b.cm = q + 18;
     b.cu = b.cm + 8;
     b.cr = b.cu + 2 * (b.order_user + 1);
+    const double* tq = b.cr + 2 * (b.order_rel + 1);
+    b.trig.n = (int) __double_as_longlong(tq[0]);
+    b.trig.rho = tq[1];
+    b.trig.t = tq + 2;
     const uint32_t a = (uint32_t) aux;
     b.integrator = a & 3;
     b.drift_model = (int) ((a >> 2) & 15) - 1;
@@ -670,7 +714,7 @@ __device__ __noinline__ void magnet_body(PState& P, const PSlot& G, const XtbTra
     const double length = q[0], k0d = q[1], k1d = q[2], hd = q[3];
     const int dm = b.drift_model;
     RadSnapshot snap;
-#define XTB_DRIFT(dl) magnet_drift<FRZ>(P, (dl), k0d, k1d, hd, dm)
+#define XTB_DRIFT(dl) magnet_drift<FRZ>(P, (dl), k0d, k1d, hd, dm, b.trig)
 #define XTB_KICK(w) magnet_kick<FRZ>(P, b, (w))
     if (b.drift_only) {
         rad_begin<SYNRAD>(snap, P);

@@ -754,11 +754,14 @@ def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl,
                 coeffs_rel = [0.0, 0.0]
             ou = len(coeffs) // 2 - 1
             orl = len(coeffs_rel) // 2 - 1
+            trig = _trig_table(c['drift_model'], integrator, num_multipole_kicks, drift_only,
+                               core_length, c['h_drift'])
             params = [core_length, c['k0_drift'], c['k1_drift'], c['h_drift'], c['h_kick'], hxl,
                       a0, a1, htot, _RawWord(ou | (orl << 32)),
                       c['k0_drift'] + c['k0_kick'], c['k1_drift'] + c['k1_kick'], k2, k3,
                       k0s, k1s, k2s, k3s,
-                      *coeffs_main, *coeffs, *coeffs_rel]
+                      *coeffs_main, *coeffs, *coeffs_rel,
+                      _RawWord(len(trig) // 4), (1 / c['h_drift']) if trig else 0.0, *trig]
             prog.op(OP_MAGNET_BODY, params, aux=aux,
                     flops=_body_flops(c['drift_model'], integrator, num_multipole_kicks,
                                       drift_only, ou, coeffs_main),
@@ -775,6 +778,61 @@ def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl,
         if rbend_model == 2:
             prog.op(OP_ADD_X, [-x0_out])
             prog.op(OP_YROT, [-sin_theta_out, cos_theta_out, -sin_theta_out / cos_theta_out])
+
+
+_YOSHIDA_D = (3.922568052387799819591407413100e-01, 5.100434119184584780271052295575e-01,
+              -4.710533854097565531482416645304e-01, 6.875316825251809316199569366290e-02)
+
+
+def _body_drift_lengths(integrator, n_kicks, drift_only, length):
+    """The distinct lengths the integrator loops of csrc/xtb_thick.cuh::magnet_body
+    (track_magnet.h:181-276) pass to the drift map, computed with the same operations."""
+    if drift_only:
+        return [length]
+    if integrator == 1:
+        edge_w, inside_w = 0.5, 0.0
+        if n_kicks > 1:
+            edge_w = 1. / (2 * (1 + n_kicks))
+            inside_w = float(n_kicks) / (float(n_kicks * n_kicks) - 1)
+        out = [edge_w * length]
+        if n_kicks > 1:
+            out.append(inside_w * length)
+        return out
+    if integrator == 3:
+        drift_weight = 1. / n_kicks
+        return [0.5 * drift_weight * length]
+    n_slices = n_kicks // 7 + (1 if n_kicks % 7 else 0)
+    slice_length = length / n_slices
+    return [slice_length * d for d in _YOSHIDA_D]
+
+
+def _trig_table(drift_model, integrator, n_kicks, drift_only, length, h):
+    """cos(h*s), sin(h*s), sin(h*s/2) for every length s that the polar drift / curved exact
+    bend of this body op will be called with (track_magnet_drift.h:45-87, 272-345, 521-550):
+    element constants that the reference evaluates per particle.  Flat list of
+    [s, cos, sin, sin_half] entries; evaluated with the C library's libm (math.*), the one
+    the reference's CPU build links."""
+    if drift_model not in (2, 4, 7, 8) or h == 0.0:
+        return []
+    lengths = []
+    for dl in _body_drift_lengths(integrator, n_kicks, drift_only, length):
+        if dl == 0.0:
+            continue
+        if drift_model in (2, 4):
+            lengths.append(dl)
+        elif drift_model == 7:
+            lengths += [0.6756035959798289 * dl, -0.17560359597982889 * dl]
+        else:
+            lengths += [d * dl for d in _YOSHIDA_D]
+    out, seen = [], set()
+    for s in lengths:
+        if s in seen:
+            continue
+        seen.add(s)
+        out += [s, math.cos(h * s), math.sin(h * s), math.sin(0.5 * h * s)]
+    if len(out) // 4 > 24:      # (long uniform splittings repeat one length: never reached)
+        return []
+    return out
 
 
 _DRIFT_FLOPS = {-1: 0, 0: 17, 1: 21, 2: 45, 3: 95, 4: 60, 5: 40, 7: 4 * 45 + 9, 8: 8 * 45 + 21}
