@@ -110,6 +110,14 @@ SPECS = {
                       isthick=False, rot_shift=False),
     'XYShift': dict(header='xyshift.h', fields=[('dx', 'f64'), ('dy', 'f64')],
                     isthick=False, rot_shift=False),
+    # rotation.py:29-36, translation.py:27-30
+    'Rotation': dict(header='rotation.h',
+                     fields=[('rot_s_rad', 'f64'), ('rot_x_rad', 'f64'), ('rot_y_rad', 'f64'),
+                             ('_first_rot', 'i64'), ('_second_rot', 'i64'), ('_third_rot', 'i64')],
+                     isthick=False, rot_shift=False),
+    'Translation': dict(header='translation.h',
+                        fields=[('shift_x', 'f64'), ('shift_y', 'f64')],
+                        isthick=False, rot_shift=False),
     'LimitRect': dict(header='limitrect.h',
                       fields=[('min_x', 'f64'), ('max_x', 'f64'), ('min_y', 'f64'),
                               ('max_y', 'f64')],

@@ -289,3 +289,25 @@ def test_oracle_openmp_builds_equal_serial():
             assert np.array_equal(a[ff], b[ff]), ff
         # with losses, parallel=True falls back to the serial build
         _assert_identical(common.oracle_track(line, p_host, 4, variant=variant, parallel=True), a)
+
+
+def test_rotation_and_translation_elements():
+    """`Rotation` / `Translation` (they supersede the deprecated
+    SRotation / XYShift; elements_src/rotation.h:13-60, translation.h:13-26), every rotation
+    order, zero angles skipped."""
+    els = []
+    for seq in ('yxs', 'xys', 'sxy', 'syx'):
+        els += [xb.Drift(length=0.5),
+                xb.Rotation(rot_s_rad=0.02, rot_x_rad=-3e-3, rot_y_rad=2e-3, seq=seq),
+                xb.Translation(shift_x=1e-4, shift_y=-2e-4)]
+    els += [xb.Rotation(rot_s_rad=0.3), xb.Rotation(rot_y_rad=1e-3), xb.Rotation(),
+            xb.Multipole(knl=[0, 0.1])]
+    line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=3e9)
+    p_host = common.gaussian_particles(line, 100, 4, common.SIGMAS['toy'])
+    ref = common.oracle_track(line, p_host, 2)
+    _assert_identical(common.by_id(_track(line, p_host, 2)), ref)
+    # round trip through the dictionary form
+    line2 = xb.Line.from_dict(line.to_dict()) if hasattr(line, 'to_dict') else line
+    line2.particle_ref = line.particle_ref
+    _assert_identical(common.by_id(_track(line2, p_host, 2)), ref)

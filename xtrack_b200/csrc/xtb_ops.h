@@ -112,7 +112,9 @@
 #define XTB_NOT_ADDRESSABLE 0xffffffffu
 
 /* tiling of the program through shared memory */
-#define XTB_TILE_WORDS   1024      /* 8 KiB per tile                                  */
+#ifndef XTB_TILE_WORDS
+#define XTB_TILE_WORDS   1024      /* 8 KiB per tile (>= TILE_WORDS of lowering.py)   */
+#endif
 #define XTB_NUM_BUF      2
 
 #endif /* XTB_OPS_H */

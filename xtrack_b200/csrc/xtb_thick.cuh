@@ -62,8 +62,8 @@ __device__ __forceinline__ void trig_of(const TrigTab& tt, const double h, const
 
 // track_polar_drift_single_particle, track_magnet_drift.h:45-87
 template <bool FRZ>
-__device__ __noinline__ void polar_drift(PState& P, const double length, const double h,
-                                         const TrigTab tt) {
+__device__ __forceinline__ void polar_drift(PState& P, const double length, const double h,
+                                            const TrigTab tt) {
     const double rvv = P.rvv;
     const double x = P.x, y = P.y, px = P.px, py = P.py;
     const double s = length;
@@ -238,7 +238,7 @@ __device__ __noinline__ void straight_exact_bend(PState& P, const double length,
 
 // track_magnet_drift_single_particle, track_magnet_drift.h:468-555
 template <bool FRZ>
-__device__ __forceinline__ void magnet_drift(PState& P, const double length, const double k0,
+__device__ __noinline__ void magnet_drift(PState& P, const double length, const double k0,
                                              const double k1, const double h, const int drift_model,
                                              const TrigTab tt) {
     if (drift_model == -1) return;
@@ -250,35 +250,35 @@ __device__ __forceinline__ void magnet_drift(PState& P, const double length, con
     case 3: combined_dipole_quad<FRZ>(P, length, k0, k1, h); break;
     case 4: curved_exact_bend<FRZ>(P, length, k0, h, tt); break;
     case 5: straight_exact_bend<FRZ>(P, length, k0); break;
-    case 7:
-        polar_drift<FRZ>(P, 0.6756035959798289 * length, h, tt);
-        P.px = P.px - 1.3512071919596578 * k0 * P.chi * length;
-        polar_drift<FRZ>(P, -0.17560359597982889 * length, h, tt);
-        P.px = P.px - (-1.7024143839193155) * k0 * P.chi * length;
-        polar_drift<FRZ>(P, -0.17560359597982889 * length, h, tt);
-        P.px = P.px - 1.3512071919596578 * k0 * P.chi * length;
-        polar_drift<FRZ>(P, 0.6756035959798289 * length, h, tt);
+    case 7: {
+        // nested Yoshida-4 bend, track_magnet_drift.h:521-531.  One inlined polar drift in a
+        // loop over the step table (not 4 copies): the thick kernels are bound by instruction
+        // fetch and local-memory traffic, not by arithmetic (profiles/r01_ncu_lep.md)
+        const double pd[4] = {0.6756035959798289, -0.17560359597982889, -0.17560359597982889,
+                              0.6756035959798289};
+        const double pk[4] = {1.3512071919596578, -1.7024143839193155, 1.3512071919596578, 0.};
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            polar_drift<FRZ>(P, pd[j] * length, h, tt);
+            if (j < 3) P.px = P.px - pk[j] * k0 * P.chi * length;
+        }
         break;
+    }
     case 8: {
-        const double d[4] = {3.922568052387799819591407413100e-01, 5.100434119184584780271052295575e-01,
-                             -4.710533854097565531482416645304e-01, 6.875316825251809316199569366290e-02};
-        const double k[4] = {7.845136104775599639182814826199e-01, 2.355732133593569921359289764951e-01,
-                             -1.177679984178870098432412305556e+00, 1.315186320683906284756403692882e+00};
-        polar_drift<FRZ>(P, d[0] * length, h, tt);
-        P.px = P.px - k[0] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[1] * length, h, tt);
-        P.px = P.px - k[1] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[2] * length, h, tt);
-        P.px = P.px - k[2] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[3] * length, h, tt);
-        P.px = P.px - k[3] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[3] * length, h, tt);
-        P.px = P.px - k[2] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[2] * length, h, tt);
-        P.px = P.px - k[1] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[1] * length, h, tt);
-        P.px = P.px - k[0] * k0 * P.chi * length;
-        polar_drift<FRZ>(P, d[0] * length, h, tt);
+        // nested Yoshida-6 bend, track_magnet_drift.h:532-550
+        const double d[8] = {3.922568052387799819591407413100e-01, 5.100434119184584780271052295575e-01,
+                             -4.710533854097565531482416645304e-01, 6.875316825251809316199569366290e-02,
+                             6.875316825251809316199569366290e-02, -4.710533854097565531482416645304e-01,
+                             5.100434119184584780271052295575e-01, 3.922568052387799819591407413100e-01};
+        const double k[8] = {7.845136104775599639182814826199e-01, 2.355732133593569921359289764951e-01,
+                             -1.177679984178870098432412305556e+00, 1.315186320683906284756403692882e+00,
+                             -1.177679984178870098432412305556e+00, 2.355732133593569921359289764951e-01,
+                             7.845136104775599639182814826199e-01, 0.};
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            polar_drift<FRZ>(P, d[j] * length, h, tt);
+            if (j < 7) P.px = P.px - k[j] * k0 * P.chi * length;
+        }
         break;
     }
     default: break;
@@ -335,7 +335,7 @@ __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) 
 
 // track_magnet_kick_single_particle, track_magnet_kick.h:24-144
 template <bool FRZ>
-__device__ __forceinline__ void magnet_kick(PState& P, const BodyPar& b, const double kick_weight) {
+__device__ __noinline__ void magnet_kick(PState& P, const BodyPar& b, const double kick_weight) {
     const double chi = P.chi, x = P.x, y = P.y;
     const double length = b.q[0];
     double m, n;
@@ -758,16 +758,15 @@ __device__ __noinline__ void magnet_body(PState& P, const PSlot& G, const XtbTra
                      d2 = -4.710533854097565531482416645304e-01, d3 = 6.875316825251809316199569366290e-02;
         const double y0 = 7.845136104775599639182814826199e-01, y1 = 2.355732133593569921359289764951e-01,
                      y2 = -1.177679984178870098432412305556e+00, y3 = 1.315186320683906284756403692882e+00;
+        const double yd[8] = {d0, d1, d2, d3, d3, d2, d1, d0};
+        const double yk[8] = {y0, y1, y2, y3, y2, y1, y0, 0.};
         for (int ii = 0; ii < num_slices; ++ii) {
             rad_begin<SYNRAD>(snap, P);
-            XTB_DRIFT(slice_length * d0);  XTB_KICK(kick_weight * y0);
-            XTB_DRIFT(slice_length * d1);  XTB_KICK(kick_weight * y1);
-            XTB_DRIFT(slice_length * d2);  XTB_KICK(kick_weight * y2);
-            XTB_DRIFT(slice_length * d3);  XTB_KICK(kick_weight * y3);
-            XTB_DRIFT(slice_length * d3);  XTB_KICK(kick_weight * y2);
-            XTB_DRIFT(slice_length * d2);  XTB_KICK(kick_weight * y1);
-            XTB_DRIFT(slice_length * d1);  XTB_KICK(kick_weight * y0);
-            XTB_DRIFT(slice_length * d0);
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {       // one copy of the drift and kick bodies
+                XTB_DRIFT(slice_length * yd[j]);
+                if (j < 7) XTB_KICK(kick_weight * yk[j]);
+            }
             rad_end<SYNRAD, FRZ>(snap, P, G, a, b, slice_length);
         }
     }

@@ -529,6 +529,47 @@ class XYShift(BeamElement):
         self._finish(kwargs)
 
 
+class Translation(BeamElement):
+    """beam_elements/translation.py:15-40, elements_src/translation.h:13-26 (supersedes the
+    deprecated XYShift)."""
+    allow_rot_and_shift = False
+    has_backtrack = True
+
+    def __init__(self, shift_x=0.0, shift_y=0.0, **kwargs):
+        self.shift_x = float(shift_x)
+        self.shift_y = float(shift_y)
+        self._finish(kwargs)
+
+
+class Rotation(BeamElement):
+    """beam_elements/rotation.py:14-100, elements_src/rotation.h:13-60: up to three frame
+    rotations about x, y, s in the order `seq` (default 'yxs'); zero angles are skipped."""
+    allow_rot_and_shift = False
+    has_backtrack = True
+    _AXIS = {'x': 0, 'y': 1, 's': 2}
+
+    def __init__(self, rot_s_rad=0.0, rot_x_rad=0.0, rot_y_rad=0.0, seq='yxs', **kwargs):
+        self.rot_s_rad = float(rot_s_rad)
+        self.rot_x_rad = float(rot_x_rad)
+        self.rot_y_rad = float(rot_y_rad)
+        if sorted(seq) != ['s', 'x', 'y']:
+            raise ValueError("seq must be a permutation of 'x', 'y', 's'")
+        self.seq = seq
+        self._finish(kwargs)
+
+    @property
+    def _first_rot(self):
+        return self._AXIS[self.seq[0]]
+
+    @property
+    def _second_rot(self):
+        return self._AXIS[self.seq[1]]
+
+    @property
+    def _third_rot(self):
+        return self._AXIS[self.seq[2]]
+
+
 class LimitRect(BeamElement):
     has_backtrack = True
 
@@ -585,5 +626,5 @@ class _Placeholder(Marker):
 
 ELEMENT_CLASSES = {cls.__name__: cls for cls in (
     Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupole, Octupole, Bend,
-    RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, LimitRect, LimitEllipse,
+    RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation, LimitRect, LimitEllipse,
     LimitPolygon)}

@@ -1095,6 +1095,23 @@ def lower_element(prog, el, cfg):
         prog.op(OP_XYSHIFT, [el.dx, el.dy])
         return False
 
+    if name == 'Translation':           # elements_src/translation.h:13-26
+        prog.op(OP_XYSHIFT, [el.shift_x, el.shift_y])
+        return False
+
+    if name == 'Rotation':              # elements_src/rotation.h:13-60
+        for axis in (el._first_rot, el._second_rot, el._third_rot):
+            if axis == 0 and el.rot_x_rad != 0.0:
+                aa = el.rot_x_rad
+                prog.op(OP_XROT, [math.sin(aa), math.cos(aa), math.tan(aa)])
+            elif axis == 1 and el.rot_y_rad != 0.0:
+                aa = el.rot_y_rad
+                prog.op(OP_YROT, [math.sin(aa), math.cos(aa), math.tan(aa)])
+            elif axis == 2 and el.rot_s_rad != 0.0:
+                aa = el.rot_s_rad
+                prog.op(OP_SROT, [math.sin(aa), math.cos(aa)])
+        return False
+
     if name == 'LimitRect':
         _with_transformations(prog, el, lambda: prog.op(
             OP_LIMIT_RECT, [el.min_x, el.max_x, el.min_y, el.max_y]))
