@@ -44,10 +44,16 @@ WORKLOADS = {
     'hllhc_da': ('hllhc_14', 'HL-LHC thin DA (hllhc_14 stand-in, BB->Marker), polar grid'),
     'sps_apertures': ('sps', 'SPS thin lattice with LimitRect/LimitEllipse, Gaussian beam'),
     'lep_thick': ('lep', 'LEP thick lattice (RBend/Quadrupole/Sextupole), Gaussian beam'),
+    # BASELINE.json configs[3] stand-ins: synchrotron radiation with quantum excitation,
+    # per-particle Tausworthe generator (configure_radiation('quantum'))
+    'clic_dr_quantum': ('clic_dr', 'CLIC-DR thin lattice, quantum synchrotron radiation, '
+                                   'Gaussian beam'),
+    'lep_quantum': ('lep', 'LEP thick lattice, quantum synchrotron radiation, Gaussian beam'),
 }
+RADIATION = {'clic_dr_quantum': 'quantum', 'lep_quantum': 'quantum'}
 
 
-def load_line(fixture):
+def load_line(fixture, radiation=None):
     import gzip
     import xtrack_b200 as xb
     with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'lattices', fixture + '.json.gz'),
@@ -56,6 +62,8 @@ def load_line(fixture):
     line = xb.Line.from_dict(dd, replace_unsupported=True)
     if line.particle_ref is None and 'particle' in dd:
         line.particle_ref = xb.Particles.from_dict(dd['particle'])
+    if radiation:
+        line.configure_radiation(model=radiation)
     return line
 
 
@@ -75,6 +83,8 @@ def initial_conditions(workload, line, n, rank):
     rng = np.random.default_rng(100 + rank)
     if workload == 'sps_apertures':
         sig = dict(x=4e-3, px=1e-4, y=2e-3, py=1e-4, zeta=0.2, delta=1e-3)
+    elif workload == 'clic_dr_quantum':
+        sig = dict(x=1e-4, px=2e-5, y=2e-5, py=4e-6, zeta=2e-3, delta=1e-3)
     else:
         sig = dict(x=2e-4, px=2e-6, y=5e-5, py=1e-6, zeta=5e-3, delta=3e-4)
     return {kk: rng.normal(0, vv, n) for kk, vv in sig.items()}
@@ -135,15 +145,22 @@ def cpu_reference_run(workload, line, n_particles, target_seconds, warm=True):
     ic = initial_conditions(workload, line, n_particles, 0)
     p = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0, **ic)
     re = ro.RefElements(line.elements)
-    cores = ro.load('omp').xt_ref_num_threads()
+    variant = 'synrad_omp' if workload in RADIATION else 'omp'
+    cores = ro.load(variant).xt_ref_num_threads()
     kw = dict(ele_start=0, num_ele_track=len(line), flag_end_turn_actions=1,
-              flag_reset_s_at_end_turn=1, line_length=line.get_length(), variant='omp')
+              flag_reset_s_at_end_turn=1, line_length=line.get_length(), variant=variant)
     hp = ro.HostParticles.from_particles(p)
+    if workload in RADIATION:
+        ro.init_rand_gen(hp, np.arange(1, n_particles + 1, dtype=np.uint32), variant=variant)
+        p = None
     t0 = time.perf_counter()
     ro.track_line(hp, re, num_turns=1, **kw)          # warm-up turn, also calibrates
     t_turn = time.perf_counter() - t0
     turns = max(2, int(target_seconds / max(t_turn, 1e-6)))
-    hp = ro.HostParticles.from_particles(p)
+    if p is not None:
+        hp = ro.HostParticles.from_particles(p)
+    else:       # (radiation: go on from the warmed-up, seeded beam)
+        hp.arrays['at_turn'][:] = 0
     t0 = time.perf_counter()
     ro.track_line(hp, re, num_turns=turns, **kw)
     dt = time.perf_counter() - t0
@@ -185,7 +202,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        line = load_line(fixture)
+        line = load_line(fixture, RADIATION.get(args.workload))
         config['n_elements'] = len(line)
         vals = []
         for ii in range(args.warmup + args.steps):
@@ -218,7 +235,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    line = load_line(fixture)
+    line = load_line(fixture, RADIATION.get(args.workload))
     n_el = len(line)
     config['n_elements'] = n_el
     ref = line.particle_ref

@@ -24,8 +24,9 @@
 
 // Launch shape (measured on B200, profiles/r01_history.md): 128 threads, 4 blocks per SM for
 // the thin kernels (128 registers per thread, 16 warps per SM; smaller blocks desynchronise
-// the warps of an SM sub-partition a little better than 256 x 2), 2 blocks per SM for the
-// register-hungry thick kernels (<= 255 registers per thread, 8 warps per SM).
+// the warps of an SM sub-partition a little better than 256 x 2), and 4 blocks per SM for
+// the thick kernels too: they are bound by dependent division / square-root chains, and 16
+// warps per SM at 128 registers (a few spills) beat 8 warps at 246 registers by 25 %.
 #ifndef XTB_THREADS
 #define XTB_THREADS 128
 #endif
@@ -33,7 +34,7 @@
 #define XTB_THIN_BLOCKS_PER_SM 4
 #endif
 #ifndef XTB_HEAVY_BLOCKS_PER_SM
-#define XTB_HEAVY_BLOCKS_PER_SM 2
+#define XTB_HEAVY_BLOCKS_PER_SM 4
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -16,6 +16,20 @@
 #include "xtb_state.cuh"
 #include "xtb_thin.cuh"
 
+// Inlining of the thick-body pieces (tuning knob, measured in profiles/r01_history.md):
+//   0  polar drift inlined into ONE drift function, drift and kick out of line
+//   1  drift and kick inlined into the integrator loops, polar drift out of line
+#ifndef XTB_THICK_INLINE_MODE
+#define XTB_THICK_INLINE_MODE 1
+#endif
+#if XTB_THICK_INLINE_MODE == 0
+#define XTB_POLAR_INLINE __forceinline__
+#define XTB_DRIFTKICK_INLINE __noinline__
+#else
+#define XTB_POLAR_INLINE __noinline__
+#define XTB_DRIFTKICK_INLINE __forceinline__
+#endif
+
 #define XTB_QELEM 1.60217662e-19
 #define XTB_EPSILON_0 8.854187817620e-12
 #define XTB_POW2(X) ((X) * (X))
@@ -62,8 +76,8 @@ __device__ __forceinline__ void trig_of(const TrigTab& tt, const double h, const
 
 // track_polar_drift_single_particle, track_magnet_drift.h:45-87
 template <bool FRZ>
-__device__ __forceinline__ void polar_drift(PState& P, const double length, const double h,
-                                            const TrigTab tt) {
+__device__ XTB_POLAR_INLINE void polar_drift(PState& P, const double length, const double h,
+                                             const TrigTab tt) {
     const double rvv = P.rvv;
     const double x = P.x, y = P.y, px = P.px, py = P.py;
     const double s = length;
@@ -238,7 +252,7 @@ __device__ __noinline__ void straight_exact_bend(PState& P, const double length,
 
 // track_magnet_drift_single_particle, track_magnet_drift.h:468-555
 template <bool FRZ>
-__device__ __noinline__ void magnet_drift(PState& P, const double length, const double k0,
+__device__ XTB_DRIFTKICK_INLINE void magnet_drift(PState& P, const double length, const double k0,
                                              const double k1, const double h, const int drift_model,
                                              const TrigTab tt) {
     if (drift_model == -1) return;
@@ -335,7 +349,7 @@ __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) 
 
 // track_magnet_kick_single_particle, track_magnet_kick.h:24-144
 template <bool FRZ>
-__device__ __noinline__ void magnet_kick(PState& P, const BodyPar& b, const double kick_weight) {
+__device__ XTB_DRIFTKICK_INLINE void magnet_kick(PState& P, const BodyPar& b, const double kick_weight) {
     const double chi = P.chi, x = P.x, y = P.y;
     const double length = b.q[0];
     double m, n;
