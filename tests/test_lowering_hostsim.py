@@ -311,3 +311,31 @@ def test_rotation_and_translation_elements():
     line2 = xb.Line.from_dict(line.to_dict()) if hasattr(line, 'to_dict') else line
     line2.particle_ref = line.particle_ref
     _assert_identical(common.by_id(_track(line2, p_host, 2)), ref)
+
+
+@pytest.mark.parametrize('name', ['hllhc_14', 'sps'])
+def test_optimize_for_tracking(name):
+    """`Line.optimize_for_tracking` (line.py:4951-5026): markers, inactive multipoles and
+    zero-length drifts removed, consecutive drifts / multipoles merged, redundant apertures
+    dropped.  The optimised line is tracked bit-identically to the reference tracking the SAME
+    optimised element list, and agrees with the unoptimised line to rounding (merged drift
+    lengths round once instead of twice)."""
+    line = common.load_line(name)
+    n0 = len(line)
+    p_host = common.gaussian_particles(line, 40, 11, common.SIGMAS[name])
+    ref_plain = common.oracle_track(line, p_host, 5)
+    length0 = line.get_length()
+    line.optimize_for_tracking()
+    n1 = len(line)
+    assert n1 < n0
+    cls = {type(ee).__name__ for ee in line.elements}
+    assert 'Marker' not in cls
+    names = [type(ee).__name__ for ee in line.elements]
+    assert not any(a == b == 'Drift' for a, b in zip(names, names[1:]))
+    assert abs(line.get_length() - length0) < 1e-9 * length0
+    ref_opt = common.oracle_track(line, p_host, 5)
+    got = common.by_id(_track(line, p_host, 5))
+    _assert_identical(got, ref_opt, fields=common.ALL_F64 + ('state', 'at_turn'))
+    dev = common.max_rel_dev(got, ref_plain)
+    assert max(dev.values()) < 1e-8, dev
+    print(name, n0, '->', n1, 'elements; dev vs unoptimised', max(dev.values()))

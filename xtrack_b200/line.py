@@ -192,6 +192,40 @@ class Line:
     def _invalidate(self):
         self.tracker = None
 
+    # -- clean-up passes (xtrack/line.py:4951-5683; see optimize.py) --------
+    def optimize_for_tracking(self, compile=True, verbose=False, keep_markers=False):
+        from . import optimize
+        dev = self.tracker.device if self.tracker is not None else None
+        optimize.optimize_for_tracking(self, keep_markers=keep_markers, verbose=verbose)
+        if dev is not None and compile and dev.type == 'cuda':
+            self.build_tracker(_device=dev)
+        return self
+
+    def remove_markers(self, inplace=True, keep=None):
+        from . import optimize
+        return optimize.remove_markers(self, keep=keep)
+
+    def remove_inactive_multipoles(self, inplace=True, keep=None):
+        from . import optimize
+        return optimize.remove_inactive_multipoles(self, keep=keep)
+
+    def remove_zero_length_drifts(self, inplace=True, keep=None):
+        from . import optimize
+        return optimize.remove_zero_length_drifts(self, keep=keep)
+
+    def merge_consecutive_drifts(self, inplace=True, keep=None):
+        from . import optimize
+        return optimize.merge_consecutive_drifts(self, keep=keep)
+
+    def merge_consecutive_multipoles(self, inplace=True, keep=None):
+        from . import optimize
+        return optimize.merge_consecutive_multipoles(self, keep=keep)
+
+    def remove_redundant_apertures(self, inplace=True, keep=None, drifts_that_need_aperture=()):
+        from . import optimize
+        return optimize.remove_redundant_apertures(
+            self, keep=keep, drifts_that_need_aperture=drifts_that_need_aperture)
+
     # -- tracking ----------------------------------------------------------
     def build_tracker(self, _device=None, **kwargs):
         """Lowers the lattice and uploads it to the GPU (replaces
