@@ -146,6 +146,12 @@ def cpu_reference_run(workload, line, n_particles, target_seconds, warm=True):
     p = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0, **ic)
     re = ro.RefElements(line.elements)
     variant = 'synrad_omp' if workload in RADIATION else 'omp'
+    # all the host cores this process may use (torchrun pins OMP_NUM_THREADS=1 in its workers)
+    try:
+        n_host = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_host = os.cpu_count() or 1
+    ro.load(variant).xt_ref_set_num_threads(n_host)
     cores = ro.load(variant).xt_ref_num_threads()
     kw = dict(ele_start=0, num_ele_track=len(line), flag_end_turn_actions=1,
               flag_reset_s_at_end_turn=1, line_length=line.get_length(), variant=variant)
@@ -192,6 +198,18 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    # stdout carries ONE JSON line: anything a library prints there meanwhile (NCCL's version
+    # banner ...) goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     fixture, descr = WORKLOADS[args.workload]
     config = {'workload': f'{args.workload}: {descr}; {args.particles} particles/GPU x '
                           f'{args.turns} turns/step', 'fixture': fixture,
@@ -213,7 +231,7 @@ def main():
         value = float(np.mean([r['value'] for r, _ in vals]))
         res = dict(vals[-1][0])
         res['value'] = value
-        print(json.dumps({
+        emit(({
             'impl': 'reference', 'metric': 'particle-element-turns/s', 'value': value,
             'unit': 'particle-element-turns/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean([d for _, d in vals])),
@@ -302,7 +320,7 @@ def main():
         peak_sustained, peak_burst = _cabi.measure_dfma_peak(local_rank, 0.5)
         achieved = (pet / n_el) * flop_per_turn / (float(np.sum(kernel_ms)) * 1e-3)
         if rank == 0:
-            print(json.dumps({'metric': 'particle-element-turns/s', 'value': value, 'quick': True,
+            emit(({'metric': 'particle-element-turns/s', 'value': value, 'quick': True,
                               'ms_per_step': ms_total / args.steps, 'config': config,
                               'clocks': clocks, 'gpu_launches': int(launches),
                               'kernel_variant': 'fma' if args.fma else 'exact',
@@ -400,7 +418,7 @@ def main():
             cpu = {'value': None, 'unit': 'particle-element-turns/s', 'cores': os.cpu_count(),
                    'kind': 'reference', 'sample': f'unavailable: {err}'}
 
-    print(json.dumps({
+    emit(({
         'metric': 'particle-element-turns/s', 'value': value,
         'unit': 'particle-element-turns/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,

@@ -102,6 +102,7 @@ def load(variant='serial'):
         lib.xt_ref_init_rand_gen.argtypes = [ct.POINTER(ParticlesDataC),
                                              ct.POINTER(ct.c_uint32), ct.c_int]
         lib.xt_ref_num_threads.restype = ct.c_int
+        lib.xt_ref_set_num_threads.argtypes = [ct.c_int]
         _LIBS[variant] = lib
     return _LIBS[variant]
 

@@ -27,6 +27,15 @@ double xtb_oracle_global_xy_limit = 1.0;       /* line.config XTRACK_GLOBAL_XY_L
 
 void xt_ref_set_global_xy_limit(double v){ xtb_oracle_global_xy_limit = v; }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline wants every core */
+void xt_ref_set_num_threads(int n){
+#ifdef XO_CONTEXT_CPU_OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void) n;
+#endif
+}
+
 int xt_ref_num_threads(void){
 #ifdef XO_CONTEXT_CPU_OPENMP
     return omp_get_max_threads();

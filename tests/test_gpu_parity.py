@@ -229,3 +229,54 @@ def test_compaction_keeps_results():
     assert (a['state'] <= 0).sum() > 100
     for ff, _ in xb.Particles.per_particle_vars:
         assert np.array_equal(a[ff], b[ff], equal_nan=True), ff
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] at its full per-GPU size (10^6 particles, hllhc_14 stand-in),
+    through size-independent properties:
+      * a sample of the beam (every 997th particle) against the oracle, the 1e-12 bar;
+      * launch splitting: 6 turns in one launch == 2 + 4 turns in two launches, bit for bit
+        (every field of every particle);
+      * slot independence: the same particles tracked in reversed slot order give the same
+        result per particle_id (what sharding over GPUs relies on);
+      * no particle lost or duplicated: particle_id is a permutation, at_turn == 6 for all
+        survivors."""
+    line = common.load_line('hllhc_14')
+    n = 1_000_000
+    nr = 1000
+    r = np.linspace(0, 2e-3, nr + 1)[1:]
+    th = np.linspace(0, np.pi / 2, n // nr)
+    rr, tt = np.meshgrid(r, th, indexing='ij')
+    ref_p = line.particle_ref
+    kw = dict(p0c=float(ref_p.get('p0c')[0]), mass0=ref_p.mass0, q0=ref_p.q0)
+    p_host = xb.Particles(x=(rr * np.cos(tt)).ravel(), y=(rr * np.sin(tt)).ravel(),
+                          delta=np.full(n, 2.7e-4), **kw)
+    one = common.by_id(_track_gpu(line, p_host, 6, True))
+    assert np.array_equal(one['particle_id'], np.arange(n))
+    alive = one['state'] > 0
+    assert np.all(one['at_turn'][alive] == 6)
+    # sample vs oracle
+    idx = np.arange(0, n, 997)
+    p_s = xb.Particles(x=p_host.get('x')[idx], y=p_host.get('y')[idx],
+                       delta=p_host.get('delta')[idx], **kw)
+    ref = common.oracle_track(line, p_s, 6, parallel=True)
+    yard = common.libm_yardstick(line, p_s, 6, ref=ref, parallel=True)
+    got_s = {ff: one[ff][idx] for ff in one}
+    common.assert_parity(got_s, ref, yard, True, mask=ref['state'] > 0, label='hllhc 1e6 sample')
+    for ff in ('state', 'at_turn', 'at_element'):
+        assert np.array_equal(got_s[ff], ref[ff]), ff
+    # launch splitting
+    p = p_host.copy(_device='cuda:0')
+    line.build_tracker(_device='cuda:0', exact_arithmetic=True)
+    line.track(p, num_turns=2)
+    line.track(p, num_turns=4)
+    two = common.by_id(p)
+    for ff, _ in xb.Particles.per_particle_vars:
+        assert np.array_equal(one[ff], two[ff], equal_nan=True), ff
+    # slot independence
+    rev = np.arange(n)[::-1].copy()
+    p_rev = xb.Particles(x=p_host.get('x')[rev], y=p_host.get('y')[rev],
+                         delta=p_host.get('delta')[rev], particle_id=rev, **kw)
+    three = common.by_id(_track_gpu(line, p_rev, 6, True))
+    for ff in common.ALL_F64 + ('state', 'at_turn', 'at_element'):
+        assert np.array_equal(one[ff], three[ff], equal_nan=True), ff
