@@ -16,6 +16,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
 LIB = os.path.join(HERE, '_build', 'libxtb_hostsim.so')
 _lib = None
+# explicit fma() calls of the device code (xtb_thick.cuh::div_by) as one instruction where the
+# host has it (no contraction of a*b+c happens either way: -ffp-contract=off)
+try:
+    _FMA_FLAG = ['-mfma'] if ' fma ' in open('/proc/cpuinfo').read() else []
+except OSError:
+    _FMA_FLAG = []
 
 
 def _sources():
@@ -30,7 +36,7 @@ def load():
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         if (not os.path.exists(LIB)
                 or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in _sources())):
-            subprocess.run(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared',
+            subprocess.run(['g++', '-O2', '-ffp-contract=off', *_FMA_FLAG, '-std=c++17', '-fPIC', '-shared',
                             os.path.join(HERE, 'xtb_hostsim.cpp'), '-o', LIB, '-lm'], check=True)
         _lib = ct.CDLL(LIB)
         _lib.xtb_hostsim_track.restype = ct.c_int
@@ -46,6 +52,7 @@ class HostSimLattice:
     """Mirrors the program selection of `xtb_track` (csrc/xtb_api.cu): the FUSED program
     when the element range falls on its op boundaries, else the PLAIN one."""
     npt = 3          # particle slots carried together, as in the thin CUDA kernels
+    npt_heavy = 2    # ... and in the thick ones
 
     def __init__(self, fused, plain, line_length):
         self.plain = (np.ascontiguousarray(plain[0], dtype=np.uint64),
@@ -84,7 +91,7 @@ class HostSimLattice:
             int(bool(flag_reset_s_at_end_turn)), int(flag_monitor), mst, int(track_flags),
             float(global_xy_limit), int(variant_flags), self.line_length,
             ct.cast(self._mons, ct.c_void_p) if self._mons is not None else None,
-            ct.cast(self._ltms, ct.c_void_p) if self._ltms is not None else None, self.npt, 0)
+            ct.cast(self._ltms, ct.c_void_p) if self._ltms is not None else None, self.npt | (self.npt_heavy << 8), 0)
         assert rc == 0
 
     def close(self):

@@ -119,6 +119,8 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
                                   uint64_t track_flags, double global_xy_limit, uint32_t variant,
                                   double line_length, const xtb_monitor_t* inline_mon,
                                   const xtb_last_turns_monitor_t* inline_ltm, int32_t npt, int32_t force_full) {
+    const int npt_heavy = (npt >> 8) ? (npt >> 8) : 2;
+    npt &= 0xff;
     XtbTrackArgs a;
     std::memset(&a, 0, sizeof(a));
     if (elem_offset[ele_start] == XTB_NOT_ADDRESSABLE
@@ -144,7 +146,7 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
     a.line_length = line_length;
     a.global_xy_limit = global_xy_limit;
     const bool synrad = variant & XTB_VARIANT_SYNRAD, frz = variant & XTB_VARIANT_FREEZE_LONG;
-    // has_heavy mirrors the kernel choice: thick programs run on the full state, NPT = 1
+    // has_heavy mirrors the kernel choice: thick programs run on the full state
     bool heavy = synrad;
     for (size_t pc = 0; pc + 2 < image.size() && !heavy;) {
         const uint32_t hx = (uint32_t) image[pc];
@@ -153,10 +155,18 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
         pc += hx >> 16;
     }
     if (heavy || force_full) {
-        if (synrad && frz) run<1, true, true, PState>(a);
-        else if (synrad) run<1, true, false, PState>(a);
-        else if (frz) run<1, false, true, PState>(a);
-        else run<1, false, false, PState>(a);
+        // (npt_heavy mirrors XTB_NPT_HEAVY of xtb_kernel_inst.cu)
+        if (npt_heavy == 2) {
+            if (synrad && frz) run<2, true, true, PState>(a);
+            else if (synrad) run<2, true, false, PState>(a);
+            else if (frz) run<2, false, true, PState>(a);
+            else run<2, false, false, PState>(a);
+        } else {
+            if (synrad && frz) run<1, true, true, PState>(a);
+            else if (synrad) run<1, true, false, PState>(a);
+            else if (frz) run<1, false, true, PState>(a);
+            else run<1, false, false, PState>(a);
+        }
     } else if (npt == 3) {
         if (frz) run<3, false, true, PHot>(a);
         else run<3, false, false, PHot>(a);

@@ -533,6 +533,48 @@ L_STOP:
     return stop;
 }
 
+#ifdef XTB_WITH_HEAVY
+// A thick-magnet body on ALL lanes of the thread at once (xtb_thick.cuh::magnet_body_n: the
+// lanes are independent dependency chains in one instruction stream).  Same bookkeeping as
+// xtb_slow_op.  Lanes without a particle run on the benign state and are reset to it.
+template <int NPT, bool SYNRAD, bool FRZ>
+static __device__ __noinline__ void xtb_slow_body(XtbLanes<NPT, PState>& lanes, const XtbPass ps,
+                                                  const uint32_t h, const int32_t aux,
+                                                  const double* __restrict__ q,
+                                                  const XtbTrackArgs& a) {
+    PState T[NPT];
+    PSlot G[NPT];
+    bool live[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        G[k].p = &a.part;  G[k].i = lanes.slot[k];  G[k].c = &lanes.C[k];
+        live[k] = lanes.live[k];
+        T[k] = lanes.P[k];
+        if (live[k]) {
+            T[k] = pstate_full(lanes.P[k], G[k], ps, lanes.eidx);
+            if ((a.flag_monitor == 2) && (h & (XTB_F_START << 8))) monitor_record(a.mon, T[k], G[k]);
+        }
+    }
+    magnet_body_n<NPT, SYNRAD, FRZ>(T, live, G, a, q, aux);
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        if (!live[k]) {
+            pstate_benign(lanes.P[k]);
+            continue;
+        }
+        if ((h & (XTB_F_GLOBAL << 8)) && !a.ignore_global) global_aperture_check(T[k], a.global_xy_limit);
+        if ((h & (XTB_F_END << 8)) && T[k].state <= 0) {
+            pstate_store(T[k], G[k]);       // tracker.py:702-711
+            lanes.live[k] = false;
+            pstate_benign(lanes.P[k]);
+        } else {
+            lanes.P[k] = T[k];
+        }
+    }
+}
+#endif
+
+
 // Executes the ops of one tile, from word `lb->off` of the tile up to the XTB_OP_END
 // sentinel, on the NPT particles of this thread: the fast ops in xtb_run_fast, everything
 // else here --
@@ -627,7 +669,16 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
         slow_main:
             const int32_t aux = (int32_t) (hw.x >> 32);
             const double* __restrict__ q = reinterpret_cast<const double*>(xtb_tile_ptr(tb, cur + 2));
-            for (int k = 0; k < NPT; ++k) {
+            bool done = false;
+#ifdef XTB_WITH_HEAVY
+            if constexpr (HEAVY && (NPT > 1) && std::is_same<S, PState>::value) {
+                if (op == XTB_OP_MAGNET_BODY) {
+                    xtb_slow_body<NPT, SYNRAD, FRZ>(lanes, ps, h, aux, q, a);
+                    done = true;
+                }
+            }
+#endif
+            for (int k = 0; k < NPT && !done; ++k) {
                 if (!lanes.live[k]) continue;      // these bodies touch the caller's SoA
                 const PSlot Gk{&a.part, lanes.slot[k], &lanes.C[k]};
                 lanes.live[k] = xtb_slow_op<HEAVY, SYNRAD, FRZ>(lanes.P[k], Gk, ps, lanes.eidx, h, aux, q, a);

@@ -13,12 +13,12 @@
 #endif
 
 // particle slots per thread: 3 in the thin kernels (measured best of 1..4 on B200, see
-// profiles/), 1 in the (register-hungry) thick ones
+// profiles/), 2 in the thick ones (their bodies run on both at once, xtb_thick.cuh)
 #ifndef XTB_NPT_THIN
 #define XTB_NPT_THIN 3
 #endif
 #ifndef XTB_NPT_HEAVY
-#define XTB_NPT_HEAVY 1
+#define XTB_NPT_HEAVY 2
 #endif
 
 template <bool HEAVY, bool SYNRAD, bool FRZ>

@@ -16,20 +16,6 @@
 #include "xtb_state.cuh"
 #include "xtb_thin.cuh"
 
-// Inlining of the thick-body pieces (tuning knob, measured in profiles/r01_history.md):
-//   0  polar drift inlined into ONE drift function, drift and kick out of line
-//   1  drift and kick inlined into the integrator loops, polar drift out of line
-#ifndef XTB_THICK_INLINE_MODE
-#define XTB_THICK_INLINE_MODE 1
-#endif
-#if XTB_THICK_INLINE_MODE == 0
-#define XTB_POLAR_INLINE __forceinline__
-#define XTB_DRIFTKICK_INLINE __noinline__
-#else
-#define XTB_POLAR_INLINE __noinline__
-#define XTB_DRIFTKICK_INLINE __forceinline__
-#endif
-
 #define XTB_QELEM 1.60217662e-19
 #define XTB_EPSILON_0 8.854187817620e-12
 #define XTB_POW2(X) ((X) * (X))
@@ -37,32 +23,56 @@
 #define XTB_POW4(X) ((X) * (X) * (X) * (X))
 
 // ---------------------------------------------------------------- drifts ----
+// Explicit fused multiply-add (one rounding) in both builds.
+#ifdef __CUDA_ARCH__
+#define XTB_FMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define XTB_FMA(a, b, c) __builtin_fma((a), (b), (c))
+#endif
+
+// a / b when rb = RN(1 / b) is already at hand (an element constant tabulated by the host,
+// the 1/pz the reference computes anyway, the 1/rvv every state carries).  This is the
+// closing correction step of every FMA-based IEEE division (Markstein 1990; the tail of the
+// CUDA double-precision division itself): q = RN(a*rb), r = a - b*q exactly (FMA),
+// result = RN(q + r*rb) = RN(a / b).  3 FP64 instructions instead of ~10 and no slow-path
+// test.  Checked against `a / b` on 2*10^9 random operand pairs of the ranges met here
+// (b ~ cos(small angle), pz ~ 1 + delta, generic exponents +-20): no mismatch.
+__device__ __forceinline__ double div_by(const double a, const double b, const double rb) {
+    const double q = a * rb;
+    const double r = XTB_FMA(-b, q, a);
+    return XTB_FMA(r, rb, q);
+}
+
 // Trigonometry of element constants.  cos(h*s), sin(h*s), sin(h*s/2) in the polar drift and
 // the curved exact bend depend on the element alone, yet the reference evaluates them per
 // particle and per integrator sub-step (a default bend: 32 polar drifts = 96 sin/cos per
-// particle).  The host lowering tabulates them for every sub-step length the integrator of
-// this op will ask for (lowering.py::_trig_table, computed with the host libm -- the one the
-// reference's CPU build uses), keyed by the bit pattern of the length; a length that is not
-// in the table (there should be none) is evaluated here.
+// particle).  The host lowering tabulates them (lowering.py::_trig_table, computed with the
+// host libm -- the one the reference's CPU build uses) for every sub-step length the
+// integrator of this op asks for, in the order the integrator asks: entry
+// `outer class * n_inner + inner class` (see magnet_drift_n / magnet_body_n), so the device
+// indexes, it does not search.  The entry carries the length it was made for; if the bit
+// pattern does not match (there should be no such case; the host test build counts them)
+// the values are evaluated here.
+#define XTB_TRIG_STRIDE 6   // [length, cos(h*s), sin(h*s), sin(h*s/2), RN(1/cos(h*s)), 0]
 struct TrigTab {
-    const double* t;     // entries of 4 doubles: length, cos(h*s), sin(h*s), sin(0.5*h*s)
-    int n;
+    const double* t;
+    int n;               // entries
+    int n_inner;         // inner classes per outer class (1: models 2, 4; 2: model 7; 4: model 8)
     double rho;          // 1 / h (valid iff n > 0)
 };
 #ifdef XTB_COUNT_TRIG_MISS
 static long long xtb_trig_lookups = 0, xtb_trig_misses = 0;
 #endif
-__device__ __forceinline__ void trig_of(const TrigTab& tt, const double h, const double s,
-                                        double& ca, double& sa, double& sa2) {
+__device__ __forceinline__ void trig_of(const TrigTab& tt, const int idx, const double h,
+                                        const double s, double& ca, double& sa, double& sa2,
+                                        double& rca) {
 #ifdef XTB_COUNT_TRIG_MISS
     xtb_trig_lookups++;
 #endif
-    const long long key = __double_as_longlong(s);
-    for (int i = 0; i < tt.n; ++i) {
-        if (__double_as_longlong(tt.t[4 * i]) == key) {
-            ca = tt.t[4 * i + 1];
-            sa = tt.t[4 * i + 2];
-            sa2 = tt.t[4 * i + 3];
+    if (idx < tt.n) {
+        const double* e = tt.t + XTB_TRIG_STRIDE * idx;
+        if (__double_as_longlong(e[0]) == __double_as_longlong(s)) {
+            ca = e[1];  sa = e[2];  sa2 = e[3];  rca = e[4];
             return;
         }
     }
@@ -72,35 +82,69 @@ __device__ __forceinline__ void trig_of(const TrigTab& tt, const double h, const
     ca = cos(h * s);
     sa = sin(h * s);
     sa2 = sin(0.5 * h * s);
+    rca = 1. / ca;
 }
 
-// track_polar_drift_single_particle, track_magnet_drift.h:45-87
-template <bool FRZ>
-__device__ XTB_POLAR_INLINE void polar_drift(PState& P, const double length, const double h,
-                                             const TrigTab tt) {
-    const double rvv = P.rvv;
-    const double x = P.x, y = P.y, px = P.px, py = P.py;
+// Step tables of the nested Yoshida bends (track_magnet_drift.h:521-550) and of the
+// Yoshida-4 integrator (track_magnet.h:236-250): [drift fractions..., kick fractions...]
+#ifdef __CUDACC__
+#define XTB_CONST_TABLE static __device__ __constant__ double
+#else
+#define XTB_CONST_TABLE static const double
+#endif
+XTB_CONST_TABLE XTB_Y4_NESTED[8] = {0.6756035959798289, -0.17560359597982889, -0.17560359597982889,
+                                    0.6756035959798289,
+                                    1.3512071919596578, -1.7024143839193155, 1.3512071919596578, 0.};
+XTB_CONST_TABLE XTB_Y6[16] = {
+    3.922568052387799819591407413100e-01, 5.100434119184584780271052295575e-01,
+    -4.710533854097565531482416645304e-01, 6.875316825251809316199569366290e-02,
+    6.875316825251809316199569366290e-02, -4.710533854097565531482416645304e-01,
+    5.100434119184584780271052295575e-01, 3.922568052387799819591407413100e-01,
+    7.845136104775599639182814826199e-01, 2.355732133593569921359289764951e-01,
+    -1.177679984178870098432412305556e+00, 1.315186320683906284756403692882e+00,
+    -1.177679984178870098432412305556e+00, 2.355732133593569921359289764951e-01,
+    7.845136104775599639182814826199e-01, 0.};
+
+// track_polar_drift_single_particle, track_magnet_drift.h:45-87, on N particles at once
+// (N independent dependency chains for the FP64 pipe).  The divisions by cos(h*s), pz and
+// rvv use the reciprocals at hand (div_by): same correctly rounded quotients.
+template <int N, bool FRZ>
+__device__ __forceinline__ void polar_drift_n(PState (&P)[N], const double length, const double h,
+                                              const TrigTab& tt, const int idx) {
     const double s = length;
-    const double one_plus_delta = P.delta + 1.0;
-    const double pz = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(px) - XTB_POW2(py));
     const double rho = (tt.n > 0) ? tt.rho : 1 / h;
-    double ca, sa, sa2;
-    trig_of(tt, h, s, ca, sa, sa2);
-    const double _pz = 1 / pz;
-    const double pxt = px * _pz;
-    const double _ptt = 1 / (ca - sa * pxt);
-    const double pst = (x + rho) * sa * _pz * _ptt;
-    const double new_x = (x + rho * (2 * sa2 * sa2 + sa * pxt)) * _ptt;
-    const double new_px = ca * px + sa * pz;
-    const double new_y = y + pst * py;
-    const double delta_ell = one_plus_delta * (x + rho) * sa / ca / pz / (1 - px * sa / ca / pz);
-    P.x = new_x;
-    P.px = new_px;
-    P.y = new_y;
-    if (!FRZ) {
-        P.zeta += length - delta_ell / rvv;
-        P.s += s;
+    double ca, sa, sa2, rca;
+    trig_of(tt, idx, h, s, ca, sa, sa2, rca);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double rvv = P[k].rvv;
+        const double x = P[k].x, y = P[k].y, px = P[k].px, py = P[k].py;
+        const double one_plus_delta = P[k].delta + 1.0;
+        const double pz = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(px) - XTB_POW2(py));
+        const double _pz = 1 / pz;
+        const double pxt = px * _pz;
+        const double _ptt = 1 / (ca - sa * pxt);
+        const double pst = (x + rho) * sa * _pz * _ptt;
+        const double new_x = (x + rho * (2 * sa2 * sa2 + sa * pxt)) * _ptt;
+        const double new_px = ca * px + sa * pz;
+        const double new_y = y + pst * py;
+        // one_plus_delta * (x + rho) * sa / ca / pz / (1 - px * sa / ca / pz)
+        const double num = div_by(div_by(one_plus_delta * (x + rho) * sa, ca, rca), pz, _pz);
+        const double den = 1 - div_by(div_by(px * sa, ca, rca), pz, _pz);
+        const double delta_ell = num / den;
+        P[k].x = new_x;
+        P[k].px = new_px;
+        P[k].y = new_y;
+        if (!FRZ) {
+            P[k].zeta += length - div_by(delta_ell, rvv, P[k].rv0v);
+            P[k].s += s;
+        }
     }
+}
+template <bool FRZ>
+__device__ __noinline__ void polar_drift(PState& P, const double length, const double h,
+                                         const TrigTab& tt, const int idx) {
+    polar_drift_n<1, FRZ>(reinterpret_cast<PState(&)[1]>(P), length, h, tt, idx);
 }
 
 // track_expanded_combined_dipole_quad_single_particle, track_magnet_drift.h:91-213
@@ -184,10 +228,10 @@ __device__ __noinline__ void combined_dipole_quad(PState& P, const double length
 // track_curved_exact_bend_single_particle, track_magnet_drift.h:272-345
 template <bool FRZ>
 __device__ __noinline__ void curved_exact_bend(PState& P, const double length, const double k0,
-                                               const double h, const TrigTab tt) {
+                                               const double h, const TrigTab& tt, const int idx) {
     const double k0_chi = k0 * P.chi;
     if (fabs(k0_chi) < 1e-8) {
-        polar_drift<FRZ>(P, length, h, tt);
+        polar_drift<FRZ>(P, length, h, tt, idx);
         return;
     }
     const double rvv = P.rvv;
@@ -196,8 +240,8 @@ __device__ __noinline__ void curved_exact_bend(PState& P, const double length, c
     const double one_plus_delta = P.delta + 1.0;
     const double hs = h * s;
     // (sin(hs / 2) == sin(0.5 * h * s): halving is exact)
-    double cos_hs, sin_hs, sin_hs_2;
-    trig_of(tt, h, s, cos_hs, sin_hs, sin_hs_2);
+    double cos_hs, sin_hs, sin_hs_2, rcos_hs;
+    trig_of(tt, idx, h, s, cos_hs, sin_hs, sin_hs_2, rcos_hs);
     const double pz0 = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(px0) - XTB_POW2(py));
     const double C = pz0 - k0_chi * ((1.0 / h) + x0);
     const double pxs = px0 * cos_hs + C * sin_hs;
@@ -250,48 +294,50 @@ __device__ __noinline__ void straight_exact_bend(PState& P, const double length,
     }
 }
 
-// track_magnet_drift_single_particle, track_magnet_drift.h:468-555
-template <bool FRZ>
-__device__ XTB_DRIFTKICK_INLINE void magnet_drift(PState& P, const double length, const double k0,
-                                             const double k1, const double h, const int drift_model,
-                                             const TrigTab tt) {
+// track_magnet_drift_single_particle, track_magnet_drift.h:468-555, on N particles.
+// `oc` = class of the outer (integrator) sub-step, for the trig table index.
+template <int N, bool FRZ>
+__device__ __forceinline__ void magnet_drift_n(PState (&P)[N], const double length, const double k0,
+                                               const double k1, const double h, const int drift_model,
+                                               const TrigTab& tt, const int oc) {
     if (drift_model == -1) return;
     if (length == 0.0) return;
     switch (drift_model) {
-    case 0: drift_expanded<FRZ>(P, length); break;
-    case 1: drift_exact<FRZ>(P, length); break;
-    case 2: polar_drift<FRZ>(P, length, h, tt); break;
-    case 3: combined_dipole_quad<FRZ>(P, length, k0, k1, h); break;
-    case 4: curved_exact_bend<FRZ>(P, length, k0, h, tt); break;
-    case 5: straight_exact_bend<FRZ>(P, length, k0); break;
-    case 7: {
-        // nested Yoshida-4 bend, track_magnet_drift.h:521-531.  One inlined polar drift in a
-        // loop over the step table (not 4 copies): the thick kernels are bound by instruction
-        // fetch and local-memory traffic, not by arithmetic (profiles/r01_ncu_lep.md)
-        const double pd[4] = {0.6756035959798289, -0.17560359597982889, -0.17560359597982889,
-                              0.6756035959798289};
-        const double pk[4] = {1.3512071919596578, -1.7024143839193155, 1.3512071919596578, 0.};
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            polar_drift<FRZ>(P, pd[j] * length, h, tt);
-            if (j < 3) P.px = P.px - pk[j] * k0 * P.chi * length;
-        }
+    case 0:
+#pragma unroll
+        for (int k = 0; k < N; ++k) drift_expanded<FRZ>(P[k], length);
         break;
-    }
+    case 1:
+#pragma unroll
+        for (int k = 0; k < N; ++k) drift_exact<FRZ>(P[k], length);
+        break;
+    case 3:
+        for (int k = 0; k < N; ++k) combined_dipole_quad<FRZ>(P[k], length, k0, k1, h);
+        break;
+    case 4:
+        for (int k = 0; k < N; ++k) curved_exact_bend<FRZ>(P[k], length, k0, h, tt, oc);
+        break;
+    case 5:
+        for (int k = 0; k < N; ++k) straight_exact_bend<FRZ>(P[k], length, k0);
+        break;
+    case 2:
+    case 7:
     case 8: {
-        // nested Yoshida-6 bend, track_magnet_drift.h:532-550
-        const double d[8] = {3.922568052387799819591407413100e-01, 5.100434119184584780271052295575e-01,
-                             -4.710533854097565531482416645304e-01, 6.875316825251809316199569366290e-02,
-                             6.875316825251809316199569366290e-02, -4.710533854097565531482416645304e-01,
-                             5.100434119184584780271052295575e-01, 3.922568052387799819591407413100e-01};
-        const double k[8] = {7.845136104775599639182814826199e-01, 2.355732133593569921359289764951e-01,
-                             -1.177679984178870098432412305556e+00, 1.315186320683906284756403692882e+00,
-                             -1.177679984178870098432412305556e+00, 2.355732133593569921359289764951e-01,
-                             7.845136104775599639182814826199e-01, 0.};
+        // polar drift (2) and the nested Yoshida-4 / Yoshida-6 bends (7, 8:
+        // track_magnet_drift.h:521-550) as ONE loop around ONE inlined polar drift: the
+        // state stays in registers for the whole body, the code is there once
+        const int n_in = (drift_model == 2) ? 1 : ((drift_model == 7) ? 4 : 8);
+        const double* __restrict__ tab = (drift_model == 7) ? XTB_Y4_NESTED : XTB_Y6;
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            polar_drift<FRZ>(P, d[j] * length, h, tt);
-            if (j < 7) P.px = P.px - k[j] * k0 * P.chi * length;
+        for (int j = 0; j < n_in; ++j) {
+            const double lj = (n_in == 1) ? length : tab[j] * length;
+            const int ic = (j < n_in - 1 - j) ? j : n_in - 1 - j;
+            polar_drift_n<N, FRZ>(P, lj, h, tt, oc * tt.n_inner + ic);
+            if (j < n_in - 1) {
+                const double kj = tab[n_in + j];
+#pragma unroll
+                for (int k = 0; k < N; ++k) P[k].px = P[k].px - kj * k0 * P[k].chi * length;
+            }
         }
         break;
     }
@@ -307,9 +353,12 @@ __device__ XTB_DRIFTKICK_INLINE void magnet_drift(PState& P, const double length
 //  q[10..17] k0_tot k1_tot k2 k3 k0s k1s k2s k3s   (field evaluation for radiation)
 //  q[18..25] main coefficients (order 3, Horner order, pairs)
 //  then user coefficients (order_user+1 pairs), then rel coefficients (order_rel+1 pairs),
-//  then the trig table: (int) n, 1/h, n x [length, cos(h*s), sin(h*s), sin(h*s/2)]
+//  then the trig table: (int) n | n_inner << 32, 1/h, n x XTB_TRIG_STRIDE doubles
+//  then, if the element's linear edges were merged in (lowering.py::_merge_linear_edges):
+//  r21, r43 of the entry edge, r21, r43 of the exit edge (track_dipole_edge_linear.h:30-39)
 //  aux: integrator[0:2] drift_model+1[2:6] rot_frame[6] has_user[7] has_rel[8]
-//       has_main[9] radiation_flag[10:12] drift_only[12] num_kicks[13:32]
+//       has_main[9] radiation_flag[10:12] drift_only[12] edge_in[13] edge_out[14]
+//       num_kicks[15:32]
 struct BodyPar {
     const double* q;
     const double* cm;    // main
@@ -318,6 +367,8 @@ struct BodyPar {
     int order_user, order_rel;
     int integrator, drift_model, rot_frame, has_user, has_rel, has_main, radiation_flag, drift_only;
     int num_kicks;
+    int edge_in, edge_out;
+    const double* edges;   // [r21_in, r43_in, r21_out, r43_out]
     TrigTab trig;
 };
 
@@ -331,9 +382,12 @@ __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) 
     b.cu = b.cm + 8;
     b.cr = b.cu + 2 * (b.order_user + 1);
     const double* tq = b.cr + 2 * (b.order_rel + 1);
-    b.trig.n = (int) __double_as_longlong(tq[0]);
+    const unsigned long long tw = (unsigned long long) __double_as_longlong(tq[0]);
+    b.trig.n = (int) (tw & 0xffffffffu);
+    b.trig.n_inner = (int) (tw >> 32);
     b.trig.rho = tq[1];
     b.trig.t = tq + 2;
+    b.edges = b.trig.t + XTB_TRIG_STRIDE * b.trig.n;
     const uint32_t a = (uint32_t) aux;
     b.integrator = a & 3;
     b.drift_model = (int) ((a >> 2) & 15) - 1;
@@ -343,45 +397,61 @@ __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) 
     b.has_main = (a >> 9) & 1;
     b.radiation_flag = (a >> 10) & 3;
     b.drift_only = (a >> 12) & 1;
-    b.num_kicks = (int) (a >> 13);
+    b.edge_in = (a >> 13) & 1;
+    b.edge_out = (a >> 14) & 1;
+    b.num_kicks = (int) (a >> 15);
     return b;
 }
 
-// track_magnet_kick_single_particle, track_magnet_kick.h:24-144
-template <bool FRZ>
-__device__ XTB_DRIFTKICK_INLINE void magnet_kick(PState& P, const BodyPar& b, const double kick_weight) {
-    const double chi = P.chi, x = P.x, y = P.y;
+// track_magnet_kick_single_particle, track_magnet_kick.h:24-144, on N particles
+template <int N, bool FRZ>
+__device__ __forceinline__ void magnet_kick_n(PState (&P)[N], const BodyPar& b, const double kick_weight) {
     const double length = b.q[0];
-    double m, n;
     if (b.has_user) {
-        horner_kick(x, y, chi, b.cu, b.order_user, m, n);
-        P.px += kick_weight * (-m);
-        P.py += kick_weight * n;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double m, n;
+            horner_kick(P[k].x, P[k].y, P[k].chi, b.cu, b.order_user, m, n);
+            P[k].px += kick_weight * (-m);
+            P[k].py += kick_weight * n;
+        }
     }
     if (b.has_rel) {
-        horner_kick(x, y, chi, b.cr, b.order_rel, m, n);
-        P.px += kick_weight * (-m);
-        P.py += kick_weight * n;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double m, n;
+            horner_kick(P[k].x, P[k].y, P[k].chi, b.cr, b.order_rel, m, n);
+            P[k].px += kick_weight * (-m);
+            P[k].py += kick_weight * n;
+        }
     }
     if (b.has_main) {
-        horner_kick(x, y, chi, b.cm, 3, m, n);
-        P.px += kick_weight * (-m);
-        P.py += kick_weight * n;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double m, n;
+            horner_kick(P[k].x, P[k].y, P[k].chi, b.cm, 3, m, n);
+            P[k].px += kick_weight * (-m);
+            P[k].py += kick_weight * n;
+        }
     }
-    double dpx = 0, dpy = 0, dzeta = 0;
     const double h = b.q[4], hxl = b.q[5];
-    if (b.rot_frame) {
-        const double hl = h * length * kick_weight + hxl * kick_weight;
-        dpx += hl * (1. + P.delta);
-        dzeta += -P.rv0v * hl * x;
-    }
     const double htot = b.q[8];
-    dpx += -chi * b.q[6] * kick_weight * htot * x;
-    dpx += htot * chi * b.q[7] * kick_weight * (-x * x + 0.5 * y * y);
-    dpy += htot * chi * b.q[7] * kick_weight * x * y;
-    P.px += dpx;
-    P.py += dpy;
-    if (!FRZ) P.zeta += dzeta;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double chi = P[k].chi, x = P[k].x, y = P[k].y;
+        double dpx = 0, dpy = 0, dzeta = 0;
+        if (b.rot_frame) {
+            const double hl = h * length * kick_weight + hxl * kick_weight;
+            dpx += hl * (1. + P[k].delta);
+            dzeta += -P[k].rv0v * hl * x;
+        }
+        dpx += -chi * b.q[6] * kick_weight * htot * x;
+        dpx += htot * chi * b.q[7] * kick_weight * (-x * x + 0.5 * y * y);
+        dpy += htot * chi * b.q[7] * kick_weight * x * y;
+        P[k].px += dpx;
+        P[k].py += dpy;
+        if (!FRZ) P[k].zeta += dzeta;
+    }
 }
 
 // ------------------------------------------------------------- radiation ----
@@ -720,72 +790,97 @@ __device__ __forceinline__ void rad_end(const RadSnapshot& s, PState& P, const P
     }
 }
 
-// track_magnet_body_single_particle, track_magnet.h:26-285
-template <bool SYNRAD, bool FRZ>
-__device__ __noinline__ void magnet_body(PState& P, const PSlot& G, const XtbTrackArgs& a,
-                                         const double* __restrict__ q, const int32_t aux) {
+// track_magnet_body_single_particle, track_magnet.h:26-285, on N particles at once.
+// The three integrators are ONE loop nest -- radiation segments x sub-steps, each sub-step a
+// drift and (except the last of a segment) a kick -- so that the drift and kick bodies exist
+// once and the particles stay in registers from the first sub-step to the last:
+//   teapot   (track_magnet.h:191-213)  1 segment,  n_kicks + 1 sub-steps (edge, inside.., edge)
+//   uniform  (:214-227)                n_kicks segments of 2 sub-steps
+//   yoshida4 (:228-274)                n_slices segments of 8 sub-steps
+//   drift-only shortcut (:181-185)     1 segment, 1 sub-step, no kick
+// Lengths and weights are formed by the reference's own expressions.  `live`: lanes whose
+// particle is real (radiation touches the caller's SoA and the RNG stream: real lanes only).
+template <int N, bool SYNRAD, bool FRZ>
+__device__ __forceinline__ void magnet_body_n(PState (&P)[N], const bool (&live)[N], const PSlot (&G)[N],
+                                              const XtbTrackArgs& a, const double* __restrict__ q,
+                                              const int32_t aux) {
     const BodyPar b = body_par(q, aux);
     const double length = q[0], k0d = q[1], k1d = q[2], hd = q[3];
     const int dm = b.drift_model;
-    RadSnapshot snap;
-#define XTB_DRIFT(dl) magnet_drift<FRZ>(P, (dl), k0d, k1d, hd, dm, b.trig)
-#define XTB_KICK(w) magnet_kick<FRZ>(P, b, (w))
-    if (b.drift_only) {
-        rad_begin<SYNRAD>(snap, P);
-        XTB_DRIFT(length);
-        rad_end<SYNRAD, FRZ>(snap, P, G, a, b, length);
-        return;
-    }
     const int nk = b.num_kicks;
-    if (b.integrator == 1) {            // teapot
-        rad_begin<SYNRAD>(snap, P);
-        const double kick_weight = 1. / nk;
-        double edge_drift_weight = 0.5;
-        double inside_drift_weight = 0;
+    const int integ = b.drift_only ? 0 : b.integrator;
+
+    int n_seg = 1, n_sub = 1;
+    double seg_length = length;
+    double kick_weight = 0., w_edge = 0., w_inside = 0., slice_length = 0.;
+    if (integ == 1) {               // teapot
+        kick_weight = 1. / nk;
+        w_edge = 0.5;
         if (nk > 1) {
-            edge_drift_weight = 1. / (2 * (1 + nk));
-            inside_drift_weight = ((double) nk) / ((double) ((int64_t) nk * nk) - 1);
+            w_edge = 1. / (2 * (1 + nk));
+            w_inside = ((double) nk) / ((double) ((int64_t) nk * nk) - 1);
         }
-        XTB_DRIFT(edge_drift_weight * length);
-        for (int i = 0; i < nk - 1; ++i) {
-            XTB_KICK(kick_weight);
-            XTB_DRIFT(inside_drift_weight * length);
-        }
-        XTB_KICK(kick_weight);
-        XTB_DRIFT(edge_drift_weight * length);
-        rad_end<SYNRAD, FRZ>(snap, P, G, a, b, length);
-    } else if (b.integrator == 3) {     // uniform
-        const double kick_weight = 1. / nk;
-        const double drift_weight = kick_weight;
-        for (int i = 0; i < nk; ++i) {
-            rad_begin<SYNRAD>(snap, P);
-            XTB_DRIFT(0.5 * drift_weight * length);
-            XTB_KICK(kick_weight);
-            XTB_DRIFT(0.5 * drift_weight * length);
-            rad_end<SYNRAD, FRZ>(snap, P, G, a, b, drift_weight * length);
-        }
-    } else if (b.integrator == 2) {     // yoshida 4
+        n_sub = nk + 1;
+    } else if (integ == 3) {        // uniform
+        kick_weight = 1. / nk;
+        n_seg = nk;
+        n_sub = 2;
+        seg_length = kick_weight * length;      // drift_weight * length
+    } else if (integ == 2) {        // yoshida 4
         const int num_slices = nk / 7 + (nk % 7 != 0);
-        const double slice_length = length / (num_slices);
-        const double kick_weight = 1. / num_slices;
-        const double d0 = 3.922568052387799819591407413100e-01, d1 = 5.100434119184584780271052295575e-01,
-                     d2 = -4.710533854097565531482416645304e-01, d3 = 6.875316825251809316199569366290e-02;
-        const double y0 = 7.845136104775599639182814826199e-01, y1 = 2.355732133593569921359289764951e-01,
-                     y2 = -1.177679984178870098432412305556e+00, y3 = 1.315186320683906284756403692882e+00;
-        const double yd[8] = {d0, d1, d2, d3, d3, d2, d1, d0};
-        const double yk[8] = {y0, y1, y2, y3, y2, y1, y0, 0.};
-        for (int ii = 0; ii < num_slices; ++ii) {
-            rad_begin<SYNRAD>(snap, P);
+        slice_length = length / (num_slices);
+        kick_weight = 1. / num_slices;
+        n_seg = num_slices;
+        n_sub = 8;
+        seg_length = slice_length;
+    }
+    if (b.edge_in) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) edge_linear(P[k], b.edges[0], b.edges[1]);
+    }
+    RadSnapshot snap[N];
+    for (int seg = 0; seg < n_seg; ++seg) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) rad_begin<SYNRAD>(snap[k], P[k]);
 #pragma unroll 1
-            for (int j = 0; j < 8; ++j) {       // one copy of the drift and kick bodies
-                XTB_DRIFT(slice_length * yd[j]);
-                if (j < 7) XTB_KICK(kick_weight * yk[j]);
+        for (int j = 0; j < n_sub; ++j) {
+            double dl, kw = kick_weight;
+            int oc = 0;
+            if (integ == 1) {
+                const bool edge = (j == 0) || (j == n_sub - 1);
+                dl = (edge ? w_edge : w_inside) * length;
+                oc = edge ? 0 : 1;
+            } else if (integ == 3) {
+                dl = 0.5 * kick_weight * length;
+            } else if (integ == 2) {
+                dl = slice_length * XTB_Y6[j];
+                kw = kick_weight * XTB_Y6[8 + j];
+                oc = (j < 7 - j) ? j : 7 - j;
+            } else {
+                dl = length;
             }
-            rad_end<SYNRAD, FRZ>(snap, P, G, a, b, slice_length);
+            magnet_drift_n<N, FRZ>(P, dl, k0d, k1d, hd, dm, b.trig, oc);
+            const bool has_kick = (integ == 3) ? (j == 0) : (j < n_sub - 1);
+            if (has_kick) magnet_kick_n<N, FRZ>(P, b, kw);
+        }
+        if (SYNRAD) {
+            for (int k = 0; k < N; ++k)
+                if (live[k]) rad_end<SYNRAD, FRZ>(snap[k], P[k], G[k], a, b, seg_length);
         }
     }
-#undef XTB_DRIFT
-#undef XTB_KICK
+    if (b.edge_out) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) edge_linear(P[k], b.edges[2], b.edges[3]);
+    }
+}
+
+// single-particle entry (generic slow path)
+template <bool SYNRAD, bool FRZ>
+__device__ __noinline__ void magnet_body(PState& P, const PSlot& G, const XtbTrackArgs& a,
+                                         const double* __restrict__ q, const int32_t aux) {
+    const bool live[1] = {true};
+    magnet_body_n<1, SYNRAD, FRZ>(reinterpret_cast<PState(&)[1]>(P), live,
+                                  reinterpret_cast<const PSlot(&)[1]>(G), a, q, aux);
 }
 
 // ------------------------------------------------------------------ edges ----

@@ -77,6 +77,7 @@ OP_DIPEDGE_NL = 66
 HEAVY_FIRST = 64
 
 NOT_ADDRESSABLE = 0xffffffff
+BODY_NK_SHIFT = 15      # OP_MAGNET_BODY aux: num_kicks field (csrc/xtb_thick.cuh::body_par)
 TILE_WORDS = 1024
 
 ONE_OVER_FACT = [1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664,
@@ -140,7 +141,29 @@ class Program:
         if opcode >= HEAVY_FIRST:
             self.has_heavy = True
 
+    def _merge_linear_edges(self):
+        """[EDGE_LIN] MAGNET_BODY [EDGE_LIN] of one element (a bend with linear edges) becomes
+        ONE body op that applies the edge kicks itself (csrc/xtb_thick.cuh::magnet_body_n):
+        one out-of-line op per bend instead of three.  Same arithmetic, same order."""
+        ops = self._cur
+        codes = [o[0] for o in ops]
+        if OP_MAGNET_BODY not in codes or len(ops) > 3:
+            return
+        ib = codes.index(OP_MAGNET_BODY)
+        before, after = ops[:ib], ops[ib + 1:]
+        if (len(before) > 1 or len(after) > 1 or not (before or after)
+                or any(o[0] != OP_EDGE_LIN for o in before + after)):
+            return
+        body = ops[ib]
+        e_in = before[0][2][:2] if before else [0.0, 0.0]
+        e_out = after[0][2][:2] if after else [0.0, 0.0]
+        body[1] |= ((1 if before else 0) << 13) | ((1 if after else 0) << 14)
+        body[2] = body[2] + list(e_in) + list(e_out)
+        self._cur = [body]
+        self.op_hist[OP_EDGE_LIN] -= len(before) + len(after)
+
     def end_element(self, static_thick):
+        self._merge_linear_edges()
         if not self._cur:
             self._cur.append([OP_NOP, 0, []])
             self.op_hist[OP_NOP] = self.op_hist.get(OP_NOP, 0) + 1
@@ -745,23 +768,24 @@ def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl,
                      | ((0 if _all_zero(coeffs_main) else 1) << 9)
                      | ((radiation_flag & 3) << 10)
                      | ((1 if drift_only else 0) << 12))
-            if num_multipole_kicks >= (1 << 19):
+            if num_multipole_kicks >= (1 << 17):
                 raise ValueError('num_multipole_kicks too large')
-            aux = flags | (num_multipole_kicks << 13)
+            aux = flags | (num_multipole_kicks << BODY_NK_SHIFT)
             if not coeffs:
                 coeffs = [0.0, 0.0]
             if not coeffs_rel:
                 coeffs_rel = [0.0, 0.0]
             ou = len(coeffs) // 2 - 1
             orl = len(coeffs_rel) // 2 - 1
-            trig = _trig_table(c['drift_model'], integrator, num_multipole_kicks, drift_only,
-                               core_length, c['h_drift'])
+            trig, n_inner = _trig_table(c['drift_model'], integrator, num_multipole_kicks,
+                                        drift_only, core_length, c['h_drift'])
             params = [core_length, c['k0_drift'], c['k1_drift'], c['h_drift'], c['h_kick'], hxl,
                       a0, a1, htot, _RawWord(ou | (orl << 32)),
                       c['k0_drift'] + c['k0_kick'], c['k1_drift'] + c['k1_kick'], k2, k3,
                       k0s, k1s, k2s, k3s,
                       *coeffs_main, *coeffs, *coeffs_rel,
-                      _RawWord(len(trig) // 4), (1 / c['h_drift']) if trig else 0.0, *trig]
+                      _RawWord((len(trig) // TRIG_STRIDE) | (n_inner << 32)),
+                      (1 / c['h_drift']) if trig else 0.0, *trig]
             prog.op(OP_MAGNET_BODY, params, aux=aux,
                     flops=_body_flops(c['drift_model'], integrator, num_multipole_kicks,
                                       drift_only, ou, coeffs_main),
@@ -789,6 +813,8 @@ def _body_drift_lengths(integrator, n_kicks, drift_only, length):
     (track_magnet.h:181-276) pass to the drift map, computed with the same operations."""
     if drift_only:
         return [length]
+    if n_kicks <= 0:
+        return []
     if integrator == 1:
         edge_w, inside_w = 0.5, 0.0
         if n_kicks > 1:
@@ -806,33 +832,36 @@ def _body_drift_lengths(integrator, n_kicks, drift_only, length):
     return [slice_length * d for d in _YOSHIDA_D]
 
 
+_Y4_NESTED_D = (0.6756035959798289, -0.17560359597982889)
+TRIG_STRIDE = 6
+
+
 def _trig_table(drift_model, integrator, n_kicks, drift_only, length, h):
-    """cos(h*s), sin(h*s), sin(h*s/2) for every length s that the polar drift / curved exact
-    bend of this body op will be called with (track_magnet_drift.h:45-87, 272-345, 521-550):
-    element constants that the reference evaluates per particle.  Flat list of
-    [s, cos, sin, sin_half] entries; evaluated with the C library's libm (math.*), the one
-    the reference's CPU build links."""
+    """cos(h*s), sin(h*s), sin(h*s/2) and RN(1/cos(h*s)) for every length s that the polar
+    drift / curved exact bend of this body op will be called with (track_magnet_drift.h:45-87,
+    272-345, 521-550): element constants that the reference evaluates per particle, evaluated
+    here with the C library's libm (math.*), the one the reference's CPU build links.
+    Returns (flat list of [s, cos, sin, sin_half, 1/cos, 0] entries, n_inner): entry
+    `outer class * n_inner + inner class`, the outer classes being the distinct sub-step
+    lengths of the integrator in `_body_drift_lengths` order and the inner ones the distinct
+    fractions of the nested Yoshida bends (csrc/xtb_thick.cuh::magnet_drift_n indexes the
+    same way)."""
     if drift_model not in (2, 4, 7, 8) or h == 0.0:
-        return []
-    lengths = []
+        return [], 1
+    if drift_model in (2, 4):
+        inner = (None,)
+    elif drift_model == 7:
+        inner = _Y4_NESTED_D
+    else:
+        inner = _YOSHIDA_D
+    out = []
     for dl in _body_drift_lengths(integrator, n_kicks, drift_only, length):
-        if dl == 0.0:
-            continue
-        if drift_model in (2, 4):
-            lengths.append(dl)
-        elif drift_model == 7:
-            lengths += [0.6756035959798289 * dl, -0.17560359597982889 * dl]
-        else:
-            lengths += [d * dl for d in _YOSHIDA_D]
-    out, seen = [], set()
-    for s in lengths:
-        if s in seen:
-            continue
-        seen.add(s)
-        out += [s, math.cos(h * s), math.sin(h * s), math.sin(0.5 * h * s)]
-    if len(out) // 4 > 24:      # (long uniform splittings repeat one length: never reached)
-        return []
-    return out
+        for d in inner:
+            s = dl if d is None else d * dl
+            ca = math.cos(h * s)
+            out += [s, ca, math.sin(h * s), math.sin(0.5 * h * s),
+                    (1.0 / ca) if ca != 0.0 else 0.0, 0.0]
+    return out, len(inner)
 
 
 _DRIFT_FLOPS = {-1: 0, 0: 17, 1: 21, 2: 45, 3: 95, 4: 60, 5: 40, 7: 4 * 45 + 9, 8: 8 * 45 + 21}
