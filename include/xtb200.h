@@ -142,6 +142,13 @@ int xtb_compact(const xtb_particles_t* particles, int64_t* perm_dev,
  * roofline denominator).  Returns achieved FLOP/s in *flops_out. */
 int xtb_measure_dfma_peak(int device, double seconds, double* flops_out);
 
+/* Self-test: the guard-free FP64 reciprocal / square root / division sequences of the thick
+ * maps (csrc/xtb_math.cuh) against the built-in IEEE operators on `n_samples` random operands
+ * with binary exponents in [-exponent_range, exponent_range].  mismatches_out[3] receives the
+ * number of results that differ in any bit (rcp, sqrt, div): expected 0, 0, 0. */
+int xtb_selftest_math(int device, int64_t n_samples, uint64_t seed, int exponent_range,
+                      uint64_t* mismatches_out);
+
 /* Kernel launches issued by this library since load (bench bookkeeping). */
 int64_t xtb_launch_count(void);
 

@@ -280,3 +280,30 @@ def test_full_size_properties():
     three = common.by_id(_track_gpu(line, p_rev, 6, True))
     for ff in common.ALL_F64 + ('state', 'at_turn', 'at_element'):
         assert np.array_equal(one[ff], three[ff], equal_nan=True), ff
+
+
+def test_guard_free_fp64_sequences_are_ieee():
+    """csrc/xtb_math.cuh: the branch-free reciprocal / square root / division of the thick
+    maps give the bits of the built-in IEEE operators (2^28 random operands each, exponents
+    within +-30 and, separately, operands of order one as the maps have them)."""
+    from xtrack_b200 import _cabi
+    assert _cabi.selftest_math(0, 1 << 28, seed=11, exponent_range=30) == (0, 0, 0)
+    assert _cabi.selftest_math(0, 1 << 28, seed=12, exponent_range=1) == (0, 0, 0)
+    assert _cabi.selftest_math(0, 1 << 26, seed=13, exponent_range=300) == (0, 0, 0)
+
+
+def test_thick_single_bend_bit_exact_on_gpu():
+    """A default RBend / Bend (Yoshida-4 integrator around the nested Yoshida polar drifts:
+    no libm call left on the device -- the element trigonometry is tabulated by the host, the
+    divisions and square roots are IEEE) is reproduced bit for bit by the EXACT kernel."""
+    for cls in (xb.RBend, xb.Bend):
+        kw = dict(length_straight=2.0) if cls is xb.RBend else dict(length=2.0)
+        el = cls(angle=0.03, k0='from_h', **kw)
+        line = xb.Line(elements=[xb.Drift(length=0.5), el, xb.Drift(length=0.5)])
+        line.particle_ref = xb.Particles(p0c=45.6e9, mass0=xb.ELECTRON_MASS_EV)
+        p_host = common.gaussian_particles(line, 301, 5, common.SIGMAS['lep'])
+        ref = common.oracle_track(line, p_host, 2)
+        got = common.by_id(_track_gpu(line, p_host, 2, True))
+        for ff in ('x', 'px', 'y', 'py', 'zeta', 'delta', 's'):
+            assert np.array_equal(got[ff], ref[ff]), (cls.__name__, ff)
+        _assert_int_fields(got, ref)

@@ -135,7 +135,12 @@ def test_single_bend_energy_loss(thick):
         p = xb.Particles(p0c=p0c, x=np.zeros(n), px=1e-4, py=-1e-4, mass0=xb.ELECTRON_MASS_EV,
                          _device='cuda:0')
         line.build_tracker(_device='cuda:0')
-        line.track(p)            # seeds the generator itself (tracker.py:1364-1365)
+        if flag == 2:
+            # fixed seeds: the statistical comparison below is then the same every run
+            # (with np.random seeds the 5e-3 bar is a ~3 sigma bar: 0.15 % spread per draw)
+            p._init_random_number_generator(
+                seeds=(np.arange(1, n + 1, dtype=np.uint64) * 104729 % (1 << 32)).astype(np.uint32))
+        line.track(p)            # flag 1: seeds the generator itself (tracker.py:1364-1365)
         assert p._has_valid_rng_state()
         res[flag] = common.by_id(p)
     gamma0 = float(res[1]['gamma0'][0])

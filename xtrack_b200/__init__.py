@@ -10,7 +10,8 @@ from .particles import Particles, LAST_INVALID_STATE, PROTON_MASS_EV, ELECTRON_M
 from .elements import (Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupole,
                        Octupole, Bend, RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation,
                        LimitRect, LimitEllipse, LimitPolygon)
-from .monitors import ParticlesMonitor, LastTurnsMonitor
+from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
+                       BeamSizeMonitor)
 from .line import Line
 
 __version__ = '0.1.0'

@@ -90,6 +90,8 @@ def load():
     lib.xtb_compact.argtypes = [ct.POINTER(XtbParticles), ct.c_void_p, ct.c_void_p, ct.c_void_p,
                                 ct.c_int, ct.c_void_p]
     lib.xtb_measure_dfma_peak.argtypes = [ct.c_int, ct.c_double, ct.POINTER(ct.c_double)]
+    lib.xtb_selftest_math.argtypes = [ct.c_int, ct.c_int64, ct.c_uint64, ct.c_int,
+                                      ct.POINTER(ct.c_uint64)]
     _lib = lib
     return lib
 
@@ -251,6 +253,13 @@ def measure_dfma_peak(device=0, seconds=1.0):
     out = (ct.c_double * 2)()
     _check(load().xtb_measure_dfma_peak(int(device), float(seconds), out))
     return float(out[0]), float(out[1])
+
+
+def selftest_math(device=0, n_samples=1 << 28, seed=1, exponent_range=30):
+    """Mismatches (rcp, sqrt, div) of csrc/xtb_math.cuh against the IEEE operators."""
+    out = (ct.c_uint64 * 3)()
+    _check(load().xtb_selftest_math(int(device), int(n_samples), int(seed), int(exponent_range), out))
+    return tuple(int(v) for v in out)
 
 
 def launch_count():

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/xtb200.h"
+#include "xtb_math.cuh"
 #include "xtb_ops.h"
 #include "xtb_state.cuh"
 
@@ -569,5 +570,61 @@ extern "C" int xtb_measure_dfma_peak(int device, double seconds, double* flops_o
     cudaSetDevice(prev);
     flops_out[0] = last_half_time > 0 ? last_half_flop / last_half_time : best;
     flops_out[1] = best;
+    return XTB_OK;
+}
+
+// ---- self-test of the guard-free FP64 sequences (xtb_math.cuh) ------------------------
+__device__ __forceinline__ uint64_t xtb_mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// a double with a random significand and a binary exponent drawn from [-erange, erange]
+__device__ __forceinline__ double xtb_rand_double(uint64_t r, int erange, bool with_sign) {
+    const uint64_t mant = r & 0x000fffffffffffffull;
+    const int e = (erange > 0) ? (int) ((r >> 52) % (uint64_t) (2 * erange + 1)) - erange : 0;
+    const uint64_t sign = with_sign ? (r >> 63) << 63 : 0ull;
+    return __longlong_as_double((long long) (sign | ((uint64_t) (1023 + e) << 52) | mant));
+}
+__global__ void xtb_selftest_math_kernel(int64_t n_per_thread, uint64_t seed, int erange,
+                                         unsigned long long* mismatches) {
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad_rcp = 0, bad_sqrt = 0, bad_div = 0;
+    for (int64_t i = 0; i < n_per_thread; ++i) {
+        const uint64_t r0 = xtb_mix64(seed + tid * 0x100000001B3ull + (uint64_t) i * 0x9E3779B9ull);
+        const uint64_t r1 = xtb_mix64(r0);
+        const double b = xtb_rand_double(r0, erange, true);
+        const double a = xtb_rand_double(r1, erange, true);
+        const double p = fabs(b);
+        if (__double_as_longlong(xtb_rcp(b)) != __double_as_longlong(1.0 / b)) bad_rcp++;
+        if (__double_as_longlong(xtb_sqrt(p)) != __double_as_longlong(sqrt(p))) bad_sqrt++;
+        if (__double_as_longlong(xtb_div(a, b)) != __double_as_longlong(a / b)) bad_div++;
+    }
+    if (bad_rcp) atomicAdd(&mismatches[0], bad_rcp);
+    if (bad_sqrt) atomicAdd(&mismatches[1], bad_sqrt);
+    if (bad_div) atomicAdd(&mismatches[2], bad_div);
+}
+
+extern "C" int xtb_selftest_math(int device, int64_t n_samples, uint64_t seed, int exponent_range,
+                                 uint64_t* mismatches_out /* [3]: rcp, sqrt, div */) {
+    if (!mismatches_out || n_samples <= 0) return fail(XTB_E_INVALID, "bad argument");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    cudaMemset(d, 0, 3 * sizeof(unsigned long long));
+    const unsigned grid = 148u * 8u, block = 256u;
+    const int64_t per_thread = (n_samples + (int64_t) grid * block - 1) / ((int64_t) grid * block);
+    xtb_selftest_math_kernel<<<grid, block>>>(per_thread, seed, exponent_range, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(XTB_E_CUDA, "math self-test: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    for (int i = 0; i < 3; ++i) mismatches_out[i] = h[i];
     return XTB_OK;
 }

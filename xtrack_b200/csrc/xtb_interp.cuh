@@ -87,6 +87,58 @@ static __device__ __noinline__ void last_turns_record(const xtb_last_turns_monit
     }
 }
 
+// BeamPositionMonitor / BeamSizeMonitor, monitors/beam_position_monitor.h:16-58 and
+// beam_size_monitor.h:16-64: per time slot, the count and the sums of x, y (and x^2, y^2)
+// of the particles that cross the monitor in that slot.
+//   q: (int) start_at_turn, (int) particle_id_start, (int) particle_id_stop, frev,
+//      sampling_frequency, (int) n_slots, (ptr) record = [count | x_sum | y_sum | x2_sum |
+//      y2_sum], n_slots doubles each;  aux = number of sums (3: position, 5: size)
+// The reference adds with one atomicAdd per particle and quantity.  Here the lanes of a warp
+// that fall into the same slot (a bunch: all of them) are summed in the warp first and ONE
+// lane adds to memory: 5 atomics per warp instead of 160 to five addresses everyone wants.
+// (The order of a floating-point sum is free in the reference too: OpenMP / GPU atomics.)
+static __device__ __noinline__ void beam_monitor_record(const double* __restrict__ q, const int32_t n_sums,
+                                                        const PState& P, const PSlot& G) {
+    const int64_t start_at_turn = __double_as_longlong(q[0]);
+    const int64_t id_start = __double_as_longlong(q[1]), id_stop = __double_as_longlong(q[2]);
+    const double frev = q[3], sampling_frequency = q[4];
+    const int64_t max_slot = __double_as_longlong(q[5]);
+    double* rec = reinterpret_cast<double*>(__double_as_longlong(q[6]));
+    const int64_t particle_id = G.ldgi(F_PARTICLE_ID);
+    int64_t slot = -1;
+    if (id_stop < 0 || (id_start <= particle_id && particle_id < id_stop)) {
+        const double at_turn = (double) P.at_turn;
+        const double beta0 = G.ld(F_BETA0);
+        slot = (int64_t) round(sampling_frequency
+                               * ((at_turn - start_at_turn) / frev - P.zeta / beta0 / XTB_C_LIGHT));
+        if (!(slot >= 0 && slot < max_slot)) slot = -1;
+    }
+    double v[5] = {1.0, P.x, P.y, P.x * P.x, P.y * P.y};
+#ifdef __CUDA_ARCH__
+    const unsigned active = __activemask();
+    int same = 0;
+    __match_all_sync(active, (long long) slot, &same);
+    if (same) {
+        if (slot < 0) return;
+        const int leader = __ffs(active) - 1;
+        double sum[5] = {0., 0., 0., 0., 0.};
+        for (unsigned m = active; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            for (int j = 0; j < 5; ++j)
+                if (j < n_sums) sum[j] += __shfl_sync(active, v[j], src);
+        }
+        if ((int) (threadIdx.x & 31) == leader)
+            for (int j = 0; j < n_sums; ++j) atomicAdd(rec + j * max_slot + slot, sum[j]);
+        return;
+    }
+    if (slot < 0) return;
+    for (int j = 0; j < n_sums; ++j) atomicAdd(rec + j * max_slot + slot, v[j]);
+#else
+    if (slot < 0) return;
+    for (int j = 0; j < n_sums; ++j) rec[j * max_slot + slot] += v[j];
+#endif
+}
+
 // Generic thin ops, kept out of line so that they do not weigh on the hot loop's
 // register allocation.  `P.at_element` holds the current element index here.
 template <bool FRZ>
@@ -153,6 +205,9 @@ static __device__ __noinline__ void generic_op(const uint32_t op, const int32_t 
         break;
     case XTB_OP_LAST_TURNS:
         if (live) last_turns_record(a.inline_ltm[aux], P, G);
+        break;
+    case XTB_OP_BEAM_MON:
+        if (live) beam_monitor_record(q, aux, P, G);
         break;
     case XTB_OP_KILL:
         kill_particle<FRZ>(P, G, aux);

@@ -15,6 +15,7 @@
 #pragma once
 #include "xtb_state.cuh"
 #include "xtb_thin.cuh"
+#include "xtb_math.cuh"
 
 #define XTB_QELEM 1.60217662e-19
 #define XTB_EPSILON_0 8.854187817620e-12
@@ -106,8 +107,9 @@ XTB_CONST_TABLE XTB_Y6[16] = {
     7.845136104775599639182814826199e-01, 0.};
 
 // track_polar_drift_single_particle, track_magnet_drift.h:45-87, on N particles at once
-// (N independent dependency chains for the FP64 pipe).  The divisions by cos(h*s), pz and
-// rvv use the reciprocals at hand (div_by): same correctly rounded quotients.
+// (N independent dependency chains for the FP64 pipe: straight-line code, the square root,
+// reciprocals and division being the guard-free fast paths of xtb_math.cuh).  The divisions by
+// cos(h*s), pz and rvv use the reciprocals at hand (div_by): same correctly rounded quotients.
 template <int N, bool FRZ>
 __device__ __forceinline__ void polar_drift_n(PState (&P)[N], const double length, const double h,
                                               const TrigTab& tt, const int idx) {
@@ -115,30 +117,38 @@ __device__ __forceinline__ void polar_drift_n(PState (&P)[N], const double lengt
     const double rho = (tt.n > 0) ? tt.rho : 1 / h;
     double ca, sa, sa2, rca;
     trig_of(tt, idx, h, s, ca, sa, sa2, rca);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const double rvv = P[k].rvv;
-        const double x = P[k].x, y = P[k].y, px = P[k].px, py = P[k].py;
-        const double one_plus_delta = P[k].delta + 1.0;
-        const double pz = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(px) - XTB_POW2(py));
-        const double _pz = 1 / pz;
-        const double pxt = px * _pz;
-        const double _ptt = 1 / (ca - sa * pxt);
-        const double pst = (x + rho) * sa * _pz * _ptt;
-        const double new_x = (x + rho * (2 * sa2 * sa2 + sa * pxt)) * _ptt;
-        const double new_px = ca * px + sa * pz;
-        const double new_y = y + pst * py;
-        // one_plus_delta * (x + rho) * sa / ca / pz / (1 - px * sa / ca / pz)
-        const double num = div_by(div_by(one_plus_delta * (x + rho) * sa, ca, rca), pz, _pz);
-        const double den = 1 - div_by(div_by(px * sa, ca, rca), pz, _pz);
-        const double delta_ell = num / den;
-        P[k].x = new_x;
-        P[k].px = new_px;
-        P[k].y = new_y;
-        if (!FRZ) {
-            P[k].zeta += length - div_by(delta_ell, rvv, P[k].rv0v);
-            P[k].s += s;
-        }
+    // (each statement of the reference's map, for all N particles in turn: see XTB_LANES)
+    double opd[N], pz2[N], pz[N], ipz[N], pxt[N], dtt[N], iptt[N], xr[N];
+    XTB_LANES opd[k] = P[k].delta + 1.0;
+    XTB_LANES pz2[k] = XTB_POW2(opd[k]) - XTB_POW2(P[k].px) - XTB_POW2(P[k].py);
+    xtb_vsqrt<N>(pz, pz2);
+    xtb_vrcp<N>(ipz, pz);                              // _pz = 1 / pz
+    XTB_LANES pxt[k] = P[k].px * ipz[k];
+    XTB_LANES dtt[k] = ca - sa * pxt[k];
+    xtb_vrcp<N>(iptt, dtt);                            // _ptt = 1 / (ca - sa * pxt)
+    XTB_LANES xr[k] = P[k].x + rho;
+    double pst[N], new_x[N], new_px[N], new_y[N], num[N], den[N], dell[N];
+    XTB_LANES pst[k] = xr[k] * sa * ipz[k] * iptt[k];
+    XTB_LANES new_x[k] = (P[k].x + rho * (2 * sa2 * sa2 + sa * pxt[k])) * iptt[k];
+    XTB_LANES new_px[k] = ca * P[k].px + sa * pz[k];
+    XTB_LANES new_y[k] = P[k].y + pst[k] * P[k].py;
+    // delta_ell = one_plus_delta * (x + rho) * sa / ca / pz / (1 - px * sa / ca / pz)
+    XTB_LANES num[k] = opd[k] * xr[k] * sa;
+    XTB_LANES den[k] = P[k].px * sa;
+    XTB_LANES num[k] = div_by(num[k], ca, rca);
+    XTB_LANES den[k] = div_by(den[k], ca, rca);
+    XTB_LANES num[k] = div_by(num[k], pz[k], ipz[k]);
+    XTB_LANES den[k] = 1 - div_by(den[k], pz[k], ipz[k]);
+    xtb_vdiv<N>(dell, num, den);
+    XTB_LANES {
+        P[k].x = new_x[k];
+        P[k].px = new_px[k];
+        P[k].y = new_y[k];
+    }
+    if (!FRZ) {
+        XTB_LANES dell[k] = div_by(dell[k], P[k].rvv, P[k].rv0v);
+        XTB_LANES P[k].zeta += length - dell[k];
+        XTB_LANES P[k].s += s;
     }
 }
 template <bool FRZ>

@@ -18,11 +18,14 @@ import json
 import numpy as np
 
 from . import elements as _el
-from .monitors import ParticlesMonitor, LastTurnsMonitor
+from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
+                       BeamSizeMonitor)
 from .particles import Particles
 
 _MONITOR_CLASSES = {'ParticlesMonitor': ParticlesMonitor,
-                    'LastTurnsMonitor': LastTurnsMonitor}
+                    'LastTurnsMonitor': LastTurnsMonitor,
+                    'BeamPositionMonitor': BeamPositionMonitor,
+                    'BeamSizeMonitor': BeamSizeMonitor}
 
 
 class Line:

@@ -70,6 +70,7 @@ OP_KILL = 50
 OP_SET_STATE = 51
 OP_ADD_S_ZETA = 52
 OP_ADD_X = 53
+OP_BEAM_MON = 54
 # heavy set
 OP_MAGNET_BODY = 64
 OP_MAGNET_EDGE = 65
@@ -77,6 +78,7 @@ OP_DIPEDGE_NL = 66
 HEAVY_FIRST = 64
 
 NOT_ADDRESSABLE = 0xffffffff
+MASK64 = (1 << 64) - 1
 BODY_NK_SHIFT = 15      # OP_MAGNET_BODY aux: num_kicks field (csrc/xtb_thick.cuh::body_par)
 TILE_WORDS = 1024
 
@@ -129,6 +131,7 @@ class Program:
         self.has_heavy = False
         self.monitors = []      # in-line ParticlesMonitor objects (index = aux)
         self.last_turns_monitors = []
+        self.beam_monitors = []     # BeamPosition / BeamSize monitors (records kept alive here)
 
     def op(self, opcode, params=(), aux=0, flops=None, transc=0):
         self._cur.append([int(opcode), int(aux), [float(p) if not isinstance(p, _RawWord)
@@ -1167,12 +1170,25 @@ def lower_element(prog, el, cfg):
         prog.op(OP_LAST_TURNS, aux=len(prog.last_turns_monitors) - 1)
         return False
 
+    if name in ('BeamPositionMonitor', 'BeamSizeMonitor'):
+        # the op carries the monitor's parameters and the device address of its record
+        rec = el.allocate(cfg.get('device'))
+        stop = el.particle_id_start + el.num_particles
+        prog.op(OP_BEAM_MON, [_RawWord(el.start_at_turn & MASK64),
+                              _RawWord(el.particle_id_start & MASK64), _RawWord(stop & MASK64),
+                              el.frev, el.sampling_frequency, _RawWord(el.n_slots),
+                              _RawWord(rec.data_ptr()), 0.0],
+                aux=len(el.properties), flops=10)
+        prog.beam_monitors.append(el)
+        return False
+
     raise NotImplementedError(f'element class {name} is outside the hot-path contract')
 
 
-def lower_line(elements, *, synrad=False, exact_drifts=False):
-    """Lowers a sequence of host elements.  Returns the `Program`."""
-    cfg = dict(synrad=bool(synrad), exact_drifts=bool(exact_drifts))
+def lower_line(elements, *, synrad=False, exact_drifts=False, device=None):
+    """Lowers a sequence of host elements.  Returns the `Program`.  `device`: where the
+    records of in-line beam monitors live (their address goes into the program)."""
+    cfg = dict(synrad=bool(synrad), exact_drifts=bool(exact_drifts), device=device)
     prog = Program()
     cache = {}
     for el in elements:

@@ -175,3 +175,95 @@ class LastTurnsMonitor(BeamElement):
             c = (c + off[:, np.newaxis]) % val.shape[1]
             return val[r, c]
         raise AttributeError(attr)
+
+
+class _BeamSlotMonitor(BeamElement):
+    """Common part of BeamPositionMonitor / BeamSizeMonitor: per time slot
+    `i = round(sampling_frequency * ((at_turn - start_at_turn) / frev - zeta / beta0 / c0))`
+    the count and the sums of x, y (, x^2, y^2) of the particles crossing the monitor
+    (xtrack/monitors/beam_position_monitor.py:25-137, beam_size_monitor.py:27-149).
+    The record lives on the tracking device: one float64 tensor `[n_sums, n_slots]`."""
+    allow_rot_and_shift = False
+    behaves_like_drift = True
+    allow_loss_refinement = True
+    properties = ()
+
+    def __init__(self, *, particle_id_range=None, particle_id_start=None, num_particles=None,
+                 start_at_turn=None, stop_at_turn=None, frev=None, sampling_frequency=None,
+                 _device='cpu', **kwargs):
+        if particle_id_range is None:
+            if particle_id_start is None:
+                particle_id_start = 0
+            if num_particles is None:
+                num_particles = -1
+        elif particle_id_start is None and num_particles is None:
+            particle_id_start = particle_id_range[0]
+            num_particles = particle_id_range[1] - particle_id_range[0]
+        else:
+            raise ValueError('Parameter `particle_id_range` must not be used together with '
+                             '`num_particles` and/or `particle_id_start`')
+        self.particle_id_start = int(particle_id_start)
+        self.num_particles = int(num_particles)
+        self.start_at_turn = int(0 if start_at_turn is None else start_at_turn)
+        self.stop_at_turn = int(0 if stop_at_turn is None else stop_at_turn)
+        self.frev = float(1 if frev is None else frev)
+        self.sampling_frequency = float(1 if sampling_frequency is None else sampling_frequency)
+        self.n_slots = int(round((self.stop_at_turn - self.start_at_turn)
+                                 * self.sampling_frequency / self.frev))
+        self._device = torch.device(_device)
+        self._data = None
+        data = kwargs.pop('data', None)
+        self._finish(kwargs)
+        if data is not None:
+            self.allocate()
+            for ii, prop in enumerate(self.properties):
+                self._data[ii] = torch.as_tensor(np.asarray(data[prop], dtype=np.float64))
+
+    @classmethod
+    def from_dict(cls, dct):
+        dct = dict(dct)
+        for kk in ('__class__', '_index'):
+            dct.pop(kk, None)
+        return cls(**dct)
+
+    def to_dict(self):
+        return {'__class__': type(self).__name__, 'particle_id_start': self.particle_id_start,
+                'num_particles': self.num_particles, 'start_at_turn': self.start_at_turn,
+                'stop_at_turn': self.stop_at_turn, 'frev': self.frev,
+                'sampling_frequency': self.sampling_frequency,
+                'data': {pp: getattr(self, pp).tolist() for pp in self.properties}}
+
+    def allocate(self, device=None):
+        if device is not None:
+            self._device = torch.device(device)
+        if self._data is None:
+            self._data = torch.zeros((len(self.properties), max(self.n_slots, 1)),
+                                     dtype=torch.float64, device=self._device)
+        elif self._data.device != self._device:
+            self._data = self._data.to(self._device)
+        return self._data
+
+    def __getattr__(self, attr):
+        if attr.startswith('_'):
+            raise AttributeError(attr)
+        props = type(self).properties
+        if attr in props:
+            return self.allocate()[props.index(attr), :self.n_slots].cpu().numpy()
+        if attr in ('x_mean', 'y_mean', 'x_cen', 'y_cen', 'x_centroid', 'y_centroid'):
+            with np.errstate(invalid='ignore', divide='ignore'):   # NaN for empty slots
+                return getattr(self, attr[0] + '_sum') / self.count
+        if attr in ('x_var', 'y_var') and 'x2_sum' in props:
+            with np.errstate(invalid='ignore', divide='ignore'):
+                return (getattr(self, attr[0] + '2_sum') / self.count
+                        - getattr(self, attr[0] + '_mean') ** 2)
+        if attr in ('x_std', 'y_std') and 'x2_sum' in props:
+            return getattr(self, attr[0] + '_var') ** 0.5
+        raise AttributeError(attr)
+
+
+class BeamPositionMonitor(_BeamSlotMonitor):
+    properties = ('count', 'x_sum', 'y_sum')
+
+
+class BeamSizeMonitor(_BeamSlotMonitor):
+    properties = ('count', 'x_sum', 'y_sum', 'x2_sum', 'y2_sum')

@@ -52,7 +52,8 @@ class Tracker:
         if self._lattice is not None and key == self._config_key:
             return
         synrad, exact_drifts = key
-        prog = lowering.lower_line(self.line.elements, synrad=synrad, exact_drifts=exact_drifts)
+        prog = lowering.lower_line(self.line.elements, synrad=synrad, exact_drifts=exact_drifts,
+                                   device=self.device)
         fused = prog.finish(fused=True) if self.fuse else (None, None)
         plain = prog.finish(fused=False)
         self.line_length = self.line.get_length()
