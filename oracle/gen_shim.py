@@ -172,6 +172,33 @@ XTB_LTD_SET(x, float) XTB_LTD_SET(px, float) XTB_LTD_SET(y, float) XTB_LTD_SET(p
 XTB_LTD_SET(delta, float) XTB_LTD_SET(zeta, float)
 '''
 
+BEAM_MONITOR_API = r'''
+/* ---- BeamPositionMonitorData / BeamSizeMonitorData (monitors/beam_position_monitor.py:18-36,
+ *      beam_size_monitor.py:18-38): same layout, the size monitor has two more sums ---- */
+typedef struct XtbBeamRecord_s { int64_t n; double *count, *x_sum, *y_sum, *x2_sum, *y2_sum; } *XtbBeamRecord;
+typedef struct XtbBeamMonitorData_s {
+    int64_t particle_id_start, num_particles, start_at_turn, stop_at_turn;
+    double frev, sampling_frequency;
+    XtbBeamRecord data;
+} *XtbBeamMonitorData;
+#define XTB_BEAMMON_API(CLS) \
+typedef XtbBeamMonitorData CLS##Data; typedef XtbBeamRecord CLS##Record; \
+GPUFUN int64_t CLS##Data_get_start_at_turn(CLS##Data el){ return el->start_at_turn; } \
+GPUFUN int64_t CLS##Data_get_particle_id_start(CLS##Data el){ return el->particle_id_start; } \
+GPUFUN int64_t CLS##Data_get_num_particles(CLS##Data el){ return el->num_particles; } \
+GPUFUN double CLS##Data_get_frev(CLS##Data el){ return el->frev; } \
+GPUFUN double CLS##Data_get_sampling_frequency(CLS##Data el){ return el->sampling_frequency; } \
+GPUFUN CLS##Record CLS##Data_getp_data(CLS##Data el){ return el->data; } \
+GPUFUN int64_t CLS##Record_len_count(CLS##Record r){ return r->n; } \
+GPUFUN double* CLS##Record_getp1_count(CLS##Record r, int64_t i){ return r->count + i; } \
+GPUFUN double* CLS##Record_getp1_x_sum(CLS##Record r, int64_t i){ return r->x_sum + i; } \
+GPUFUN double* CLS##Record_getp1_y_sum(CLS##Record r, int64_t i){ return r->y_sum + i; } \
+GPUFUN double* CLS##Record_getp1_x2_sum(CLS##Record r, int64_t i){ return r->x2_sum + i; } \
+GPUFUN double* CLS##Record_getp1_y2_sum(CLS##Record r, int64_t i){ return r->y2_sum + i; }
+XTB_BEAMMON_API(BeamPositionMonitor)
+XTB_BEAMMON_API(BeamSizeMonitor)
+'''
+
 RECORD_STUBS = r'''
 /* In-kernel photon logging is outside the contract: the record handle is NULL
    everywhere (synrad_spectrum.h:505 checks it), these only satisfy the compiler. */
@@ -214,6 +241,9 @@ def generate():
     out.append(MONITOR_API)
     out.append('#include "xtrack/monitors/particles_monitor.h"')
     out.append('#include "xtrack/monitors/last_turns_monitor.h"')
+    out.append(BEAM_MONITOR_API)
+    out.append('#include "xtrack/monitors/beam_position_monitor.h"')
+    out.append('#include "xtrack/monitors/beam_size_monitor.h"')
     for name in CLASS_ORDER:
         out.append(gen_element_struct(name))
         out.append(f'#include "xtrack/beam_elements/elements_src/{SPECS[name]["header"]}"')
@@ -232,6 +262,8 @@ def generate():
         out.append('            break;')
     out.append('        case 1000: ParticlesMonitor_track_local_particle((ParticlesMonitorData) el, lpart); break;')
     out.append('        case 1001: LastTurnsMonitor_track_local_particle((LastTurnsMonitorData) el, lpart); break;')
+    out.append('        case 1002: BeamPositionMonitor_track_local_particle((BeamPositionMonitorData) el, lpart); break;')
+    out.append('        case 1003: BeamSizeMonitor_track_local_particle((BeamSizeMonitorData) el, lpart); break;')
     out.append('    }\n}')
     out.append('#endif')
     return '\n'.join(out) + '\n'

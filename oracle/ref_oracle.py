@@ -63,6 +63,18 @@ class LastTurnsMonitorC(ct.Structure):
                 + [('data', ct.POINTER(LastTurnsDataC))])
 
 
+class BeamRecordC(ct.Structure):
+    _fields_ = ([('n', ct.c_int64)]
+                + [(n, ct.POINTER(ct.c_double)) for n in ('count', 'x_sum', 'y_sum', 'x2_sum', 'y2_sum')])
+
+
+class BeamMonitorC(ct.Structure):
+    _fields_ = ([(n, ct.c_int64) for n in ('particle_id_start', 'num_particles', 'start_at_turn',
+                                           'stop_at_turn')]
+                + [('frev', ct.c_double), ('sampling_frequency', ct.c_double),
+                   ('data', ct.POINTER(BeamRecordC))])
+
+
 _STRUCTS = {}
 
 
@@ -189,6 +201,8 @@ class RefElements:
             return self._make_monitor(el), 1000
         if name == 'LastTurnsMonitor':
             return self._make_last_turns(el), 1001
+        if name in ('BeamPositionMonitor', 'BeamSizeMonitor'):
+            return self._make_beam_monitor(el), 1002 if name == 'BeamPositionMonitor' else 1003
         if name not in SPECS:
             raise NotImplementedError(f'oracle: element class {name} not supported')
         st = _struct_for(name)()
@@ -209,6 +223,21 @@ class RefElements:
     def _make_monitor(self, mon):
         cm, keep = make_monitor_struct(mon)
         self._keep += [cm, keep]
+        return ct.addressof(cm)
+
+    def _make_beam_monitor(self, mon):
+        """The oracle accumulates into `mon._host`: float64 [5, n_slots] (rows count, x_sum,
+        y_sum, x2_sum, y2_sum; the position monitor uses the first three)."""
+        rec = BeamRecordC()
+        rec.n = mon.n_slots
+        for ii, nn in enumerate(('count', 'x_sum', 'y_sum', 'x2_sum', 'y2_sum')):
+            setattr(rec, nn, mon._host[ii].ctypes.data_as(ct.POINTER(ct.c_double)))
+        cm = BeamMonitorC()
+        for nn in ('particle_id_start', 'num_particles', 'start_at_turn', 'stop_at_turn',
+                   'frev', 'sampling_frequency'):
+            setattr(cm, nn, getattr(mon, nn))
+        cm.data = ct.pointer(rec)
+        self._keep += [rec, cm]
         return ct.addressof(cm)
 
     def _make_last_turns(self, mon):

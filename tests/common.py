@@ -190,3 +190,28 @@ def seed_rng_host(particles, seeds):
     for nn in ro.U32_VARS:
         setattr(particles, nn, hp.arrays[nn])
     return particles
+
+
+def beam_monitor_ring(kind, n=400, turns=6):
+    """SPS ring (losses on the way) with a BeamPositionMonitor / BeamSizeMonitor in the middle:
+    4 slots per turn (sampling_frequency = 4 frev) so that zeta sorts the beam into several
+    slots, id range restricted.  Returns (line, reference line for the oracle, its monitor,
+    our monitor, host particles)."""
+    line = load_line('sps')
+    cls = getattr(xb, kind)
+    frev = 299792458.0 / line.get_length()
+    kw = dict(particle_id_range=(15, n - 20), start_at_turn=1, stop_at_turn=turns - 1,
+              frev=frev, sampling_frequency=4 * frev)
+    els = list(line.elements)
+    mon = cls(**kw)
+    els.insert(len(els) // 2, mon)
+    line2 = xb.Line(elements=els)
+    line2.particle_ref = line.particle_ref
+    mon_ref = cls(**kw)
+    mon_ref._host = np.zeros((5, mon_ref.n_slots))
+    els_ref = list(els)
+    els_ref[len(line.elements) // 2] = mon_ref
+    sig = dict(SIGMAS['sps'])
+    sig['zeta'] = 0.25 * line.get_length() / 4          # spread over neighbouring slots
+    p_host = gaussian_particles(line2, n, 3, sig, scale=5.0)
+    return line2, els_ref, mon_ref, mon, p_host

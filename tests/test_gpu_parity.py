@@ -307,3 +307,25 @@ def test_thick_single_bend_bit_exact_on_gpu():
         for ff in ('x', 'px', 'y', 'py', 'zeta', 'delta', 's'):
             assert np.array_equal(got[ff], ref[ff]), (cls.__name__, ff)
         _assert_int_fields(got, ref)
+
+
+@pytest.mark.parametrize('kind', ['BeamPositionMonitor', 'BeamSizeMonitor'])
+def test_beam_monitors_vs_oracle_gpu(kind):
+    """In-kernel BeamPositionMonitor / BeamSizeMonitor (warp-aggregated atomics) against the
+    reference's monitor code: counts identical, sums equal up to the order of the additions."""
+    import ref_oracle as ro
+    turns = 6
+    line2, els_ref, mon_ref, mon, p_host = common.beam_monitor_ring(kind, n=5000, turns=turns)
+    hp = ro.HostParticles.from_particles(p_host)
+    ro.track_line(hp, ro.RefElements(els_ref), num_turns=turns, ele_start=0,
+                  num_ele_track=len(els_ref), flag_end_turn_actions=True,
+                  flag_reset_s_at_end_turn=True, line_length=line2.get_length(),
+                  global_xy_limit=1.0)
+    ref = hp.sorted_by_id()
+    got = common.by_id(_track_gpu(line2, p_host, turns, True))
+    assert np.array_equal(got['state'], ref['state'])
+    assert np.array_equal(mon.count, mon_ref._host[0])
+    assert mon.count.sum() > 1000
+    for ii, nn in enumerate(mon.properties):
+        np.testing.assert_allclose(getattr(mon, nn), mon_ref._host[ii], rtol=1e-11, atol=1e-13,
+                                   err_msg=nn)

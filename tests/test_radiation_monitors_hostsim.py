@@ -194,6 +194,37 @@ def test_last_turns_monitor_in_ring_vs_oracle():
         assert np.array_equal(dd[nn].numpy(), mon_ref._host[nn]), nn
 
 
+@pytest.mark.parametrize('kind', ['BeamPositionMonitor', 'BeamSizeMonitor'])
+def test_beam_monitors_vs_oracle(kind):
+    """monitors/beam_position_monitor.h:16-58, beam_size_monitor.h:16-64 against the
+    reference's own code: counts identical, sums equal up to the order of the additions
+    (the reference adds with atomics; a few ulp of the sum)."""
+    import ref_oracle as ro
+    turns = 6
+    line2, els_ref, mon_ref, mon, p_host = common.beam_monitor_ring(kind, turns=turns)
+    hp = ro.HostParticles.from_particles(p_host)
+    ro.track_line(hp, ro.RefElements(els_ref), num_turns=turns, ele_start=0,
+                  num_ele_track=len(els_ref), flag_end_turn_actions=True,
+                  flag_reset_s_at_end_turn=True, line_length=line2.get_length(),
+                  global_xy_limit=1.0)
+    ref = hp.sorted_by_id()
+    got = common.by_id(_track(line2, p_host, turns))
+    assert np.array_equal(got['state'], ref['state'])
+    assert mon_ref._host[0].sum() > 100 and (mon_ref._host[0] > 0).sum() >= 6
+    assert np.array_equal(mon.count, mon_ref._host[0])
+    for ii, nn in enumerate(mon.properties):
+        np.testing.assert_allclose(getattr(mon, nn), mon_ref._host[ii], rtol=1e-13, atol=1e-18,
+                                   err_msg=nn)
+    filled = mon.count > 0
+    np.testing.assert_allclose(mon.x_mean[filled], (mon_ref._host[1] / mon_ref._host[0])[filled],
+                               rtol=1e-12)
+    if kind == 'BeamSizeMonitor':
+        assert np.all(mon.x_std[filled & (mon.count > 1)] > 0)
+    # dict round trip keeps parameters and record
+    mon2 = type(mon).from_dict(mon.to_dict())
+    assert mon2.n_slots == mon.n_slots and np.array_equal(mon2.count, mon.count)
+
+
 def test_cabi_library_exports_every_declared_symbol():
     """§8(b): libxtb200.so loads without a GPU and exports every function that
     include/xtb200.h declares (no compute call is made here)."""

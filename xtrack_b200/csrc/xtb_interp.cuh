@@ -589,43 +589,116 @@ L_STOP:
 }
 
 #ifdef XTB_WITH_HEAVY
-// A thick-magnet body on ALL lanes of the thread at once (xtb_thick.cuh::magnet_body_n: the
-// lanes are independent dependency chains in one instruction stream).  Same bookkeeping as
-// xtb_slow_op.  Lanes without a particle run on the benign state and are reset to it.
+// The run loop of the thick lattices.  A thick ring is a sequence of magnet bodies and
+// drifts (LEP: 92 % of the ops); going back to xtb_run_fast / xtb_run_tile between them cost
+// a fifth of the kernel in state round trips through thread-local memory (ncu,
+// profiles/r01_ncu_lep.md).  This loop keeps the lanes in registers over a whole RUN of
+//   XTB_OP_MAGNET_BODY (any flags, drift prefix), XTB_OP_FDRIFT (with / without prefix) and
+//   generic XTB_OP_DRIFT ops,
+// the bodies on all lanes at once (xtb_thick.cuh::magnet_body_n), and returns at the first op
+// of another kind (lanes.off points at it).  Element bookkeeping exactly as xtb_slow_op /
+// xtb_run_tile: global aperture check after statically thick elements, loss check and
+// at_element + 1 at the end of an element (tracker.py:681-711); a lost particle is stored at
+// once and its lane goes on, benign.
 template <int NPT, bool SYNRAD, bool FRZ>
-static __device__ __noinline__ void xtb_slow_body(XtbLanes<NPT, PState>& lanes, const XtbPass ps,
-                                                  const uint32_t h, const int32_t aux,
-                                                  const double* __restrict__ q,
-                                                  const XtbTrackArgs& a) {
+static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<NPT, PState>& lanes,
+                                                  const XtbPass ps, const XtbTrackArgs& a) {
     PState T[NPT];
     PSlot G[NPT];
     bool live[NPT];
+    int32_t ae_base[NPT];
 #pragma unroll
     for (int k = 0; k < NPT; ++k) {
         G[k].p = &a.part;  G[k].i = lanes.slot[k];  G[k].c = &lanes.C[k];
         live[k] = lanes.live[k];
         T[k] = lanes.P[k];
+        ae_base[k] = 0;
         if (live[k]) {
-            T[k] = pstate_full(lanes.P[k], G[k], ps, lanes.eidx);
-            if ((a.flag_monitor == 2) && (h & (XTB_F_START << 8))) monitor_record(a.mon, T[k], G[k]);
+            T[k].at_turn = G[k].ldi(F_AT_TURN) + ps.turn_inc;
+            ae_base[k] = (ps.el_reset ? 0 : (int32_t) G[k].ldi(F_AT_ELEMENT)) + (int32_t) ps.el_off;
         }
     }
-    magnet_body_n<NPT, SYNRAD, FRZ>(T, live, G, a, q, aux);
+    uint32_t off = lanes.off, eidx = lanes.eidx;
+    const double lim = a.global_xy_limit;
+
+    // lane k is lost in the current element (index eidx): write it back, go on benign
+    auto retire = [&](const int k) {
+        T[k].at_element = ae_base[k] + (int32_t) eidx;
+        pstate_store(T[k], G[k]);
+        live[k] = false;
+        lanes.live[k] = false;
+        pstate_benign(T[k]);
+    };
+    // end of a statically thick element: global aperture check, loss check, at_element + 1
+    auto end_thick = [&]() {
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        if (!live[k]) {
-            pstate_benign(lanes.P[k]);
-            continue;
+        for (int k = 0; k < NPT; ++k) {
+            if (!live[k]) { pstate_benign(T[k]);  continue; }
+            if (!a.ignore_global) global_aperture_check(T[k], lim);
+            if (T[k].state <= 0) retire(k);
         }
-        if ((h & (XTB_F_GLOBAL << 8)) && !a.ignore_global) global_aperture_check(T[k], a.global_xy_limit);
-        if ((h & (XTB_F_END << 8)) && T[k].state <= 0) {
-            pstate_store(T[k], G[k]);       // tracker.py:702-711
-            lanes.live[k] = false;
-            pstate_benign(lanes.P[k]);
+        eidx += 1;
+    };
+
+    for (;;) {
+        const xtb_w128 hw = xtb_ld_w(tb, off);
+        const uint32_t h = (uint32_t) hw.x;
+        const uint32_t op = h & 0xffu;
+        const double L = __longlong_as_double((long long) hw.y);
+        if (op == XTB_OP_MAGNET_BODY || op == XTB_OP_DRIFT) {
+            const int32_t aux = (int32_t) (hw.x >> 32);
+            const double* __restrict__ q = reinterpret_cast<const double*>(xtb_tile_ptr(tb, off + 2));
+            if (h & (XTB_F_DRIFT << 8)) {           // the Drift element in front
+#pragma unroll
+                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(T[k], L);
+                end_thick();
+            }
+            if ((a.flag_monitor == 2) && (h & (XTB_F_START << 8))) {
+                for (int k = 0; k < NPT; ++k)
+                    if (live[k]) {
+                        T[k].at_element = ae_base[k] + (int32_t) eidx;
+                        monitor_record(a.mon, T[k], G[k]);
+                    }
+            }
+            if (op == XTB_OP_MAGNET_BODY) {
+                magnet_body_n<NPT, SYNRAD, FRZ>(T, live, G, a, q, aux);
+            } else {
+                const double len = q[0];
+#pragma unroll
+                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(T[k], len);
+            }
+            if (h & (XTB_F_END << 8)) {
+#pragma unroll
+                for (int k = 0; k < NPT; ++k) {
+                    if (!live[k]) { pstate_benign(T[k]);  continue; }
+                    if ((h & (XTB_F_GLOBAL << 8)) && !a.ignore_global) global_aperture_check(T[k], lim);
+                    if (T[k].state <= 0) retire(k);
+                }
+                eidx += 1;
+            } else if ((h & (XTB_F_GLOBAL << 8)) && !a.ignore_global) {
+#pragma unroll
+                for (int k = 0; k < NPT; ++k)
+                    if (live[k]) global_aperture_check(T[k], lim);
+            }
+        } else if (op == XTB_OP_FDRIFT || op == (XTB_OP_FDRIFT | XTB_OPBIT_DRIFT)) {
+            if (op & XTB_OPBIT_DRIFT) {
+#pragma unroll
+                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(T[k], L);
+                end_thick();
+            }
+            const double len = __longlong_as_double((long long) xtb_ld_w(tb, off + 2).x);
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(T[k], len);
+            end_thick();
         } else {
-            lanes.P[k] = T[k];
+            break;
         }
+        off += h >> 16;
     }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) lanes.P[k] = T[k];
+    lanes.off = off;
+    lanes.eidx = eidx;
 }
 #endif
 
@@ -716,6 +789,14 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
             break;
         }
         default: {      // XTB_STOP_SLOW: generic / heavy op, flags honoured
+#ifdef XTB_WITH_HEAVY
+            if constexpr (HEAVY && (NPT > 1) && std::is_same<S, PState>::value) {
+                if (op == XTB_OP_MAGNET_BODY || op == XTB_OP_DRIFT) {
+                    xtb_run_heavy<NPT, SYNRAD, FRZ>(tb, lanes, ps, a);     // a whole run of them
+                    break;
+                }
+            }
+#endif
             if (h & (XTB_F_DRIFT << 8)) {
                 for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(lanes.P[k], L);
                 global_check();
@@ -724,16 +805,7 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
         slow_main:
             const int32_t aux = (int32_t) (hw.x >> 32);
             const double* __restrict__ q = reinterpret_cast<const double*>(xtb_tile_ptr(tb, cur + 2));
-            bool done = false;
-#ifdef XTB_WITH_HEAVY
-            if constexpr (HEAVY && (NPT > 1) && std::is_same<S, PState>::value) {
-                if (op == XTB_OP_MAGNET_BODY) {
-                    xtb_slow_body<NPT, SYNRAD, FRZ>(lanes, ps, h, aux, q, a);
-                    done = true;
-                }
-            }
-#endif
-            for (int k = 0; k < NPT && !done; ++k) {
+            for (int k = 0; k < NPT; ++k) {
                 if (!lanes.live[k]) continue;      // these bodies touch the caller's SoA
                 const PSlot Gk{&a.part, lanes.slot[k], &lanes.C[k]};
                 lanes.live[k] = xtb_slow_op<HEAVY, SYNRAD, FRZ>(lanes.P[k], Gk, ps, lanes.eidx, h, aux, q, a);
