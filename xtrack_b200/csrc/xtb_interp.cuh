@@ -613,16 +613,15 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
         live[k] = lanes.live[k];
         T[k] = lanes.P[k];
         ae_base[k] = 0;
-        if (live[k]) {
-            T[k].at_turn = G[k].ldi(F_AT_TURN) + ps.turn_inc;
+        if (live[k])
             ae_base[k] = (ps.el_reset ? 0 : (int32_t) G[k].ldi(F_AT_ELEMENT)) + (int32_t) ps.el_off;
-        }
     }
     uint32_t off = lanes.off, eidx = lanes.eidx;
     const double lim = a.global_xy_limit;
 
     // lane k is lost in the current element (index eidx): write it back, go on benign
     auto retire = [&](const int k) {
+        T[k].at_turn = G[k].ldi(F_AT_TURN) + ps.turn_inc;
         T[k].at_element = ae_base[k] + (int32_t) eidx;
         pstate_store(T[k], G[k]);
         live[k] = false;
@@ -656,6 +655,7 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
             if ((a.flag_monitor == 2) && (h & (XTB_F_START << 8))) {
                 for (int k = 0; k < NPT; ++k)
                     if (live[k]) {
+                        T[k].at_turn = G[k].ldi(F_AT_TURN) + ps.turn_inc;
                         T[k].at_element = ae_base[k] + (int32_t) eidx;
                         monitor_record(a.mon, T[k], G[k]);
                     }
@@ -696,7 +696,12 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
         off += h >> 16;
     }
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) lanes.P[k] = T[k];
+    for (int k = 0; k < NPT; ++k) {      // (at_turn / at_element of lanes.P are never read)
+        PState& Q = lanes.P[k];
+        Q.x = T[k].x;  Q.px = T[k].px;  Q.y = T[k].y;  Q.py = T[k].py;  Q.zeta = T[k].zeta;
+        Q.delta = T[k].delta;  Q.rpp = T[k].rpp;  Q.rvv = T[k].rvv;  Q.rv0v = T[k].rv0v;
+        Q.chi = T[k].chi;  Q.s = T[k].s;  Q.state = T[k].state;
+    }
     lanes.off = off;
     lanes.eidx = eidx;
 }

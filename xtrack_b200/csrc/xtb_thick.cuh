@@ -56,10 +56,20 @@ __device__ __forceinline__ double div_by(const double a, const double b, const d
 // the values are evaluated here.
 #define XTB_TRIG_STRIDE 6   // [length, cos(h*s), sin(h*s), sin(h*s/2), RN(1/cos(h*s)), 0]
 struct TrigTab {
-    const double* t;
-    int n;               // entries
-    int n_inner;         // inner classes per outer class (1: models 2, 4; 2: model 7; 4: model 8)
-    double rho;          // 1 / h (valid iff n > 0)
+    // block in the op's parameters: [(int) n | n_inner << 32, 1/h, n entries]; read on demand
+    // (shared-memory broadcast loads) instead of being carried in registers through the body
+    const double* base;
+    __device__ __forceinline__ int n() const {
+        return (int) ((unsigned long long) __double_as_longlong(base[0]) & 0xffffffffu);
+    }
+    // inner classes per outer class (1: models 2, 4; 2: model 7; 4: model 8)
+    __device__ __forceinline__ int n_inner() const {
+        return (int) ((unsigned long long) __double_as_longlong(base[0]) >> 32);
+    }
+    __device__ __forceinline__ double rho() const { return base[1]; }      // 1 / h (iff n > 0)
+    __device__ __forceinline__ const double* entry(const int idx) const {
+        return base + 2 + XTB_TRIG_STRIDE * idx;
+    }
 };
 #ifdef XTB_COUNT_TRIG_MISS
 static long long xtb_trig_lookups = 0, xtb_trig_misses = 0;
@@ -70,8 +80,8 @@ __device__ __forceinline__ void trig_of(const TrigTab& tt, const int idx, const 
 #ifdef XTB_COUNT_TRIG_MISS
     xtb_trig_lookups++;
 #endif
-    if (idx < tt.n) {
-        const double* e = tt.t + XTB_TRIG_STRIDE * idx;
+    if (idx < tt.n()) {
+        const double* e = tt.entry(idx);
         if (__double_as_longlong(e[0]) == __double_as_longlong(s)) {
             ca = e[1];  sa = e[2];  sa2 = e[3];  rca = e[4];
             return;
@@ -114,7 +124,7 @@ template <int N, bool FRZ>
 __device__ __forceinline__ void polar_drift_n(PState (&P)[N], const double length, const double h,
                                               const TrigTab& tt, const int idx) {
     const double s = length;
-    const double rho = (tt.n > 0) ? tt.rho : 1 / h;
+    const double rho = (tt.n() > 0) ? tt.rho() : 1 / h;
     double ca, sa, sa2, rca;
     trig_of(tt, idx, h, s, ca, sa, sa2, rca);
     // (each statement of the reference's map, for all N particles in turn: see XTB_LANES)
@@ -157,44 +167,45 @@ __device__ __noinline__ void polar_drift(PState& P, const double length, const d
     polar_drift_n<1, FRZ>(reinterpret_cast<PState(&)[1]>(P), length, h, tt, idx);
 }
 
-// track_expanded_combined_dipole_quad_single_particle, track_magnet_drift.h:91-213
+// S = sin(sqrt(K) L) / sqrt(K), C = cos(sqrt(K) L) for K > 0, the hyperbolic pair for K < 0,
+// (L, 1) for K == 0: track_magnet_drift.h:121-147, once per plane.  Out of line, one copy: the
+// four libm bodies inlined twice made the quadrupole map miss the instruction cache (ncu:
+// 31 % of its samples were no_instruction).
+static __device__ __noinline__ void focusing_terms(const double K, const double length, double& S,
+                                                   double& C) {
+    if (K > 0.0) {
+        const double sqrt_K = sqrt(K);
+        S = sin(sqrt_K * length) / sqrt_K;
+        C = cos(sqrt_K * length);
+    } else if (K < 0.0) {
+        const double sqrt_K = sqrt(-K);
+        S = sinh(sqrt_K * length) / sqrt_K;
+        C = cosh(sqrt_K * length);
+    } else {
+        S = length;
+        C = 1.0;
+    }
+}
+
+// track_expanded_combined_dipole_quad_single_particle, track_magnet_drift.h:91-213.
+// Its 13 divisions by 1 + delta, Kx and Ky share three reciprocals (div_by: same correctly
+// rounded quotients; `t / (2 K)` is `(t / K) / 2` exactly).
 template <bool FRZ>
 __device__ __noinline__ void combined_dipole_quad(PState& P, const double length, const double k0_,
                                                   const double k1_, const double h) {
     const double x = P.x, y = P.y, px = P.px, py = P.py, rvv = P.rvv;
     const double delta_plus_1 = P.delta + 1;
+    const double r_dp1 = xtb_rcp(delta_plus_1);
     const double chi = P.chi;
-    const double k0 = chi * k0_ / delta_plus_1;
-    const double k1 = chi * k1_ / delta_plus_1;
+    const double k0 = div_by(chi * k0_, delta_plus_1, r_dp1);
+    const double k1 = div_by(chi * k1_, delta_plus_1, r_dp1);
     const double Kx = k0 * h + k1;
     const double Ky = -k1;
     double Sx, Sy, Cx, Cy;
-    if (Kx > 0.0) {
-        const double sqrt_Kx = sqrt(Kx);
-        Sx = sin(sqrt_Kx * length) / sqrt_Kx;
-        Cx = cos(sqrt_Kx * length);
-    } else if (Kx < 0.0) {
-        const double sqrt_Kx = sqrt(-Kx);
-        Sx = sinh(sqrt_Kx * length) / sqrt_Kx;
-        Cx = cosh(sqrt_Kx * length);
-    } else {
-        Sx = length;
-        Cx = 1.0;
-    }
-    if (Ky > 0.0) {
-        const double sqrt_Ky = sqrt(Ky);
-        Sy = sin(sqrt_Ky * length) / sqrt_Ky;
-        Cy = cos(sqrt_Ky * length);
-    } else if (Ky < 0.0) {
-        const double sqrt_Ky = sqrt(-Ky);
-        Sy = sinh(sqrt_Ky * length) / sqrt_Ky;
-        Cy = cosh(sqrt_Ky * length);
-    } else {
-        Sy = length;
-        Cy = 1.0;
-    }
-    const double xp = px / delta_plus_1;
-    const double yp = py / delta_plus_1;
+    focusing_terms(Kx, length, Sx, Cx);
+    focusing_terms(Ky, length, Sy, Cy);
+    const double xp = div_by(px, delta_plus_1, r_dp1);
+    const double yp = div_by(py, delta_plus_1, r_dp1);
     const double A = -Kx * x - k0 + h;
     const double B = xp;
     const double C = -Ky * y;
@@ -203,28 +214,28 @@ __device__ __noinline__ void combined_dipole_quad(PState& P, const double length
     const double y_ = y * Cy + yp * Sy;
     const double px_ = (A * Sx + B * Cx) * delta_plus_1;
     const double py_ = (C * Sy + D * Cy) * delta_plus_1;
-    if (Kx != 0.0)
-        x_ = x_ + (k0 - h) * (Cx - 1.0) / Kx;
-    else
-        x_ = x_ - (k0 - h) * 0.5 * XTB_POW2(length);
     double length_ = length;
     if (Kx != 0.0) {
-        length_ -= (h * ((Cx - 1.0) * xp + Sx * A + length * (k0 - h))) / Kx;
-        length_ += 0.5 * (-(XTB_POW2(A) * Cx * Sx) / (2.0 * Kx) + (XTB_POW2(B) * Cx * Sx) / 2.0
-                          + (XTB_POW2(A) * length) / (2.0 * Kx) + (XTB_POW2(B) * length) / 2.0
-                          - (A * B * XTB_POW2(Cx)) / Kx + (A * B) / Kx);
+        const double r_Kx = xtb_rcp(Kx);
+        x_ = x_ + div_by((k0 - h) * (Cx - 1.0), Kx, r_Kx);
+        length_ -= div_by(h * ((Cx - 1.0) * xp + Sx * A + length * (k0 - h)), Kx, r_Kx);
+        length_ += 0.5 * (div_by(-(XTB_POW2(A) * Cx * Sx), Kx, r_Kx) * 0.5 + (XTB_POW2(B) * Cx * Sx) / 2.0
+                          + div_by(XTB_POW2(A) * length, Kx, r_Kx) * 0.5 + (XTB_POW2(B) * length) / 2.0
+                          - div_by(A * B * XTB_POW2(Cx), Kx, r_Kx) + div_by(A * B, Kx, r_Kx));
     } else {
+        x_ = x_ - (k0 - h) * 0.5 * XTB_POW2(length);
         length_ += h * length * (3.0 * length * xp + 6.0 * x - (k0 - h) * XTB_POW2(length)) / 6.0;
         length_ += 0.5 * (XTB_POW2(B)) * length;
     }
     if (Ky != 0.0) {
-        length_ += 0.5 * (-(XTB_POW2(C) * Cy * Sy) / (2.0 * Ky) + (XTB_POW2(D) * Cy * Sy) / 2.0
-                          + (XTB_POW2(C) * length) / (2.0 * Ky) + (XTB_POW2(D) * length) / 2.0
-                          - (C * D * XTB_POW2(Cy)) / Ky + (C * D) / Ky);
+        const double r_Ky = xtb_rcp(Ky);
+        length_ += 0.5 * (div_by(-(XTB_POW2(C) * Cy * Sy), Ky, r_Ky) * 0.5 + (XTB_POW2(D) * Cy * Sy) / 2.0
+                          + div_by(XTB_POW2(C) * length, Ky, r_Ky) * 0.5 + (XTB_POW2(D) * length) / 2.0
+                          - div_by(C * D * XTB_POW2(Cy), Ky, r_Ky) + div_by(C * D, Ky, r_Ky));
     } else {
         length_ += 0.5 * XTB_POW2(D) * length;
     }
-    const double dzeta = length - length_ / rvv;
+    const double dzeta = length - div_by(length_, rvv, P.rv0v);
     P.x = x_;
     P.px = px_;
     P.y = y_;
@@ -342,7 +353,7 @@ __device__ __forceinline__ void magnet_drift_n(PState (&P)[N], const double leng
         for (int j = 0; j < n_in; ++j) {
             const double lj = (n_in == 1) ? length : tab[j] * length;
             const int ic = (j < n_in - 1 - j) ? j : n_in - 1 - j;
-            polar_drift_n<N, FRZ>(P, lj, h, tt, oc * tt.n_inner + ic);
+            polar_drift_n<N, FRZ>(P, lj, h, tt, oc * tt.n_inner() + ic);
             if (j < n_in - 1) {
                 const double kj = tab[n_in + j];
 #pragma unroll
@@ -370,46 +381,46 @@ __device__ __forceinline__ void magnet_drift_n(PState (&P)[N], const double leng
 //       has_main[9] radiation_flag[10:12] drift_only[12] edge_in[13] edge_out[14]
 //       num_kicks[15:32]
 struct BodyPar {
+    // only the parameter pointer and the flag word are carried; everything else is decoded
+    // where it is used (a few integer instructions against ~30 registers held through the
+    // whole body, which kept ptxas from interleaving the lanes)
     const double* q;
-    const double* cm;    // main
-    const double* cu;    // user
-    const double* cr;    // rel
-    int order_user, order_rel;
-    int integrator, drift_model, rot_frame, has_user, has_rel, has_main, radiation_flag, drift_only;
-    int num_kicks;
-    int edge_in, edge_out;
-    const double* edges;   // [r21_in, r43_in, r21_out, r43_out]
-    TrigTab trig;
+    uint32_t a;
+    __device__ __forceinline__ int order_user() const {
+        return (int) ((unsigned long long) __double_as_longlong(q[9]) & 0xffffffffu);
+    }
+    __device__ __forceinline__ int order_rel() const {
+        return (int) ((unsigned long long) __double_as_longlong(q[9]) >> 32);
+    }
+    __device__ __forceinline__ const double* cm() const { return q + 18; }
+    __device__ __forceinline__ const double* cu() const { return q + 26; }
+    __device__ __forceinline__ const double* cr() const { return q + 26 + 2 * (order_user() + 1); }
+    __device__ __forceinline__ TrigTab trig() const {
+        TrigTab tt;
+        tt.base = cr() + 2 * (order_rel() + 1);
+        return tt;
+    }
+    __device__ __forceinline__ const double* edges() const {     // [r21_in, r43_in, r21_out, r43_out]
+        const TrigTab tt = trig();
+        return tt.entry(tt.n());
+    }
+    __device__ __forceinline__ int integrator() const { return a & 3; }
+    __device__ __forceinline__ int drift_model() const { return (int) ((a >> 2) & 15) - 1; }
+    __device__ __forceinline__ int rot_frame() const { return (a >> 6) & 1; }
+    __device__ __forceinline__ int has_user() const { return (a >> 7) & 1; }
+    __device__ __forceinline__ int has_rel() const { return (a >> 8) & 1; }
+    __device__ __forceinline__ int has_main() const { return (a >> 9) & 1; }
+    __device__ __forceinline__ int radiation_flag() const { return (a >> 10) & 3; }
+    __device__ __forceinline__ int drift_only() const { return (a >> 12) & 1; }
+    __device__ __forceinline__ int edge_in() const { return (a >> 13) & 1; }
+    __device__ __forceinline__ int edge_out() const { return (a >> 14) & 1; }
+    __device__ __forceinline__ int num_kicks() const { return (int) (a >> 15); }
 };
 
 __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) {
     BodyPar b;
     b.q = q;
-    const unsigned long long w = (unsigned long long) __double_as_longlong(q[9]);
-    b.order_user = (int) (w & 0xffffffffu);
-    b.order_rel = (int) (w >> 32);
-    b.cm = q + 18;
-    b.cu = b.cm + 8;
-    b.cr = b.cu + 2 * (b.order_user + 1);
-    const double* tq = b.cr + 2 * (b.order_rel + 1);
-    const unsigned long long tw = (unsigned long long) __double_as_longlong(tq[0]);
-    b.trig.n = (int) (tw & 0xffffffffu);
-    b.trig.n_inner = (int) (tw >> 32);
-    b.trig.rho = tq[1];
-    b.trig.t = tq + 2;
-    b.edges = b.trig.t + XTB_TRIG_STRIDE * b.trig.n;
-    const uint32_t a = (uint32_t) aux;
-    b.integrator = a & 3;
-    b.drift_model = (int) ((a >> 2) & 15) - 1;
-    b.rot_frame = (a >> 6) & 1;
-    b.has_user = (a >> 7) & 1;
-    b.has_rel = (a >> 8) & 1;
-    b.has_main = (a >> 9) & 1;
-    b.radiation_flag = (a >> 10) & 3;
-    b.drift_only = (a >> 12) & 1;
-    b.edge_in = (a >> 13) & 1;
-    b.edge_out = (a >> 14) & 1;
-    b.num_kicks = (int) (a >> 15);
+    b.a = (uint32_t) aux;
     return b;
 }
 
@@ -417,29 +428,29 @@ __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) 
 template <int N, bool FRZ>
 __device__ __forceinline__ void magnet_kick_n(PState (&P)[N], const BodyPar& b, const double kick_weight) {
     const double length = b.q[0];
-    if (b.has_user) {
+    if (b.has_user()) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             double m, n;
-            horner_kick(P[k].x, P[k].y, P[k].chi, b.cu, b.order_user, m, n);
+            horner_kick(P[k].x, P[k].y, P[k].chi, b.cu(), b.order_user(), m, n);
             P[k].px += kick_weight * (-m);
             P[k].py += kick_weight * n;
         }
     }
-    if (b.has_rel) {
+    if (b.has_rel()) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             double m, n;
-            horner_kick(P[k].x, P[k].y, P[k].chi, b.cr, b.order_rel, m, n);
+            horner_kick(P[k].x, P[k].y, P[k].chi, b.cr(), b.order_rel(), m, n);
             P[k].px += kick_weight * (-m);
             P[k].py += kick_weight * n;
         }
     }
-    if (b.has_main) {
+    if (b.has_main()) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             double m, n;
-            horner_kick(P[k].x, P[k].y, P[k].chi, b.cm, 3, m, n);
+            horner_kick(P[k].x, P[k].y, P[k].chi, b.cm(), 3, m, n);
             P[k].px += kick_weight * (-m);
             P[k].py += kick_weight * n;
         }
@@ -450,7 +461,7 @@ __device__ __forceinline__ void magnet_kick_n(PState (&P)[N], const BodyPar& b, 
     for (int k = 0; k < N; ++k) {
         const double chi = P[k].chi, x = P[k].x, y = P[k].y;
         double dpx = 0, dpy = 0, dzeta = 0;
-        if (b.rot_frame) {
+        if (b.rot_frame()) {
             const double hl = h * length * kick_weight + hxl * kick_weight;
             dpx += hl * (1. + P[k].delta);
             dzeta += -P[k].rv0v * hl * x;
@@ -724,8 +735,8 @@ __device__ __forceinline__ void field_from_strengths(const BodyPar& b, const dou
     if (length == 0.0) { Bx_T = 0.0;  By_T = 0.0;  return; }
     double dpx_mul = 0., dpy_mul = 0., dpx_rel = 0., dpy_rel = 0., dpx_main = 0., dpy_main = 0.;
     double m, n;
-    if (b.has_user) { horner_kick(x, y, 1., b.cu, b.order_user, m, n);  dpx_mul = -m;  dpy_mul = n; }
-    if (b.has_rel) { horner_kick(x, y, 1., b.cr, b.order_rel, m, n);  dpx_rel = -m;  dpy_rel = n; }
+    if (b.has_user()) { horner_kick(x, y, 1., b.cu(), b.order_user(), m, n);  dpx_mul = -m;  dpy_mul = n; }
+    if (b.has_rel()) { horner_kick(x, y, 1., b.cr(), b.order_rel(), m, n);  dpx_rel = -m;  dpy_rel = n; }
     {   // main strengths include the part integrated by the drift map (k0_drift + k0_kick, ...)
         double knl_main[4], ksl_main[4];
         for (int i = 0; i < 4; ++i) { knl_main[i] = b.q[10 + i] * length;  ksl_main[i] = b.q[14 + i] * length; }
@@ -781,7 +792,7 @@ __device__ __forceinline__ void rad_end(const RadSnapshot& s, PState& P, const P
                                         const XtbTrackArgs& a, const BodyPar& b, const double ll) {
     if (!SYNRAD) return;
     const double length = b.q[0];
-    if (!(b.radiation_flag && length > 0)) return;   // spin is (0,0,0): magnet_spin is a no-op
+    if (!(b.radiation_flag() && length > 0)) return;   // spin is (0,0,0): magnet_spin is a no-op
     const double p0c = G.ld(F_P0C);
     const double q0 = a.part.q0;
     const double mean_x = 0.5 * (s.old_x + P.x);
@@ -793,9 +804,9 @@ __device__ __forceinline__ void rad_end(const RadSnapshot& s, PState& P, const P
     const double dzeta = P.zeta - s.old_zeta;
     const double l_path = P.rvv * (ll - dzeta);
     const double B_perp_T = b_perp_mod(mean_kin_px, mean_kin_py, P.delta, Bx_T, By_T, 0. * (p0c / XTB_C_LIGHT / q0));
-    if (b.radiation_flag == 1) {
+    if (b.radiation_flag() == 1) {
         synrad_average_kick<FRZ>(P, G, a, B_perp_T, l_path);
-    } else if (b.radiation_flag == 2) {
+    } else if (b.radiation_flag() == 2) {
         synrad_emit_photons<FRZ>(P, G, a, B_perp_T, l_path);
     }
 }
@@ -816,9 +827,9 @@ __device__ __forceinline__ void magnet_body_n(PState (&P)[N], const bool (&live)
                                               const int32_t aux) {
     const BodyPar b = body_par(q, aux);
     const double length = q[0], k0d = q[1], k1d = q[2], hd = q[3];
-    const int dm = b.drift_model;
-    const int nk = b.num_kicks;
-    const int integ = b.drift_only ? 0 : b.integrator;
+    const int dm = b.drift_model();
+    const int nk = b.num_kicks();
+    const int integ = b.drift_only() ? 0 : b.integrator();
 
     int n_seg = 1, n_sub = 1;
     double seg_length = length;
@@ -844,9 +855,9 @@ __device__ __forceinline__ void magnet_body_n(PState (&P)[N], const bool (&live)
         n_sub = 8;
         seg_length = slice_length;
     }
-    if (b.edge_in) {
+    if (b.edge_in()) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) edge_linear(P[k], b.edges[0], b.edges[1]);
+        for (int k = 0; k < N; ++k) edge_linear(P[k], b.edges()[0], b.edges()[1]);
     }
     RadSnapshot snap[N];
     for (int seg = 0; seg < n_seg; ++seg) {
@@ -869,7 +880,7 @@ __device__ __forceinline__ void magnet_body_n(PState (&P)[N], const bool (&live)
             } else {
                 dl = length;
             }
-            magnet_drift_n<N, FRZ>(P, dl, k0d, k1d, hd, dm, b.trig, oc);
+            magnet_drift_n<N, FRZ>(P, dl, k0d, k1d, hd, dm, b.trig(), oc);
             const bool has_kick = (integ == 3) ? (j == 0) : (j < n_sub - 1);
             if (has_kick) magnet_kick_n<N, FRZ>(P, b, kw);
         }
@@ -878,9 +889,9 @@ __device__ __forceinline__ void magnet_body_n(PState (&P)[N], const bool (&live)
                 if (live[k]) rad_end<SYNRAD, FRZ>(snap[k], P[k], G[k], a, b, seg_length);
         }
     }
-    if (b.edge_out) {
+    if (b.edge_out()) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) edge_linear(P[k], b.edges[2], b.edges[3]);
+        for (int k = 0; k < N; ++k) edge_linear(P[k], b.edges()[2], b.edges()[3]);
     }
 }
 
