@@ -59,7 +59,7 @@ static void run(const XtbTrackArgs& a) {
             lanes.slot[k] = (uint32_t) (base + k);
             live[k] = (base + k < a.part.capacity) && G[k].ldi(F_STATE) > 0;
             if (live[k]) {
-                G[k].load_cold();
+                G[k].load_cold(SYNRAD);
                 pstate_load(P[k], G[k]);
                 P[k].state = 1;
                 chi_one = chi_one && (P[k].chi == 1.0);
@@ -119,7 +119,8 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
                                   uint64_t track_flags, double global_xy_limit, uint32_t variant,
                                   double line_length, const xtb_monitor_t* inline_mon,
                                   const xtb_last_turns_monitor_t* inline_ltm, int32_t npt, int32_t force_full) {
-    const int npt_heavy = (npt >> 8) ? (npt >> 8) : 2;
+    int npt_heavy = (npt >> 8) ? (npt >> 8) : 2;
+    if (variant & XTB_VARIANT_SYNRAD) npt_heavy = 1;      // XTB_NPT_SYNRAD of xtb_kernel_inst.cu
     npt &= 0xff;
     XtbTrackArgs a;
     std::memset(&a, 0, sizeof(a));

@@ -36,6 +36,9 @@
 #ifndef XTB_HEAVY_BLOCKS_PER_SM
 #define XTB_HEAVY_BLOCKS_PER_SM 4
 #endif
+#ifndef XTB_SYNRAD_BLOCKS_PER_SM
+#define XTB_SYNRAD_BLOCKS_PER_SM 6
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t) __cvta_generic_to_shared(p);
@@ -73,7 +76,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // EXACT only distinguishes the symbols of the two builds of this translation unit
 // (template instantiations are COMDAT: identical names would be merged at link time).
 template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT>
-__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? XTB_HEAVY_BLOCKS_PER_SM : XTB_THIN_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? (SYNRAD ? XTB_SYNRAD_BLOCKS_PER_SM : XTB_HEAVY_BLOCKS_PER_SM)
+                                                      : XTB_THIN_BLOCKS_PER_SM)
 xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     using S = typename std::conditional<HEAVY, PState, PHot>::type;
     __shared__ __align__(128) uint64_t tile[XTB_NUM_BUF][XTB_TILE_BUF_WORDS];
@@ -98,7 +102,7 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
             live[k] = G[k].ldi(F_STATE) > 0;
         }
         if (live[k]) {
-            G[k].load_cold();
+            G[k].load_cold(SYNRAD);
             pstate_load(P[k], G[k]);
             P[k].state = 1;
             chi_one = chi_one && (P[k].chi == 1.0);

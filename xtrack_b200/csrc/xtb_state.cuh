@@ -71,6 +71,11 @@ struct PCold {
     double beta0, gamma0, p0c, charge_ratio, ptau, rvv;
     int64_t at_turn0;        // at_turn / at_element at kernel entry
     int32_t at_element0;
+    // radiation kernels: the particle's generator state (4 x u32 of the SoA), so that the
+    // thousands of photon-emission calls per turn do not each wait for an HBM round trip;
+    // written back by pstate_store (exit, loss)
+    int32_t rng_cached;
+    uint32_t rng[4];
 };
 
 // Access to one particle slot: the cached cold fields through `c`, everything else in
@@ -115,19 +120,35 @@ struct PSlot {
         }
     }
     // fill the cache from the SoA (kernel entry)
-    __device__ __forceinline__ void load_cold() const {
+    __device__ __forceinline__ void load_cold(const bool with_rng) const {
         c->beta0 = ldg(F_BETA0);  c->gamma0 = ldg(F_GAMMA0);  c->p0c = ldg(F_P0C);
         c->charge_ratio = ldg(F_CHARGE_RATIO);  c->ptau = ldg(F_PTAU);  c->rvv = ldg(F_RVV);
         c->at_turn0 = ldgi(F_AT_TURN);  c->at_element0 = (int32_t) ldgi(F_AT_ELEMENT);
+        c->rng_cached = with_rng ? 1 : 0;
+        if (with_rng) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                c->rng[j] = reinterpret_cast<const uint32_t*>(p->field[F_RNG_S1 + j])[i];
+        }
     }
     __device__ __forceinline__ void sti(int f, int64_t v) const {
         reinterpret_cast<int64_t*>(p->field[f])[i] = v;
     }
     __device__ __forceinline__ uint32_t ldu(int f) const {
+        if (f >= F_RNG_S1 && f <= F_RNG_S4 && c->rng_cached) return c->rng[f - F_RNG_S1];
         return reinterpret_cast<const uint32_t*>(p->field[f])[i];
     }
     __device__ __forceinline__ void stu(int f, uint32_t v) const {
+        if (f >= F_RNG_S1 && f <= F_RNG_S4 && c->rng_cached) { c->rng[f - F_RNG_S1] = v;  return; }
         reinterpret_cast<uint32_t*>(p->field[f])[i] = v;
+    }
+    // cached generator state -> SoA
+    __device__ __forceinline__ void flush_rng() const {
+        if (c->rng_cached) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                reinterpret_cast<uint32_t*>(p->field[F_RNG_S1 + j])[i] = c->rng[j];
+        }
     }
 };
 
@@ -183,4 +204,5 @@ __device__ __forceinline__ void pstate_store(const PState& P, const PSlot& G) {
     G.sti(F_AT_TURN, P.at_turn);
     G.sti(F_AT_ELEMENT, (int64_t) P.at_element);
     G.sti(F_STATE, (int64_t) P.state);
+    G.flush_rng();
 }
