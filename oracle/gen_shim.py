@@ -197,7 +197,27 @@ GPUFUN double* CLS##Record_getp1_x2_sum(CLS##Record r, int64_t i){ return r->x2_
 GPUFUN double* CLS##Record_getp1_y2_sum(CLS##Record r, int64_t i){ return r->y2_sum + i; }
 XTB_BEAMMON_API(BeamPositionMonitor)
 XTB_BEAMMON_API(BeamSizeMonitor)
+
+/* ---- BeamProfileMonitorData (monitors/beam_profile_monitor.py:20-37) ---- */
+typedef struct BeamProfileMonitorRecord_s { int64_t n_x, n_y; double *counts_x, *counts_y; } *BeamProfileMonitorRecord;
+typedef struct BeamProfileMonitorData_s {
+    int64_t particle_id_start, num_particles, start_at_turn, stop_at_turn, nx, ny, sample_size;
+    double frev, sampling_frequency, x_min, dx, y_min, dy;
+    BeamProfileMonitorRecord data;
+} *BeamProfileMonitorData;
+#define XTB_BPROF_I(f) GPUFUN int64_t BeamProfileMonitorData_get_##f(BeamProfileMonitorData el){ return el->f; }
+#define XTB_BPROF_D(f) GPUFUN double BeamProfileMonitorData_get_##f(BeamProfileMonitorData el){ return el->f; }
+XTB_BPROF_I(particle_id_start) XTB_BPROF_I(num_particles) XTB_BPROF_I(start_at_turn)
+XTB_BPROF_I(nx) XTB_BPROF_I(ny) XTB_BPROF_I(sample_size)
+XTB_BPROF_D(frev) XTB_BPROF_D(sampling_frequency) XTB_BPROF_D(x_min) XTB_BPROF_D(dx)
+XTB_BPROF_D(y_min) XTB_BPROF_D(dy)
+GPUFUN BeamProfileMonitorRecord BeamProfileMonitorData_getp_data(BeamProfileMonitorData el){ return el->data; }
+GPUFUN int64_t BeamProfileMonitorRecord_len_counts_x(BeamProfileMonitorRecord r){ return r->n_x; }
+GPUFUN int64_t BeamProfileMonitorRecord_len_counts_y(BeamProfileMonitorRecord r){ return r->n_y; }
+GPUFUN double* BeamProfileMonitorRecord_getp1_counts_x(BeamProfileMonitorRecord r, int64_t i){ return r->counts_x + i; }
+GPUFUN double* BeamProfileMonitorRecord_getp1_counts_y(BeamProfileMonitorRecord r, int64_t i){ return r->counts_y + i; }
 '''
+
 
 RECORD_STUBS = r'''
 /* In-kernel photon logging is outside the contract: the record handle is NULL
@@ -244,6 +264,7 @@ def generate():
     out.append(BEAM_MONITOR_API)
     out.append('#include "xtrack/monitors/beam_position_monitor.h"')
     out.append('#include "xtrack/monitors/beam_size_monitor.h"')
+    out.append('#include "xtrack/monitors/beam_profile_monitor.h"')
     for name in CLASS_ORDER:
         out.append(gen_element_struct(name))
         out.append(f'#include "xtrack/beam_elements/elements_src/{SPECS[name]["header"]}"')
@@ -264,6 +285,7 @@ def generate():
     out.append('        case 1001: LastTurnsMonitor_track_local_particle((LastTurnsMonitorData) el, lpart); break;')
     out.append('        case 1002: BeamPositionMonitor_track_local_particle((BeamPositionMonitorData) el, lpart); break;')
     out.append('        case 1003: BeamSizeMonitor_track_local_particle((BeamSizeMonitorData) el, lpart); break;')
+    out.append('        case 1004: BeamProfileMonitor_track_local_particle((BeamProfileMonitorData) el, lpart); break;')
     out.append('    }\n}')
     out.append('#endif')
     return '\n'.join(out) + '\n'

@@ -75,6 +75,18 @@ class BeamMonitorC(ct.Structure):
                    ('data', ct.POINTER(BeamRecordC))])
 
 
+class BeamProfileRecordC(ct.Structure):
+    _fields_ = [('n_x', ct.c_int64), ('n_y', ct.c_int64),
+                ('counts_x', ct.POINTER(ct.c_double)), ('counts_y', ct.POINTER(ct.c_double))]
+
+
+class BeamProfileMonitorC(ct.Structure):
+    _fields_ = ([(n, ct.c_int64) for n in ('particle_id_start', 'num_particles', 'start_at_turn',
+                                           'stop_at_turn', 'nx', 'ny', 'sample_size')]
+                + [(n, ct.c_double) for n in ('frev', 'sampling_frequency', 'x_min', 'dx', 'y_min', 'dy')]
+                + [('data', ct.POINTER(BeamProfileRecordC))])
+
+
 _STRUCTS = {}
 
 
@@ -203,6 +215,8 @@ class RefElements:
             return self._make_last_turns(el), 1001
         if name in ('BeamPositionMonitor', 'BeamSizeMonitor'):
             return self._make_beam_monitor(el), 1002 if name == 'BeamPositionMonitor' else 1003
+        if name == 'BeamProfileMonitor':
+            return self._make_beam_profile(el), 1004
         if name not in SPECS:
             raise NotImplementedError(f'oracle: element class {name} not supported')
         st = _struct_for(name)()
@@ -235,6 +249,19 @@ class RefElements:
         cm = BeamMonitorC()
         for nn in ('particle_id_start', 'num_particles', 'start_at_turn', 'stop_at_turn',
                    'frev', 'sampling_frequency'):
+            setattr(cm, nn, getattr(mon, nn))
+        cm.data = ct.pointer(rec)
+        self._keep += [rec, cm]
+        return ct.addressof(cm)
+
+    def _make_beam_profile(self, mon):
+        """The oracle counts into `mon._host = {'counts_x': ..., 'counts_y': ...}` (float64)."""
+        rec = BeamProfileRecordC()
+        rec.n_x, rec.n_y = len(mon._host['counts_x']), len(mon._host['counts_y'])
+        rec.counts_x = mon._host['counts_x'].ctypes.data_as(ct.POINTER(ct.c_double))
+        rec.counts_y = mon._host['counts_y'].ctypes.data_as(ct.POINTER(ct.c_double))
+        cm = BeamProfileMonitorC()
+        for nn, _ in BeamProfileMonitorC._fields_[:-1]:
             setattr(cm, nn, getattr(mon, nn))
         cm.data = ct.pointer(rec)
         self._keep += [rec, cm]

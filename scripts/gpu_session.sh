@@ -15,6 +15,9 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 for wl in sps_apertures lep_thick; do
   timeout 400 python bench.py --workload $wl --quick --steps 3 --warmup 1 --turns 5 --particles 500000 > $OUT/bench_$wl.json 2>> $OUT/bench.err
 done
+for wl in lep_quantum clic_dr_quantum; do
+  timeout 400 python bench.py --workload $wl --quick --steps 2 --warmup 1 --turns 2 --particles 300000 > $OUT/bench_$wl.json 2>> $OUT/bench.err
+done
 kill $SMI
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --turns 2 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
@@ -22,4 +25,6 @@ for mode in "" "--fma"; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xtb_track_kernel -s 2 -c 1 \
     -o $OUT/prof_track${mode} -f python bench.py --quick --steps 1 --warmup 1 --turns 3 --no-cpu-baseline $mode > $OUT/ncu_full${mode}.log 2>&1
 done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xtb_track_kernel -s 1 -c 1 \
+    -o $OUT/prof_lep -f python bench.py --workload lep_thick --particles 300000 --quick --steps 1 --warmup 1 --turns 1 --no-cpu-baseline > $OUT/ncu_lep.log 2>&1
 tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; cat $OUT/bench.json

@@ -202,13 +202,19 @@ def beam_monitor_ring(kind, n=400, turns=6):
     frev = 299792458.0 / line.get_length()
     kw = dict(particle_id_range=(15, n - 20), start_at_turn=1, stop_at_turn=turns - 1,
               frev=frev, sampling_frequency=4 * frev)
+    if kind == 'BeamProfileMonitor':
+        kw.update(nx=24, x_range=0.03, ny=16, y_range=(-0.008, 0.012))
     els = list(line.elements)
     mon = cls(**kw)
     els.insert(len(els) // 2, mon)
     line2 = xb.Line(elements=els)
     line2.particle_ref = line.particle_ref
     mon_ref = cls(**kw)
-    mon_ref._host = np.zeros((5, mon_ref.n_slots))
+    if kind == 'BeamProfileMonitor':
+        mon_ref._host = {'counts_x': np.zeros(mon_ref.sample_size * mon_ref.nx),
+                         'counts_y': np.zeros(mon_ref.sample_size * mon_ref.ny)}
+    else:
+        mon_ref._host = np.zeros((5, mon_ref.n_slots))
     els_ref = list(els)
     els_ref[len(line.elements) // 2] = mon_ref
     sig = dict(SIGMAS['sps'])

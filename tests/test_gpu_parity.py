@@ -329,3 +329,27 @@ def test_beam_monitors_vs_oracle_gpu(kind):
     for ii, nn in enumerate(mon.properties):
         np.testing.assert_allclose(getattr(mon, nn), mon_ref._host[ii], rtol=1e-11, atol=1e-13,
                                    err_msg=nn)
+
+
+def test_beam_profile_monitor_vs_oracle_gpu():
+    """monitors/beam_profile_monitor.h:15-80 against the reference's own code: the histograms
+    (integer counts) are identical on the GPU (atomic adds of 1.0)."""
+    import ref_oracle as ro
+    turns = 6
+    line2, els_ref, mon_ref, mon, p_host = common.beam_monitor_ring('BeamProfileMonitor', n=5000,
+                                                                    turns=turns)
+    hp = ro.HostParticles.from_particles(p_host)
+    ro.track_line(hp, ro.RefElements(els_ref), num_turns=turns, ele_start=0,
+                  num_ele_track=len(els_ref), flag_end_turn_actions=True,
+                  flag_reset_s_at_end_turn=True, line_length=line2.get_length(),
+                  global_xy_limit=1.0)
+    ref = hp.sorted_by_id()
+    got = common.by_id(_track_gpu(line2, p_host, turns, True))
+    assert np.array_equal(got['state'], ref['state'])
+    assert mon_ref._host['counts_x'].sum() > 1000 and (mon_ref._host['counts_x'] > 0).sum() > 20
+    assert np.array_equal(mon.counts_x, mon_ref._host['counts_x'])
+    assert np.array_equal(mon.counts_y, mon_ref._host['counts_y'])
+    assert mon.x_intensity.shape == (mon.sample_size, 24) and mon.y_intensity.shape[1] == 16
+    assert len(mon.x_edges) == 25 and abs(mon.x_grid[0] - (-0.015 + 0.03 / 48)) < 1e-15
+    mon2 = type(mon).from_dict(mon.to_dict())
+    assert np.array_equal(mon2.counts_x, mon.counts_x) and mon2.dy == mon.dy

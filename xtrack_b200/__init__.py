@@ -11,7 +11,7 @@ from .elements import (Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupo
                        Octupole, Bend, RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation,
                        LimitRect, LimitEllipse, LimitPolygon)
 from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
-                       BeamSizeMonitor)
+                       BeamSizeMonitor, BeamProfileMonitor)
 from .line import Line
 
 __version__ = '0.1.0'

@@ -139,6 +139,41 @@ static __device__ __noinline__ void beam_monitor_record(const double* __restrict
 #endif
 }
 
+// BeamProfileMonitor, monitors/beam_profile_monitor.h:15-80: per time sample a histogram of
+// x and one of y (particle counts per bin; the bins are spread over the beam, so the plain
+// per-particle atomic add of the reference is kept).
+//   q: (int) start_at_turn, (int) particle_id_start, (int) particle_id_stop, frev,
+//      sampling_frequency, (int) sample_size, (int) nx, x_min, dx, (int) ny, y_min, dy,
+//      (ptr) counts_x [sample_size * nx], (ptr) counts_y [sample_size * ny]
+static __device__ __noinline__ void beam_profile_record(const double* __restrict__ q, const PState& P,
+                                                        const PSlot& G) {
+    const int64_t start_at_turn = __double_as_longlong(q[0]);
+    const int64_t id_start = __double_as_longlong(q[1]), id_stop = __double_as_longlong(q[2]);
+    const double frev = q[3], sampling_frequency = q[4];
+    const int64_t max_sample = __double_as_longlong(q[5]);
+    const int64_t nx = __double_as_longlong(q[6]), ny = __double_as_longlong(q[9]);
+    const double x_min = q[7], dx = q[8], y_min = q[10], dy = q[11];
+    double* counts_x = reinterpret_cast<double*>(__double_as_longlong(q[12]));
+    double* counts_y = reinterpret_cast<double*>(__double_as_longlong(q[13]));
+    const int64_t particle_id = G.ldgi(F_PARTICLE_ID);
+    if (!(id_stop < 0 || (id_start <= particle_id && particle_id < id_stop))) return;
+    const double at_turn = (double) P.at_turn;
+    const double beta0 = G.ld(F_BETA0);
+    const int64_t sample = (int64_t) round(sampling_frequency
+                                           * ((at_turn - start_at_turn) / frev - P.zeta / beta0 / XTB_C_LIGHT));
+    if (!(sample >= 0 && sample < max_sample)) return;
+    const int64_t bin_x = (int64_t) floor((P.x - x_min) / dx);
+    const int64_t bin_y = (int64_t) floor((P.y - y_min) / dy);
+    // (slot < len(counts) of the reference holds by construction: len = sample_size * n)
+#ifdef __CUDA_ARCH__
+    if (bin_x >= 0 && bin_x < nx) atomicAdd(counts_x + sample * nx + bin_x, 1.0);
+    if (bin_y >= 0 && bin_y < ny) atomicAdd(counts_y + sample * ny + bin_y, 1.0);
+#else
+    if (bin_x >= 0 && bin_x < nx) counts_x[sample * nx + bin_x] += 1.0;
+    if (bin_y >= 0 && bin_y < ny) counts_y[sample * ny + bin_y] += 1.0;
+#endif
+}
+
 // Generic thin ops, kept out of line so that they do not weigh on the hot loop's
 // register allocation.  `P.at_element` holds the current element index here.
 template <bool FRZ>
@@ -208,6 +243,9 @@ static __device__ __noinline__ void generic_op(const uint32_t op, const int32_t 
         break;
     case XTB_OP_BEAM_MON:
         if (live) beam_monitor_record(q, aux, P, G);
+        break;
+    case XTB_OP_BEAM_PROFILE:
+        if (live) beam_profile_record(q, P, G);
         break;
     case XTB_OP_KILL:
         kill_particle<FRZ>(P, G, aux);

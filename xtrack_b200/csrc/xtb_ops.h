@@ -96,6 +96,7 @@
 #define XTB_OP_ADD_S_ZETA    52   /* [ds]  s += ds; zeta += ds  (track_magnet.h:598-605)    */
 #define XTB_OP_ADD_X         53   /* [dx]  x += dx              (rbend straight body)       */
 #define XTB_OP_BEAM_MON      54   /* aux=#sums (3 position, 5 size); see beam_monitor_record */
+#define XTB_OP_BEAM_PROFILE  55   /* BeamProfileMonitor; see beam_profile_record              */
 
 /* -- heavy set (thick magnets; compiled in the HEAVY kernel variants) ------ */
 #define XTB_HEAVY_FIRST      64

@@ -19,13 +19,14 @@ import numpy as np
 
 from . import elements as _el
 from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
-                       BeamSizeMonitor)
+                       BeamSizeMonitor, BeamProfileMonitor)
 from .particles import Particles
 
 _MONITOR_CLASSES = {'ParticlesMonitor': ParticlesMonitor,
                     'LastTurnsMonitor': LastTurnsMonitor,
                     'BeamPositionMonitor': BeamPositionMonitor,
-                    'BeamSizeMonitor': BeamSizeMonitor}
+                    'BeamSizeMonitor': BeamSizeMonitor,
+                    'BeamProfileMonitor': BeamProfileMonitor}
 
 
 class Line:

@@ -71,6 +71,7 @@ OP_SET_STATE = 51
 OP_ADD_S_ZETA = 52
 OP_ADD_X = 53
 OP_BEAM_MON = 54
+OP_BEAM_PROFILE = 55
 # heavy set
 OP_MAGNET_BODY = 64
 OP_MAGNET_EDGE = 65
@@ -1179,6 +1180,18 @@ def lower_element(prog, el, cfg):
                               el.frev, el.sampling_frequency, _RawWord(el.n_slots),
                               _RawWord(rec.data_ptr()), 0.0],
                 aux=len(el.properties), flops=10)
+        prog.beam_monitors.append(el)
+        return False
+
+    if name == 'BeamProfileMonitor':
+        dd = el.allocate(cfg.get('device'))
+        stop = el.particle_id_start + el.num_particles
+        prog.op(OP_BEAM_PROFILE,
+                [_RawWord(el.start_at_turn & MASK64), _RawWord(el.particle_id_start & MASK64),
+                 _RawWord(stop & MASK64), el.frev, el.sampling_frequency, _RawWord(el.sample_size),
+                 _RawWord(el.nx), el.x_min, el.dx, _RawWord(el.ny), el.y_min, el.dy,
+                 _RawWord(dd['counts_x'].data_ptr()), _RawWord(dd['counts_y'].data_ptr())],
+                flops=10)
         prog.beam_monitors.append(el)
         return False
 

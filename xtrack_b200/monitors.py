@@ -267,3 +267,129 @@ class BeamPositionMonitor(_BeamSlotMonitor):
 
 class BeamSizeMonitor(_BeamSlotMonitor):
     properties = ('count', 'x_sum', 'y_sum', 'x2_sum', 'y2_sum')
+
+
+class BeamProfileMonitor(BeamElement):
+    """Transverse profiles per time sample (xtrack/monitors/beam_profile_monitor.py:20-207,
+    beam_profile_monitor.h:15-80): `x_intensity` / `y_intensity` of shape (sample_size, n).
+    The counts live on the tracking device as two float64 tensors, like the reference's record."""
+    allow_rot_and_shift = False
+    behaves_like_drift = True
+    allow_loss_refinement = True
+    properties = ('counts_x', 'counts_y')
+
+    def __init__(self, *, particle_id_range=None, particle_id_start=None, num_particles=None,
+                 start_at_turn=None, stop_at_turn=None, frev=None, sampling_frequency=None,
+                 nx=None, x_range=None, ny=None, y_range=None, n=None, range=None,
+                 _device='cpu', **kwargs):
+        if particle_id_range is None:
+            if particle_id_start is None:
+                particle_id_start = 0
+            if num_particles is None:
+                num_particles = -1
+        elif particle_id_start is None and num_particles is None:
+            particle_id_start = particle_id_range[0]
+            num_particles = particle_id_range[1] - particle_id_range[0]
+        else:
+            raise ValueError('Parameter `particle_id_range` must not be used together with '
+                             '`num_particles` and/or `particle_id_start`')
+        self.particle_id_start = int(particle_id_start)
+        self.num_particles = int(num_particles)
+        self.start_at_turn = int(0 if start_at_turn is None else start_at_turn)
+        self.stop_at_turn = int(0 if stop_at_turn is None else stop_at_turn)
+        self.frev = float(1 if frev is None else frev)
+        self.sampling_frequency = float(1 if sampling_frequency is None else sampling_frequency)
+        if 'x_min' in kwargs:           # from_dict: the stored raster
+            self.nx, self.x_min, self.dx = int(nx), float(kwargs.pop('x_min')), float(kwargs.pop('dx'))
+            self.ny, self.y_min, self.dy = int(ny), float(kwargs.pop('y_min')), float(kwargs.pop('dy'))
+        else:
+            if nx is None:
+                nx = n or 128
+            if x_range is None:
+                if range is None:
+                    raise ValueError('Either `x_range` or `range` must be provided')
+                x_range = range
+            if np.isscalar(x_range):
+                x_range = (-x_range / 2, x_range / 2)
+            if ny is None:
+                ny = n or 128
+            if y_range is None:
+                if range is None:
+                    raise ValueError('Either `y_range` or `range` must be provided')
+                y_range = range
+            if np.isscalar(y_range):
+                y_range = (-y_range / 2, y_range / 2)
+            self.nx, self.x_min, self.dx = int(nx), float(x_range[0]), (x_range[1] - x_range[0]) / nx
+            self.ny, self.y_min, self.dy = int(ny), float(y_range[0]), (y_range[1] - y_range[0]) / ny
+        self.sample_size = int(round((self.stop_at_turn - self.start_at_turn)
+                                     * self.sampling_frequency / self.frev))
+        kwargs.pop('sample_size', None)
+        self._device = torch.device(_device)
+        self._data = None
+        data = kwargs.pop('data', None)
+        self._finish(kwargs)
+        if data is not None:
+            dd = self.allocate()
+            dd['counts_x'][:self.sample_size * self.nx] = torch.as_tensor(
+                np.asarray(data['counts_x'], dtype=np.float64))
+            dd['counts_y'][:self.sample_size * self.ny] = torch.as_tensor(
+                np.asarray(data['counts_y'], dtype=np.float64))
+
+    @classmethod
+    def from_dict(cls, dct):
+        dct = dict(dct)
+        for kk in ('__class__', '_index'):
+            dct.pop(kk, None)
+        return cls(**dct)
+
+    def to_dict(self):
+        return {'__class__': 'BeamProfileMonitor', 'particle_id_start': self.particle_id_start,
+                'num_particles': self.num_particles, 'start_at_turn': self.start_at_turn,
+                'stop_at_turn': self.stop_at_turn, 'frev': self.frev,
+                'sampling_frequency': self.sampling_frequency, 'nx': self.nx, 'x_min': self.x_min,
+                'dx': self.dx, 'ny': self.ny, 'y_min': self.y_min, 'dy': self.dy,
+                'sample_size': self.sample_size,
+                'data': {'counts_x': self.counts_x.tolist(), 'counts_y': self.counts_y.tolist()}}
+
+    def allocate(self, device=None):
+        if device is not None:
+            self._device = torch.device(device)
+        if self._data is None:
+            self._data = {nn: torch.zeros(max(self.sample_size * nb, 1), dtype=torch.float64,
+                                          device=self._device)
+                          for nn, nb in (('counts_x', self.nx), ('counts_y', self.ny))}
+        elif self._data['counts_x'].device != self._device:
+            self._data = {nn: vv.to(self._device) for nn, vv in self._data.items()}
+        return self._data
+
+    @property
+    def counts_x(self):
+        return self.allocate()['counts_x'][:self.sample_size * self.nx].cpu().numpy()
+
+    @property
+    def counts_y(self):
+        return self.allocate()['counts_y'][:self.sample_size * self.ny].cpu().numpy()
+
+    @property
+    def x_edges(self):
+        return self.x_min + self.dx * np.arange(self.nx + 1)
+
+    @property
+    def x_grid(self):
+        return self.x_edges[1:] - self.dx / 2
+
+    @property
+    def x_intensity(self):
+        return self.counts_x.reshape((-1, self.nx))
+
+    @property
+    def y_edges(self):
+        return self.y_min + self.dy * np.arange(self.ny + 1)
+
+    @property
+    def y_grid(self):
+        return self.y_edges[1:] - self.dy / 2
+
+    @property
+    def y_intensity(self):
+        return self.counts_y.reshape((-1, self.ny))
