@@ -191,6 +191,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--quick', action='store_true',
                     help='tuning runs: skip the e2e and other-variant legs')
+    ap.add_argument('--monitor', action='store_true',
+                    help='record every turn of every particle in a ParticlesMonitor (240 B per '
+                         'particle-turn; BASELINE.json configs[4]); --quick only')
     ap.add_argument('--fma', action='store_true',
                     help='FMA-contracted kernel variant (default: exact, reference rounding)')
     args = ap.parse_args()
@@ -278,8 +281,17 @@ def main():
     # ---- resident-in-HBM measurement ("value") -----------------------------------------
     p = p_host.copy(_device=dev)
     stream = torch.cuda.current_stream(dev)
+    track_kw = {}
+    if args.monitor:
+        # one monitor for the whole run, allocated (zero-filled) outside the timed region:
+        # [32 fields][particle][turn], 240 B per particle-turn (particles_monitor.py:78-104)
+        mon = xb.ParticlesMonitor(start_at_turn=0, stop_at_turn=args.turns * (args.warmup + args.steps),
+                                  num_particles=n, _device=dev)
+        mon.allocate(dev)
+        track_kw['turn_by_turn_monitor'] = mon
+        config['monitor'] = 'ParticlesMonitor, every turn of every particle (240 B / particle-turn)'
     for _ in range(args.warmup):
-        line.track(p, num_turns=args.turns)
+        line.track(p, num_turns=args.turns, **track_kw)
     final_reduction(p)         # warm-up of the reduction leg too (lazy module loading)
     barrier()
     launches0 = _cabi.launch_count()
@@ -294,7 +306,7 @@ def main():
     ev0.record(stream)
     for ii in range(args.steps):
         kev[ii][0].record(stream)
-        line.track(p, num_turns=args.turns)
+        line.track(p, num_turns=args.turns, **track_kw)
         kev[ii][1].record(stream)
     stats = final_reduction(p)
     ev1.record(stream)
@@ -319,8 +331,14 @@ def main():
     if args.quick:
         peak_sustained, peak_burst = _cabi.measure_dfma_peak(local_rank, 0.5)
         achieved = (pet / n_el) * flop_per_turn / (float(np.sum(kernel_ms)) * 1e-3)
+        extra = {}
+        if args.monitor:
+            rec_bytes = 240.0 * (pet / n_el)          # particle-turns recorded x 240 B
+            extra['monitor'] = {'bytes_per_step': rec_bytes / args.steps,
+                                'GB_per_s_of_kernel_time': rec_bytes / (float(np.sum(kernel_ms)) * 1e-3) / 1e9,
+                                'x_last_turn_mean': float(np.mean(mon.x[:, args.turns * (args.warmup + args.steps) - 1]))}
         if rank == 0:
-            emit(({'metric': 'particle-element-turns/s', 'value': value, 'quick': True,
+            emit(({**extra, 'metric': 'particle-element-turns/s', 'value': value, 'quick': True,
                               'ms_per_step': ms_total / args.steps, 'config': config,
                               'clocks': clocks, 'gpu_launches': int(launches),
                               'kernel_variant': 'fma' if args.fma else 'exact',
