@@ -450,6 +450,8 @@ __device__ __forceinline__ void magnet_kick_n(PState (&P)[N], const BodyPar& b, 
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             double m, n;
+            // (order 3 whatever the zero pattern: trimming the leading zero orders with a
+            // run-time order measured 1.5 % SLOWER than the unrolled constant-order loop)
             horner_kick(P[k].x, P[k].y, P[k].chi, b.cm(), 3, m, n);
             P[k].px += kick_weight * (-m);
             P[k].py += kick_weight * n;
