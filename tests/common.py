@@ -221,3 +221,18 @@ def beam_monitor_ring(kind, n=400, turns=6):
     sig['zeta'] = 0.25 * line.get_length() / 4          # spread over neighbouring slots
     p_host = gaussian_particles(line2, n, 3, sig, scale=5.0)
     return line2, els_ref, mon_ref, mon, p_host
+
+
+def lep_with_apertures(every=40, half_x=4e-3, half_y=1.5e-3):
+    """The LEP thick lattice with a LimitRect after every `every`-th element: losses between
+    and inside runs of thick magnets (exercises the loss bookkeeping of the thick run loop)."""
+    line = load_line('lep')
+    els = []
+    for ii, el in enumerate(line.elements):
+        els.append(el)
+        if ii % every == every - 1:
+            els.append(xb.LimitRect(min_x=-half_x, max_x=half_x, min_y=-half_y, max_y=half_y))
+    line2 = xb.Line(elements=els)
+    line2.particle_ref = line.particle_ref
+    return line2
+

@@ -353,3 +353,25 @@ def test_beam_profile_monitor_vs_oracle_gpu():
     assert len(mon.x_edges) == 25 and abs(mon.x_grid[0] - (-0.015 + 0.03 / 48)) < 1e-15
     mon2 = type(mon).from_dict(mon.to_dict())
     assert np.array_equal(mon2.counts_x, mon.counts_x) and mon2.dy == mon.dy
+
+
+def test_losses_in_thick_lattice_gpu():
+    """LEP thick lattice + apertures, wide beam, on the B200: loss records (state / at_turn /
+    at_element) identical to the reference for every particle; coordinates within the bar."""
+    line = common.lep_with_apertures()
+    p_host = common.gaussian_particles(line, 2001, 17, common.SIGMAS['lep'], scale=4.0)
+    ref = common.oracle_track(line, p_host, 3)
+    yard = common.libm_yardstick(line, p_host, 3, ref=ref)
+    n_lost = int((ref['state'] <= 0).sum())
+    assert 200 < n_lost < 1900, n_lost
+    for exact in (True, False):
+        got = common.by_id(_track_gpu(line, p_host, 3, exact))
+        frac = np.mean((got['state'] == ref['state']) & (got['at_turn'] == ref['at_turn'])
+                       & (got['at_element'] == ref['at_element']))
+        print('exact' if exact else 'fma', 'lost', n_lost, 'identical loss records', frac)
+        assert frac >= 0.9995, frac
+        lost = ref['state'] <= 0
+        ok = lost & (got['at_element'] == ref['at_element']) & (got['at_turn'] == ref['at_turn'])
+        common.assert_parity(got, ref, yard, exact, mask=ok, label='lep lost')
+        common.assert_parity(got, ref, yard, exact, mask=~lost & (got['state'] > 0), label='lep alive')
+

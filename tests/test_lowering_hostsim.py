@@ -339,3 +339,17 @@ def test_optimize_for_tracking(name):
     dev = common.max_rel_dev(got, ref_plain)
     assert max(dev.values()) < 1e-8, dev
     print(name, n0, '->', n1, 'elements; dev vs unoptimised', max(dev.values()))
+
+
+def test_losses_in_thick_lattice_bit_identical():
+    """LEP thick lattice + apertures, wide beam: particles are lost all along the ring while
+    their thread neighbours go on (thick run loop, two particles per thread): loss records
+    and every coordinate identical to the reference, odd particle count included."""
+    line = common.lep_with_apertures()
+    p_host = common.gaussian_particles(line, 61, 17, common.SIGMAS['lep'], scale=4.0)
+    ref = common.oracle_track(line, p_host, 3)
+    n_lost = int((ref['state'] <= 0).sum())
+    assert 8 < n_lost < 55, n_lost
+    got = common.by_id(_track(line, p_host, 3))
+    _assert_identical(got, ref)
+
