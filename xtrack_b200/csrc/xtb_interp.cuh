@@ -833,7 +833,7 @@ __device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, 
         }
         default: {      // XTB_STOP_SLOW: generic / heavy op, flags honoured
 #ifdef XTB_WITH_HEAVY
-            if constexpr (HEAVY && (NPT > 1) && std::is_same<S, PState>::value) {
+            if constexpr (HEAVY && std::is_same<S, PState>::value) {
                 if (op == XTB_OP_MAGNET_BODY || op == XTB_OP_DRIFT) {
                     xtb_run_heavy<NPT, SYNRAD, FRZ>(tb, lanes, ps, a);     // a whole run of them
                     break;

@@ -525,89 +525,57 @@ __device__ __forceinline__ double rand_exponential(RadCtx& c) {
     return -log(x1);
 }
 
-// SynRad, headers/synrad_spectrum.h:80-175 (Chebyshev series from H.Burkhardt)
+// SynRad, headers/synrad_spectrum.h:80-175 (Chebyshev series from H.Burkhardt).  The
+// reference writes each series out as a chain `a = z*b - a + c_k; b = z*a - b + c_k+1; ...`:
+// t_k = z*t_(k-1) - t_(k-2) + c_k with t_0 = c_0 (t_(-1) = 0: `z*t_0 - 0` is `z*t_0` exactly)
+// and a last step with z/2.  Here the coefficients sit in constant memory and the chain is a
+// loop -- same operations in the same order -- because written out, with two 32-bit moves per
+// 64-bit literal, the three series were a third of the radiation kernel's instructions and
+// the kernel was bound by instruction fetch (ncu: 65 % of its samples `no_instruction`).
+XTB_CONST_TABLE XTB_SYNRAD_P[19] = {
+    .00000000000000000012, .00000000000000000460, .00000000000000031738, .00000000000002004426,
+    .00000000000111455474, .00000000005407460944, .00000000226722011790, .00000008125130371644,
+    .00000245751373955212, .00006181256113829740, .00127066381953661690, .02091216799114667278,
+    .26880346058164526514, 2.61902183794862213818, 18.65250896865416256398, 92.95232665922707542088,
+    308.15919413131586030542, 644.86979658236221700714, 414.56543648832546975110};
+XTB_CONST_TABLE XTB_SYNRAD_Q[18] = {
+    .00000000000000000004, .00000000000000000289, .00000000000000019786, .00000000000001196168,
+    .00000000000063427729, .00000000002923635681, .00000000115951672806, .00000003910314748244,
+    .00000110599584794379, .00002581451439721298, .00048768692916240683, .00728456195503504923,
+    .08357935463720537773, .71031361199218887514, 4.26780261265492264837, 17.05540785795221885751,
+    41.83903486779678800040, 28.41787374362784178164};
+XTB_CONST_TABLE XTB_SYNRAD_R[30] = {
+    .00000000000000000001, -.00000000000000000002, .00000000000000000006, -.00000000000000000020,
+    .00000000000000000066, -.00000000000000000216, .00000000000000000721, -.00000000000000002443,
+    .00000000000000008441, -.00000000000000029752, .00000000000000107116, -.00000000000000394564,
+    .00000000000001489474, -.00000000000005773537, .00000000000023030657, -.00000000000094784973,
+    .00000000000403683207, -.00000000001785432348, .00000000008235329314, -.00000000039817923621,
+    .00000000203088939238, -.00000001101482369622, .00000006418902302372, -.00000040756144386809,
+    .00000287536465397527, -.00002321251614543524, .00022505317277986004, -.00287636803664026799,
+    .06239591359332750793, 1.06552390798340693166};
+__device__ __forceinline__ double synrad_series(const double* __restrict__ c, const int n, const double z) {
+    double t2 = 0., t1 = c[0];
+#pragma unroll 1
+    for (int k = 1; k < n - 1; ++k) {
+        const double t = z * t1 - t2 + c[k];
+        t2 = t1;
+        t1 = t;
+    }
+    return .5 * z * t1 - t2 + c[n - 1];
+}
+
 static __device__ __noinline__ double synrad_fn(const double x) {
     double synrad = 0.;
     if (x > 0. && x < 800.) {
         if (x < 6.) {
-            double a, b, z;
-            z = x * x / 16. - 2.;
-            b = .00000000000000000012;
-            a = z * b + .00000000000000000460;
-            b = z * a - b + .00000000000000031738;
-            a = z * b - a + .00000000000002004426;
-            b = z * a - b + .00000000000111455474;
-            a = z * b - a + .00000000005407460944;
-            b = z * a - b + .00000000226722011790;
-            a = z * b - a + .00000008125130371644;
-            b = z * a - b + .00000245751373955212;
-            a = z * b - a + .00006181256113829740;
-            b = z * a - b + .00127066381953661690;
-            a = z * b - a + .02091216799114667278;
-            b = z * a - b + .26880346058164526514;
-            a = z * b - a + 2.61902183794862213818;
-            b = z * a - b + 18.65250896865416256398;
-            a = z * b - a + 92.95232665922707542088;
-            b = z * a - b + 308.15919413131586030542;
-            a = z * b - a + 644.86979658236221700714;
-            double p;
-            p = .5 * z * a - b + 414.56543648832546975110;
-            a = .00000000000000000004;
-            b = z * a + .00000000000000000289;
-            a = z * b - a + .00000000000000019786;
-            b = z * a - b + .00000000000001196168;
-            a = z * b - a + .00000000000063427729;
-            b = z * a - b + .00000000002923635681;
-            a = z * b - a + .00000000115951672806;
-            b = z * a - b + .00000003910314748244;
-            a = z * b - a + .00000110599584794379;
-            b = z * a - b + .00002581451439721298;
-            a = z * b - a + .00048768692916240683;
-            b = z * a - b + .00728456195503504923;
-            a = z * b - a + .08357935463720537773;
-            b = z * a - b + .71031361199218887514;
-            a = z * b - a + 4.26780261265492264837;
-            b = z * a - b + 17.05540785795221885751;
-            a = z * b - a + 41.83903486779678800040;
-            double q;
-            q = .5 * z * a - b + 28.41787374362784178164;
-            double y;
-            y = pow(x, 2. / 3.);
+            const double z = x * x / 16. - 2.;
+            const double p = synrad_series(XTB_SYNRAD_P, 19, z);
+            const double q = synrad_series(XTB_SYNRAD_Q, 18, z);
+            const double y = pow(x, 2. / 3.);
             synrad = (p / y - q * y - 1.) * 1.81379936423421784215530788143;
         } else {
-            double a, b, z;
-            z = 20. / x - 2.;
-            a = .00000000000000000001;
-            b = z * a - .00000000000000000002;
-            a = z * b - a + .00000000000000000006;
-            b = z * a - b - .00000000000000000020;
-            a = z * b - a + .00000000000000000066;
-            b = z * a - b - .00000000000000000216;
-            a = z * b - a + .00000000000000000721;
-            b = z * a - b - .00000000000000002443;
-            a = z * b - a + .00000000000000008441;
-            b = z * a - b - .00000000000000029752;
-            a = z * b - a + .00000000000000107116;
-            b = z * a - b - .00000000000000394564;
-            a = z * b - a + .00000000000001489474;
-            b = z * a - b - .00000000000005773537;
-            a = z * b - a + .00000000000023030657;
-            b = z * a - b - .00000000000094784973;
-            a = z * b - a + .00000000000403683207;
-            b = z * a - b - .00000000001785432348;
-            a = z * b - a + .00000000008235329314;
-            b = z * a - b - .00000000039817923621;
-            a = z * b - a + .00000000203088939238;
-            b = z * a - b - .00000001101482369622;
-            a = z * b - a + .00000006418902302372;
-            b = z * a - b - .00000040756144386809;
-            a = z * b - a + .00000287536465397527;
-            b = z * a - b - .00002321251614543524;
-            a = z * b - a + .00022505317277986004;
-            b = z * a - b - .00287636803664026799;
-            a = z * b - a + .06239591359332750793;
-            double p;
-            p = .5 * z * a - b + 1.06552390798340693166;
+            const double z = 20. / x - 2.;
+            const double p = synrad_series(XTB_SYNRAD_R, 30, z);
             synrad = p * sqrt(0.5 * XTB_PI / x) / exp(x);
         }
     }
