@@ -4,9 +4,10 @@
 // Design:
 //   * one thread carries NPT particle slots; their coordinates live in FP64
 //     registers over the whole launch (PState), SoA traffic only at entry / exit /
-//     loss / monitor records.  NPT = 2 for the thin kernels: one op decode and
-//     one set of shared-memory parameter loads serve two particles, and the two
-//     independent dependency chains keep the FP64 pipe fed;
+//     loss / monitor records.  NPT = 3 in the thin kernels, 2 in the thick ones, 1 in the
+//     radiation kernels (xtb_kernel_inst.cu): one op decode and one set of shared-memory
+//     parameter loads serve all of them, and their independent dependency chains keep the
+//     FP64 pipe fed;
 //   * the lowered lattice is streamed through shared memory in tiles with
 //     1-D bulk async copies (cp.async.bulk + mbarrier, SASS UBLKCP), double
 //     buffered; all lanes read the same op -> shared-memory broadcast;
