@@ -93,8 +93,8 @@ static void run(const XtbTrackArgs& a) {
                     }
             lanes.eidx = 0;
             lanes.off = 0;
-            if (fast_state) xtb_run_tile<NPT, true, SYNRAD, FRZ, true, true>(a.prog, lanes, ps, a);
-            else xtb_run_tile<NPT, true, SYNRAD, FRZ, false, false>(a.prog, lanes, ps, a);
+            if (fast_state) xtb_run_tile<NPT, true, SYNRAD, FRZ, true, true, true>(a.prog, lanes, ps, a);
+            else xtb_run_tile<NPT, true, SYNRAD, FRZ, false, false, true>(a.prog, lanes, ps, a);
             const uint32_t eidx = a.num_ele_track;
             if (a.flag_monitor == 2)
                 for (int k = 0; k < NPT; ++k)

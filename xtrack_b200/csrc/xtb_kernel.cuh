@@ -16,7 +16,8 @@
 //     lanes are all done skips whole tiles (warp vote), a block stops at the
 //     next turn boundary;
 //   * template switches select the kernel variant: HEAVY (thick-magnet ops
-//     compiled in), SYNRAD, FRZ (freeze_longitudinal).  The translation unit is
+//     compiled in), SYNRAD, FRZ (freeze_longitudinal), BMON (beam-monitor ops compiled
+//     in: always in the thick kernels, on demand in the thin ones).  The translation unit is
 //     compiled twice, with and without FMA contraction (xtb_kernel_inst.cu).
 #pragma once
 #include <cuda_runtime.h>
@@ -76,7 +77,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // EXACT only distinguishes the symbols of the two builds of this translation unit
 // (template instantiations are COMDAT: identical names would be merged at link time).
-template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT>
+template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT, bool BMON>
 __global__ void __launch_bounds__(XTB_THREADS, HEAVY ? (SYNRAD ? XTB_SYNRAD_BLOCKS_PER_SM : XTB_HEAVY_BLOCKS_PER_SM)
                                                       : XTB_THIN_BLOCKS_PER_SM)
 xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
@@ -220,9 +221,9 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
                 lanes.eidx = eidx;
                 lanes.off = lo - w0;
                 if (fast_state)
-                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, !HEAVY, !HEAVY>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, !HEAVY, !HEAVY, BMON>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
                 else
-                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, false, false>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
+                    xtb_run_tile<NPT, HEAVY, SYNRAD, FRZ, false, false, BMON>(xtb_tile_of(&tile[b][0]), lanes, ps, a);
                 eidx = lanes.eidx;
             }
             if (!resident) {

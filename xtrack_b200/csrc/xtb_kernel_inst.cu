@@ -26,21 +26,24 @@
 #define XTB_NPT_SYNRAD 1
 #endif
 
-template <bool HEAVY, bool SYNRAD, bool FRZ>
+template <bool HEAVY, bool SYNRAD, bool FRZ, bool BMON = HEAVY>
 static cudaError_t launch(const XtbTrackArgs& a, cudaStream_t stream) {
     constexpr int NPT = HEAVY ? (SYNRAD ? XTB_NPT_SYNRAD : XTB_NPT_HEAVY) : XTB_NPT_THIN;
     const int64_t per_block = (int64_t) XTB_THREADS * NPT;
     const unsigned grid = (unsigned) ((a.part.capacity + per_block - 1) / per_block);
-    xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0)><<<grid, XTB_THREADS, 0, stream>>>(a);
+    xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0), BMON><<<grid, XTB_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
-// variant bits: 1 = heavy ops present, 2 = synrad, 4 = freeze longitudinal
+// variant bits: 1 = heavy ops present, 2 = synrad, 4 = freeze longitudinal,
+// 8 = beam-monitor ops present (thin kernels only: the thick ones always contain them)
 extern "C" cudaError_t XTB_LAUNCH_NAME(unsigned variant, const XtbTrackArgs* a,
                                        cudaStream_t stream) {
     switch (variant & 7u) {
-    case 0: return launch<false, false, false>(*a, stream);
-    case 4: return launch<false, false, true>(*a, stream);
+    case 0: return (variant & 8u) ? launch<false, false, false, true>(*a, stream)
+                                  : launch<false, false, false, false>(*a, stream);
+    case 4: return (variant & 8u) ? launch<false, false, true, true>(*a, stream)
+                                  : launch<false, false, true, false>(*a, stream);
 #ifdef XTB_WITH_HEAVY
     case 1: return launch<true, false, false>(*a, stream);
     case 5: return launch<true, false, true>(*a, stream);

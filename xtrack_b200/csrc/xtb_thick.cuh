@@ -122,9 +122,8 @@ XTB_CONST_TABLE XTB_Y6[16] = {
 // cos(h*s), pz and rvv use the reciprocals at hand (div_by): same correctly rounded quotients.
 template <int N, bool FRZ>
 __device__ __forceinline__ void polar_drift_n(PState (&P)[N], const double length, const double h,
-                                              const TrigTab& tt, const int idx) {
+                                              const TrigTab& tt, const int idx, const double rho) {
     const double s = length;
-    const double rho = (tt.n() > 0) ? tt.rho() : 1 / h;
     double ca, sa, sa2, rca;
     trig_of(tt, idx, h, s, ca, sa, sa2, rca);
     // (each statement of the reference's map, for all N particles in turn: see XTB_LANES)
@@ -164,7 +163,8 @@ __device__ __forceinline__ void polar_drift_n(PState (&P)[N], const double lengt
 template <bool FRZ>
 __device__ __noinline__ void polar_drift(PState& P, const double length, const double h,
                                          const TrigTab& tt, const int idx) {
-    polar_drift_n<1, FRZ>(reinterpret_cast<PState(&)[1]>(P), length, h, tt, idx);
+    polar_drift_n<1, FRZ>(reinterpret_cast<PState(&)[1]>(P), length, h, tt, idx,
+                          (tt.n() > 0) ? tt.rho() : 1 / h);
 }
 
 // S = sin(sqrt(K) L) / sqrt(K), C = cos(sqrt(K) L) for K > 0, the hyperbolic pair for K < 0,
@@ -349,11 +349,13 @@ __device__ __forceinline__ void magnet_drift_n(PState (&P)[N], const double leng
         // state stays in registers for the whole body, the code is there once
         const int n_in = (drift_model == 2) ? 1 : ((drift_model == 7) ? 4 : 8);
         const double* __restrict__ tab = (drift_model == 7) ? XTB_Y4_NESTED : XTB_Y6;
+        const int n_inner = tt.n_inner();                          // (read once per call)
+        const double rho = (tt.n() > 0) ? tt.rho() : 1 / h;
 #pragma unroll 1
         for (int j = 0; j < n_in; ++j) {
             const double lj = (n_in == 1) ? length : tab[j] * length;
             const int ic = (j < n_in - 1 - j) ? j : n_in - 1 - j;
-            polar_drift_n<N, FRZ>(P, lj, h, tt, oc * tt.n_inner() + ic);
+            polar_drift_n<N, FRZ>(P, lj, h, tt, oc * n_inner + ic, rho);
             if (j < n_in - 1) {
                 const double kj = tab[n_in + j];
 #pragma unroll
