@@ -801,8 +801,11 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
 //      lanes whose high words are all below hi32(lim) are inside for sure -- no FP64
 //      instruction, no false negative; the exact test here sorts out the false positives;
 //   1  |x| < 2^e(lim) (2 DSETP per particle) as the pre-filter.
+#ifndef XTB_RUN_TILE_INLINE
+#define XTB_RUN_TILE_INLINE __forceinline__
+#endif
 template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool CHI1, bool SUNI, bool BMON, class S>
-__device__ __forceinline__ void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, S>& lanes,
+__device__ XTB_RUN_TILE_INLINE void xtb_run_tile(const xtb_tile_t tb, XtbLanes<NPT, S>& lanes,
                                              const XtbPass& ps, const XtbTrackArgs& a) {
     const double lim = a.global_xy_limit;
     // high word of the limit for the pre-filter (0: every check goes to the exact test)
