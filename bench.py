@@ -14,8 +14,10 @@ the GPU between steps).  Particles shard over the GPUs with no per-turn communic
 beam statistics (NCCL), outside the hot loop but inside the timed region.
 
   value      PET/s with the particle SoA resident in HBM (device-timed, CUDA events)
-  e2e        the same through the public API `Line.track` with HOST buffers: pinned
-             host -> device copy of the SoA, track, device -> host copy of the result
+  e2e        the same through the public API `Line.track` with HOST buffers: every step
+             copies its inputs from pinned host memory to the device, tracks, and copies
+             the result back, all inside the timed region; two device particle sets and
+             two copy streams let the copies of the neighbouring steps overlap the tracking
   roofline   bound = fp64 (FP64 FMA pipe; there is no contraction and ~0 HBM traffic
              per element-turn): achieved = algorithmic flop/PET x PET/s, peak = DFMA
              chain measured in this run by `xtb_measure_dfma_peak` (MEASURED_PEAKS.json
@@ -355,23 +357,48 @@ def main():
     pinned_in = {nn: p_host._fields[nn].clone().pin_memory() for nn in names}
     pinned_out = {nn: torch.empty_like(pinned_in[nn]).pin_memory() for nn in names}
     bytes_io = sum(t.numel() * t.element_size() for t in pinned_in.values())
-    p_dev = p_host.copy(_device=dev)
+    # Two device particle sets and two copy streams: the host->device copy of step i+1 and the
+    # device->host copy of step i-1 run while step i tracks -- what a user who streams batches
+    # through `Line.track` does.  Every step still copies its own inputs in and its own
+    # result out inside the timed region.
+    p_dev = [p_host.copy(_device=dev), p_host.copy(_device=dev)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        for nn in names:                             # H2D of this step's inputs
-            p_dev._fields[nn].copy_(pinned_in[nn], non_blocking=True)
-        line.track(p_dev, num_turns=args.turns)      # the call a user makes
-        for nn in names:                             # D2H of the result
-            pinned_out[nn].copy_(p_dev._fields[nn], non_blocking=True)
+    def h2d(ii):                                     # inputs of step ii -> device set ii % 2
+        bb = ii % 2
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[bb])             # its previous result has left the device
+            for nn in names:
+                p_dev[bb]._fields[nn].copy_(pinned_in[nn], non_blocking=True)
+            ev_in[bb].record(s_in)
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(n_steps):
+        for bb in range(2):
+            ev_free[bb].record(stream)
+        h2d(0)
+        for ii in range(n_steps):
+            bb = ii % 2
+            if ii + 1 < n_steps:
+                h2d(ii + 1)
+            stream.wait_event(ev_in[bb])
+            line.track(p_dev[bb], num_turns=args.turns)      # the call a user makes
+            ev_done[bb].record(stream)
+            with torch.cuda.stream(s_out):                   # D2H of the result
+                s_out.wait_event(ev_done[bb])
+                for nn in names:
+                    pinned_out[nn].copy_(p_dev[bb]._fields[nn], non_blocking=True)
+                ev_free[bb].record(s_out)
+        stream.wait_event(ev_free[(n_steps - 1) % 2])        # the last result is on the host
+
+    e2e_run(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(2, args.steps // 2)
+    n_e2e = max(4, args.steps)
     e0.record(stream)
-    for _ in range(n_e2e):
-        e2e_step()
+    e2e_run(n_e2e)
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
