@@ -51,8 +51,12 @@ WORKLOADS = {
     'clic_dr_quantum': ('clic_dr', 'CLIC-DR thin lattice, quantum synchrotron radiation, '
                                    'Gaussian beam'),
     'lep_quantum': ('lep', 'LEP thick lattice, quantum synchrotron radiation, Gaussian beam'),
+    # ... and with the deterministic mean energy loss (configure_radiation('mean'))
+    'clic_dr_mean': ('clic_dr', 'CLIC-DR thin lattice, mean synchrotron radiation, Gaussian beam'),
+    'lep_mean': ('lep', 'LEP thick lattice, mean synchrotron radiation, Gaussian beam'),
 }
-RADIATION = {'clic_dr_quantum': 'quantum', 'lep_quantum': 'quantum'}
+RADIATION = {'clic_dr_quantum': 'quantum', 'lep_quantum': 'quantum',
+             'clic_dr_mean': 'mean', 'lep_mean': 'mean'}
 
 
 def load_line(fixture, radiation=None):

@@ -120,7 +120,13 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
                                   double line_length, const xtb_monitor_t* inline_mon,
                                   const xtb_last_turns_monitor_t* inline_ltm, int32_t npt, int32_t force_full) {
     int npt_heavy = (npt >> 8) ? (npt >> 8) : 2;
-    if (variant & XTB_VARIANT_SYNRAD) npt_heavy = 1;      // XTB_NPT_SYNRAD of xtb_kernel_inst.cu
+    // XTB_NPT_SYNRAD of xtb_kernel_inst.cu: one lane per thread when photon-emission bodies exist
+    if (variant & XTB_VARIANT_SYNRAD) {
+        const uint64_t* w0 = words + elem_offset[ele_start];
+        const uint64_t* w1 = words + elem_offset[ele_start + num_ele_track];
+        for (const uint64_t* pw = w0; pw < w1; pw += (*pw >> 16) & 0xffffu)
+            if ((*pw & 0xffu) == XTB_OP_MAGNET_BODY && (((uint32_t) (*pw >> 32) >> 10) & 3u) == 2u) npt_heavy = 1;
+    }
     npt &= 0xff;
     XtbTrackArgs a;
     std::memset(&a, 0, sizeof(a));

@@ -40,6 +40,7 @@ struct xtb_program {
     size_t n_words = 0, n_tiles = 0;
     bool has_heavy = false;
     bool has_beam_mon = false;     // XTB_OP_BEAM_MON / XTB_OP_BEAM_PROFILE present
+    bool has_quantum = false;      // a magnet body with radiation_flag 2 (photon emission)
     uint64_t* d_prog = nullptr;          // IMAGE: tile k = its ops + one XTB_OP_END op (2 words)
     uint32_t* d_tile_off = nullptr;      // image offsets [n_tiles + 1]
     std::vector<uint32_t> elem_offset;   // host copy [n_elements + 1], XTB_NOT_ADDRESSABLE allowed
@@ -87,6 +88,7 @@ static int program_prepare(xtb_program& G, const uint64_t* words, size_t n_words
             if (nw < 2 || (nw & 1u) || pc + nw > w1) return fail(XTB_E_INVALID, "malformed op in program");
             if (op >= XTB_HEAVY_FIRST) G.has_heavy = true;
             if (op == XTB_OP_BEAM_MON || op == XTB_OP_BEAM_PROFILE) G.has_beam_mon = true;
+            if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) == 2u) G.has_quantum = true;
             pc += nw;
         }
         if (w1 - G.tile_off.back() > XTB_TILE_WORDS) G.tile_off.push_back(w0);
@@ -272,6 +274,7 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     if (variant_flags & XTB_VARIANT_SYNRAD) variant |= 2u;
     if (variant_flags & XTB_VARIANT_FREEZE_LONG) variant |= 4u;
     if (G->has_beam_mon) variant |= 8u;
+    if (G->has_quantum) variant |= 16u;
 
     int prev = 0;
     cudaGetDevice(&prev);

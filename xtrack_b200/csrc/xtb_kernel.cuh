@@ -78,7 +78,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // EXACT only distinguishes the symbols of the two builds of this translation unit
 // (template instantiations are COMDAT: identical names would be merged at link time).
 template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT, bool BMON>
-__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? (SYNRAD ? XTB_SYNRAD_BLOCKS_PER_SM : XTB_HEAVY_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? ((SYNRAD && NPT == 1) ? XTB_SYNRAD_BLOCKS_PER_SM
+                                                                               : XTB_HEAVY_BLOCKS_PER_SM)
                                                       : XTB_THIN_BLOCKS_PER_SM)
 xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     using S = typename std::conditional<HEAVY, PState, PHot>::type;

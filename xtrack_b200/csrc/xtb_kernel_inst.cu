@@ -26,9 +26,11 @@
 #define XTB_NPT_SYNRAD 1
 #endif
 
-template <bool HEAVY, bool SYNRAD, bool FRZ, bool BMON = HEAVY>
+// QUANTUM: the program contains photon-emission (radiation_flag 2) bodies.  Radiation with the
+// deterministic mean model only runs like the other thick kernels (XTB_NPT_HEAVY lanes).
+template <bool HEAVY, bool SYNRAD, bool FRZ, bool BMON = HEAVY, bool QUANTUM = true>
 static cudaError_t launch(const XtbTrackArgs& a, cudaStream_t stream) {
-    constexpr int NPT = HEAVY ? (SYNRAD ? XTB_NPT_SYNRAD : XTB_NPT_HEAVY) : XTB_NPT_THIN;
+    constexpr int NPT = HEAVY ? ((SYNRAD && QUANTUM) ? XTB_NPT_SYNRAD : XTB_NPT_HEAVY) : XTB_NPT_THIN;
     const int64_t per_block = (int64_t) XTB_THREADS * NPT;
     const unsigned grid = (unsigned) ((a.part.capacity + per_block - 1) / per_block);
     xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0), BMON><<<grid, XTB_THREADS, 0, stream>>>(a);
@@ -36,7 +38,8 @@ static cudaError_t launch(const XtbTrackArgs& a, cudaStream_t stream) {
 }
 
 // variant bits: 1 = heavy ops present, 2 = synrad, 4 = freeze longitudinal,
-// 8 = beam-monitor ops present (thin kernels only: the thick ones always contain them)
+// 8 = beam-monitor ops present (thin kernels only: the thick ones always contain them),
+// 16 = photon-emission bodies present (radiation kernels: one lane per thread)
 extern "C" cudaError_t XTB_LAUNCH_NAME(unsigned variant, const XtbTrackArgs* a,
                                        cudaStream_t stream) {
     switch (variant & 7u) {
@@ -47,8 +50,10 @@ extern "C" cudaError_t XTB_LAUNCH_NAME(unsigned variant, const XtbTrackArgs* a,
 #ifdef XTB_WITH_HEAVY
     case 1: return launch<true, false, false>(*a, stream);
     case 5: return launch<true, false, true>(*a, stream);
-    case 2: case 3: return launch<true, true, false>(*a, stream);
-    case 6: case 7: return launch<true, true, true>(*a, stream);
+    case 2: case 3: return (variant & 16u) ? launch<true, true, false, true, true>(*a, stream)
+                                           : launch<true, true, false, true, false>(*a, stream);
+    case 6: case 7: return (variant & 16u) ? launch<true, true, true, true, true>(*a, stream)
+                                           : launch<true, true, true, true, false>(*a, stream);
 #endif
     default: return cudaErrorNotSupported;
     }
