@@ -353,3 +353,25 @@ def test_losses_in_thick_lattice_bit_identical():
     got = common.by_id(_track(line, p_host, 3))
     _assert_identical(got, ref)
 
+
+
+@pytest.mark.parametrize('ele_start,ele_stop', [(0, None), (5, 3), (2, 9)])
+def test_with_progress_batches_equal_one_call(ele_start, ele_stop):
+    """`Line.track(..., with_progress=N)` (tracker.py:313-381): batches of N turns -- partial
+    first / last turns, one monitor over all batches -- give the result of the single call."""
+    line = common.toy_ring(thin=True)
+    p_host = common.gaussian_particles(line, 40, 21, common.SIGMAS['toy'])
+    hostsim.build_hostsim_tracker(line)
+    pa, pb = p_host.copy(), p_host.copy()
+    line.track(pa, num_turns=11, ele_start=ele_start, ele_stop=ele_stop, turn_by_turn_monitor=True)
+    mon_a = line.record_last_track
+    line.track(pb, num_turns=11, ele_start=ele_start, ele_stop=ele_stop, turn_by_turn_monitor=True,
+               with_progress=4)
+    mon_b = line.record_last_track
+    ga, gb = common.by_id(pa), common.by_id(pb)
+    for ff in common.ALL_F64 + ('state', 'at_turn', 'at_element'):
+        assert np.array_equal(ga[ff], gb[ff]), ff
+    for ff in ('x', 'px', 'zeta', 'at_turn', 'at_element'):
+        assert np.array_equal(mon_a.get(ff), mon_b.get(ff)), ff
+    with pytest.raises(ValueError):
+        line.track(pb, with_progress=True)

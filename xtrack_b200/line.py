@@ -239,6 +239,56 @@ class Line:
         self.tracker = tracker_class(self, device=_device, **kwargs)
         return self.tracker
 
+    def _track_in_batches(self, particles, with_progress, *, ele_start, ele_stop, num_elements,
+                          num_turns, turn_by_turn_monitor, freeze_longitudinal, time):
+        """`with_progress` of xtrack (tracker.py:313-381): the turns are tracked in batches of
+        `with_progress` turns (100 for True) -- first batch from `ele_start` to the end of the
+        line, middle batches whole turns, last batch down to `ele_stop` -- with one monitor
+        spanning all of them.  (The progress bar itself is a host nicety: one line per batch on
+        stderr when `XTRACK_B200_PROGRESS` is set.)"""
+        import os
+        import sys
+        if num_turns is None:
+            raise ValueError('Tracking with progress indicator is only possible over more than '
+                             'one turn.')
+        batch_size = 100 if with_progress is True else int(with_progress)
+        n_el = len(self.element_names)
+        e0 = ele_start or 0
+        if isinstance(e0, str):
+            e0 = self.element_names.index(e0)
+        e1 = ele_stop
+        if isinstance(e1, str):
+            e1 = self.element_names.index(e1)
+        if e1 is None:
+            e1 = n_el
+        if e0 >= e1:
+            num_turns += 1           # the incomplete turn needs its own slot (and monitor space)
+        if turn_by_turn_monitor is True:
+            _, turn_by_turn_monitor = self.tracker._get_monitor(particles, True, num_turns)
+        total_time = 0.0
+        num_turns_orig = num_turns - 1 if e0 >= e1 else num_turns
+        for ii in range(0, num_turns, batch_size):
+            kw = dict(ele_start=ele_start, ele_stop=ele_stop, num_elements=num_elements,
+                      num_turns=num_turns_orig)
+            first, last = ii == 0, ii + batch_size >= num_turns
+            if first and last:
+                pass                                     # the only batch: track as normal
+            elif first:
+                kw.update(ele_stop=None, num_turns=batch_size)
+            elif last:
+                kw.update(ele_start=None, num_turns=num_turns % batch_size or batch_size)
+            else:
+                kw.update(ele_start=None, ele_stop=None, num_turns=batch_size)
+            self.tracker.track(particles, turn_by_turn_monitor=turn_by_turn_monitor,
+                               freeze_longitudinal=freeze_longitudinal, time=time, **kw)
+            if time and self.time_last_track is not None:
+                total_time += self.time_last_track
+            if os.environ.get('XTRACK_B200_PROGRESS'):
+                print(f'Tracking: {min(ii + batch_size, num_turns)}/{num_turns} turns',
+                      file=sys.stderr)
+        if time:
+            self.time_last_track = total_time
+
     def track(self, particles, ele_start=0, ele_stop=None, num_elements=None,
               num_turns=None, turn_by_turn_monitor=None,
               multi_element_monitor_at=None, freeze_longitudinal=False,
@@ -249,13 +299,16 @@ class Line:
         if multi_element_monitor_at is not None:
             raise NotImplementedError('MultiElementMonitor is CPU-only in the reference '
                                       'and outside the hot-path contract')
-        if with_progress:
-            raise NotImplementedError('with_progress batches are host conveniences '
-                                      '(tracker.py:313-381), not provided')
         if kwargs.get('backtrack', False):
             raise NotImplementedError('backtracking is not part of the contract')
         if self.tracker is None or self.tracker.device != particles.device:
             self.build_tracker(_device=particles.device)
+        if with_progress:
+            return self._track_in_batches(
+                particles, with_progress, ele_start=ele_start, ele_stop=ele_stop,
+                num_elements=num_elements, num_turns=num_turns,
+                turn_by_turn_monitor=turn_by_turn_monitor,
+                freeze_longitudinal=freeze_longitudinal, time=time)
         return self.tracker.track(
             particles, ele_start=ele_start, ele_stop=ele_stop,
             num_elements=num_elements, num_turns=num_turns,
