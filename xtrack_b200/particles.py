@@ -263,6 +263,148 @@ class Particles:
     def energy0(self):
         return torch.sqrt(self.p0c ** 2 + self.mass0 ** 2)
 
+    # -- consistent updates of the energy variables (particles.py:1450-1560, 1956-2008) --------
+    def _masked_set(self, name, new, mask):
+        cur = self.get(name).astype(np.float64)
+        cur[mask] = new[mask]
+        setattr(self, name, cur)
+
+    def _update_energy_deviations_host(self, *, delta=None, ptau=None):
+        b0 = self.get('beta0')
+        st = self.get('state')
+        given = delta if delta is not None else ptau
+        given = np.broadcast_to(np.asarray(given, dtype=np.float64), b0.shape)
+        mask = (~np.isnan(given)) & (st > 0)
+        with np.errstate(invalid='ignore'):
+            if delta is not None:
+                _delta = given
+                _ptau = np.sqrt(_delta ** 2 + 2 * _delta + 1 / b0 ** 2) - 1 / b0
+            else:
+                _ptau = given
+                _delta = np.sqrt(_ptau ** 2 + 2 * _ptau / b0 + 1) - 1
+            delta_beta0 = _delta * b0
+            ptau_beta0 = np.sqrt(delta_beta0 ** 2 + 2 * delta_beta0 * b0 + 1) - 1
+            new_rvv = (1 + _delta) / (1 + ptau_beta0)
+            new_rpp = 1 / (1 + _delta)
+        self._masked_set('delta', _delta, mask)
+        self._masked_set('ptau', _ptau, mask)
+        self._masked_set('rvv', new_rvv, mask)
+        self._masked_set('rpp', new_rpp, mask)
+
+    def update_delta(self, new_delta_value):
+        """`delta` of the active particles; `ptau`, `rvv`, `rpp` follow (NaN entries are left
+        alone), particles.py:1450-1465."""
+        self._update_energy_deviations_host(delta=new_delta_value)
+
+    def update_ptau(self, new_ptau):
+        """particles.py:1486-1501."""
+        self._update_energy_deviations_host(ptau=new_ptau)
+
+    def update_p0c(self, new_p0c):
+        """`p0c` of the active particles; `gamma0`, `beta0` follow (particles.py:1522-1537,
+        `_update_refs`); the energy deviations are left as they are, as in the reference."""
+        new_p0c = np.broadcast_to(np.asarray(new_p0c, dtype=np.float64), self.get('p0c').shape)
+        mask = (~np.isnan(new_p0c)) & (self.get('state') > 0)
+        m0 = self.mass0
+        with np.errstate(invalid='ignore'):
+            e0 = np.sqrt(new_p0c ** 2 + m0 ** 2)
+            beta0 = new_p0c / e0
+            gamma0 = e0 / m0
+        self._masked_set('p0c', new_p0c, mask)
+        self._masked_set('beta0', beta0, mask)
+        self._masked_set('gamma0', gamma0, mask)
+
+    # -- derived quantities (read only; particles.py:1600-1900) ---------------------------
+    @property
+    def mass_ratio(self):
+        return self.charge_ratio / self.chi
+
+    @property
+    def energy(self):
+        return (self.energy0 + self.ptau * self.p0c) * self.mass_ratio
+
+    @property
+    def kinetic_energy0(self):
+        return self.energy0 - self.mass0
+
+    @property
+    def rigidity0(self):
+        return self.p0c / (abs(self.q0) * CLIGHT)
+
+    @property
+    def kin_px(self):
+        return self.px - self.ax
+
+    @property
+    def kin_py(self):
+        return self.py - self.ay
+
+    @property
+    def kin_ps(self):
+        return torch.sqrt((1 + self.delta) ** 2 - self.kin_px ** 2 - self.kin_py ** 2)
+
+    @property
+    def kin_xprime(self):
+        return self.kin_px / self.kin_ps
+
+    @property
+    def kin_yprime(self):
+        return self.kin_py / self.kin_ps
+
+    # -- subsets / unions (particles.py:1002-1130, 1280-1330) ------------------------------
+    def filter(self, mask):
+        """New Particles with the slots where `mask` is true (same device)."""
+        mask = torch.as_tensor(np.asarray(mask.cpu() if torch.is_tensor(mask) else mask),
+                               dtype=torch.bool)
+        idx = torch.nonzero(mask, as_tuple=False).flatten().to(self._device)
+        out = object.__new__(Particles)
+        for kk, vv in self.__dict__.items():
+            if kk != '_fields':
+                object.__setattr__(out, kk, vv)
+        object.__setattr__(out, '_fields', {nn: tt[idx].clone() for nn, tt in self._fields.items()})
+        object.__setattr__(out, '_capacity', int(idx.numel()))
+        return out
+
+    def remove_unused_space(self):
+        """particles.py:1280-1288."""
+        return self.filter(self.get('state') > LAST_INVALID_STATE)
+
+    @classmethod
+    def merge(cls, lst, _device=None):
+        """One Particles object out of several (same reference charge and mass); particle ids
+        are made unique as in the reference (particles.py:1002-1088): an object whose ids
+        collide with the ones before it is shifted behind them."""
+        first = lst[0]
+        dev = torch.device(_device) if _device is not None else first._device
+        for pp in lst[1:]:
+            if pp.q0 != first.q0 or pp.mass0 != first.mass0:
+                raise ValueError('Cannot merge particles with different q0 / mass0')
+        parts = [pp.remove_unused_space() for pp in lst]
+        out = parts[0].filter(np.ones(parts[0]._capacity, dtype=bool))
+        fields = {nn: [pp._fields[nn].to(dev) for pp in parts] for nn in out._fields}
+        next_id = 0
+        for ii, pp in enumerate(parts):
+            ids = fields['particle_id'][ii]
+            if ii > 0 and ids.numel() and int(ids.min()) < next_id:
+                shift = next_id - int(ids.min())
+                fields['particle_id'][ii] = ids + shift
+                par = fields['parent_particle_id'][ii]
+                fields['parent_particle_id'][ii] = par + shift
+                ids = fields['particle_id'][ii]
+            if ids.numel():
+                next_id = max(next_id, int(ids.max()) + 1)
+        object.__setattr__(out, '_fields', {nn: torch.cat(vv) for nn, vv in fields.items()})
+        object.__setattr__(out, '_capacity', int(out._fields['x'].numel()))
+        object.__setattr__(out, '_device', dev)
+        return out
+
+    def add_particles(self, part, keep_lost=False):
+        """particles.py:1291-1330 (returns nothing: this object grows)."""
+        other = part if keep_lost else part.filter(part.get('state') > 0)
+        merged = Particles.merge([self, other], _device=self._device)
+        object.__setattr__(self, '_fields', merged._fields)
+        object.__setattr__(self, '_capacity', merged._capacity)
+
     def to(self, device):
         """Move the SoA to `device` (host<->device copy of all 32 fields)."""
         new = object.__new__(Particles)
