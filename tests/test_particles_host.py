@@ -71,3 +71,13 @@ def test_filter_merge_add_particles():
     assert p._capacity == 10 and np.sum(p.get('state') > 0) == 10
     with pytest.raises(ValueError):
         xb.Particles.merge([p, xb.Particles(p0c=7e12, mass0=xb.ELECTRON_MASS_EV)])
+
+
+def test_pandas_round_trip():
+    p = _p(5)
+    df = p.to_pandas()
+    assert len(df) == 5 and 'x' in df and 'particle_id' in df
+    q = xb.Particles.from_pandas(df)
+    for ff in ('x', 'px', 'delta', 'ptau', 'rvv', 'rpp', 'zeta', 'particle_id', 'state', 'p0c'):
+        assert np.array_equal(q.get(ff), p.get(ff)), ff
+    assert q.mass0 == p.mass0 and q.q0 == p.q0

@@ -498,6 +498,20 @@ class Particles:
             out[nn] = self.get(nn)
         return out
 
+    def to_pandas(self):
+        """One row per particle slot, scalars repeated (particles.py:913-954)."""
+        import pandas as pd
+        return pd.DataFrame(self.to_dict())
+
+    @classmethod
+    def from_pandas(cls, df, load_rng_state=True, _device='cpu'):
+        """particles.py:883-911."""
+        dct = df.to_dict(orient='list')
+        for nn in list(SCALAR_VARS) + ['start_tracking_at_element']:
+            if nn in dct and not np.isscalar(dct[nn]):
+                dct[nn] = dct[nn][0]
+        return cls.from_dict(dct, load_rng_state=load_rng_state, _device=_device)
+
     @classmethod
     def from_dict(cls, dct, load_rng_state=True, _device='cpu', _capacity=None):
         dct = {k: v for k, v in dct.items()
