@@ -277,3 +277,30 @@ def test_no_cpu_fallback():
     with pytest.raises(Exception):
         line.build_tracker(_device='cpu')
         line.track(p, num_turns=1)
+
+
+def test_photon_spectrum_moments_from_energy_loss():
+    """tests/test_radiation.py:119-158 checks the first two moments of the emitted photon
+    spectrum through the photon log (E_ave = 8 sqrt(3)/45 E_crit to 1e-2, the standard
+    deviation from <E^2> = 11/27 E_crit^2).  There is no photon log here (out of scope), but the
+    energy loss of a particle is a compound Poisson sum: mean = lambda <u>, variance =
+    lambda <u^2>, lambda = 5/(2 sqrt 3) alpha gamma theta.  Both moments of the spectrum follow
+    from the beam's energy-loss statistics."""
+    n = 40000
+    line, theta, L_bend = _bend_setup(False, 2)
+    p0c = 5e9
+    p = xb.Particles(p0c=p0c, x=np.zeros(n), mass0=xb.ELECTRON_MASS_EV)
+    common.seed_rng_host(p, (np.arange(1, n + 1, dtype=np.uint64) * 7919 % (1 << 32)).astype(np.uint32))
+    line._extra_config['_needs_rng'] = False
+    got = common.by_id(_track(line, p, 1))
+    dE = -got['ptau'] * p0c                          # eV lost per particle
+    gamma = float(got['gamma0'][0])
+    hbar = 1.054571817e-34
+    mass0_kg = xb.ELECTRON_MASS_EV * QE / CLIGHT ** 2
+    B_T = 2.0
+    E_crit_eV = 3 * QE * hbar * gamma ** 2 * B_T / (2 * mass0_kg) / QE
+    lam = 5 / (2 * np.sqrt(3)) * 0.0072973525693 * gamma * theta
+    u_mean = np.mean(dE) / lam
+    u_sq = np.var(dE) / lam
+    np.testing.assert_allclose(u_mean, 8 * np.sqrt(3) / 45 * E_crit_eV, rtol=1e-2)
+    np.testing.assert_allclose(u_sq, 11 / 27 * E_crit_eV ** 2, rtol=4e-2)
