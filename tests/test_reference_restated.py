@@ -123,3 +123,72 @@ def test_cavity(on_gpu):
                                part0.get('zeta') / part0.get('beta0'), atol=1e-14, rtol=0)
     np.testing.assert_allclose((part.get('ptau') - part0.get('ptau')) * part0.get('p0c'), 30,
                                atol=1e-9, rtol=0)
+
+
+def test_particles_monitor_semantics():
+    """tests/test_monitor.py:71-192 on the hllhc_14 stand-in (the reference's own fixture json
+    is a missing blob): implicit monitor, explicit monitor, dict round trip, frames, monitors
+    installed in the line."""
+    import hostsim
+    line0 = common.load_line('hllhc_14')
+    num_particles = 50
+    particles0 = common.gaussian_particles(line0, num_particles, 5, common.SIGMAS['hllhc_14'])
+    line = line0
+    hostsim.build_hostsim_tracker(line)
+
+    particles = particles0.copy()
+    num_turns = 30
+    line.track(particles, num_turns=num_turns, turn_by_turn_monitor=True)
+    mon = line.record_last_track
+    assert mon.x.shape == (50, 30)
+    assert np.all(mon.at_turn[3, :] == np.arange(0, num_turns))
+    assert np.all(mon.particle_id[:, 3] == np.arange(0, num_particles))
+    assert np.all(mon.at_element[:, :] == 0)
+    assert np.all(mon.pzeta[:, 0] == particles0.get('ptau') / particles0.get('beta0'))
+
+    monitor = xb.ParticlesMonitor(start_at_turn=5, stop_at_turn=15, num_particles=num_particles)
+    particles = particles0.copy()
+    line.track(particles, num_turns=num_turns, turn_by_turn_monitor=monitor)
+    assert monitor.x.shape == (50, 10)
+    assert np.all(monitor.at_turn[3, :] == np.arange(5, 15))
+    assert np.all(monitor.particle_id[:, 3] == np.arange(0, num_particles))
+    assert np.all(monitor.at_element[:, :] == 0)
+    assert np.all(monitor.pzeta[:, 0] == mon.pzeta[:, 5])
+
+    dct = monitor.to_dict()
+    assert 'data' not in dct
+    monitor2 = xb.ParticlesMonitor.from_dict(dct)
+    assert monitor2.x.shape == (50, 10)
+    assert np.all(monitor2.x == 0) and np.all(monitor2.at_turn == 0) and np.all(monitor2.particle_id == 0)
+    particles = particles0.copy()
+    line.track(particles, num_turns=num_turns, turn_by_turn_monitor=monitor2)
+    assert np.all(monitor2.at_turn[3, :] == np.arange(5, 15))
+    assert np.all(monitor2.pzeta[:, 0] == mon.pzeta[:, 5])
+
+    multi = xb.ParticlesMonitor(start_at_turn=5, stop_at_turn=10, n_repetitions=3,
+                                repetition_period=20, num_particles=num_particles)
+    particles = particles0.copy()
+    line.track(particles, num_turns=100, turn_by_turn_monitor=multi)
+    assert multi.x.shape == (3, 50, 5)
+    assert np.all(multi.at_turn[1, 3, :] == np.arange(25, 30))
+    assert np.all(multi.particle_id[2, :, 3] == np.arange(0, num_particles))
+    assert np.all(multi.at_element[:, :, :] == 0)
+    assert np.all(multi.pzeta[0, :, 0] == mon.pzeta[:, 5])
+
+    # monitors installed in the line
+    mon_a = xb.ParticlesMonitor(start_at_turn=5, stop_at_turn=15, num_particles=num_particles)
+    mon_b = xb.ParticlesMonitor(start_at_turn=5, stop_at_turn=15, num_particles=num_particles)
+    els, names = list(line0.elements), list(line0.element_names)
+    ia, ib = 1200, 7000
+    els.insert(ib, mon_b);  names.insert(ib, 'mymon_b')
+    els.insert(ia, mon_a);  names.insert(ia, 'mymon_a')
+    line_w = xb.Line(elements=els, element_names=names)
+    line_w.particle_ref = line0.particle_ref
+    hostsim.build_hostsim_tracker(line_w)
+    particles = particles0.copy()
+    line_w.track(particles, num_turns=20)
+    for mm, nn in ((mon_a, 'mymon_a'), (mon_b, 'mymon_b')):
+        assert mm.x.shape == (50, 10)
+        assert np.all(mm.at_turn[3, :] == np.arange(5, 15))
+        assert np.all(mm.particle_id[:, 3] == np.arange(0, num_particles))
+        assert np.all(mm.at_element[:, :] == line_w.element_names.index(nn))

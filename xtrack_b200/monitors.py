@@ -58,7 +58,7 @@ class ParticlesMonitor(BeamElement):
     def from_dict(cls, dct):
         # particles_monitor.py:113-142
         dct = dict(dct)
-        for kk in ('__class__', 'data', 'n_records'):
+        for kk in ('__class__', 'data', 'n_records', 'auto_to_numpy'):
             dct.pop(kk, None)
         dct.setdefault('start_at_turn', 0)
         ps, pe = dct.pop('part_id_start', None), dct.pop('part_id_end', None)
@@ -69,6 +69,14 @@ class ParticlesMonitor(BeamElement):
         if 'repetition_period' not in dct and dct.get('n_repetitions', None) == 1:
             dct.pop('n_repetitions')
         return cls(**dct)
+
+    def to_dict(self):
+        """Parameters only, no `data` (particles_monitor.py:106-112)."""
+        return {'__class__': 'ParticlesMonitor', 'start_at_turn': self.start_at_turn,
+                'stop_at_turn': self.stop_at_turn, 'part_id_start': self.part_id_start,
+                'part_id_end': self.part_id_end, 'ebe_mode': self.ebe_mode,
+                'n_repetitions': self.n_repetitions, 'repetition_period': self.repetition_period,
+                'n_records': self.n_records, 'auto_to_numpy': True}
 
     # -- storage -------------------------------------------------------------
     def allocate(self, device=None):
