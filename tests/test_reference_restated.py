@@ -192,3 +192,27 @@ def test_particles_monitor_semantics():
         assert np.all(mm.at_turn[3, :] == np.arange(5, 15))
         assert np.all(mm.particle_id[:, 3] == np.arange(0, num_particles))
         assert np.all(mm.at_element[:, :] == line_w.element_names.index(nn))
+
+
+def test_standalone_element_track():
+    """`element.track(particles)` as the reference's tests use it (tests/test_elements.py:
+    497-522: `drift.track(particles)`; base_element.py:455-480): the element's map alone, no
+    turn bookkeeping, no global aperture check, `at_element` untouched unless asked."""
+    import hostsim
+    kw = dict(p0c=25.92e9, x=[1e-3, 0.5], px=[1e-5, 0.3], y=-2e-3, py=-1.5e-5, delta=1e-2, zeta=1.)
+    p = xb.Particles(**kw)
+    drift = xb.Drift(length=10.)
+    drift.track(p, _tracker_class=hostsim.HostSimTracker)
+    rpp = xb.Particles(**kw).get('rpp')
+    np.testing.assert_allclose(p.get('x'), np.array(kw['x']) + np.array(kw['px']) * rpp * 10.,
+                               rtol=1e-14, atol=1e-14)
+    assert np.all(p.get('state') == 1)              # x = 3.5 m: no global aperture check here
+    assert np.all(p.get('at_element') == 0) and np.all(p.get('at_turn') == 0)
+    assert np.all(p.get('s') == 10.)
+    drift.length = 5.
+    drift.track(p, increment_at_element=True, _tracker_class=hostsim.HostSimTracker)
+    assert np.all(p.get('s') == 15.) and np.all(p.get('at_element') == 1)
+    quad = xb.Multipole(knl=[0, 1e-2])
+    px0 = p.get('px').copy()
+    quad.track(p, _tracker_class=hostsim.HostSimTracker)
+    np.testing.assert_allclose(p.get('px'), px0 - 1e-2 * p.get('x'), rtol=1e-14)

@@ -131,6 +131,33 @@ class BeamElement:
         dct.pop('__class__', None)
         return cls(**dct)
 
+    def track(self, particles=None, increment_at_element=False, _tracker_class=None):
+        """Stand-alone tracking of this element (base_element.py:455-480): the element's map on
+        every active particle, no end-of-turn action and -- as in the reference's per-element
+        kernel -- no global aperture check; `at_element` moves only if asked to."""
+        if particles is None:
+            raise RuntimeError('Please provide particles to track!')
+        from .line import Line
+        line = self.__dict__.get('_standalone_line')
+        if line is None:
+            line = Line(elements=[self])
+            line.config['XTRACK_GLOBAL_XY_LIMIT'] = 1e300
+            if type(self).needs_rng or getattr(self, 'radiation_flag', 0):
+                line.config['XTRACK_MULTIPOLE_NO_SYNRAD'] = not bool(getattr(self, 'radiation_flag', 0))
+                line._extra_config['_needs_rng'] = True
+            object.__setattr__(self, '_standalone_line', line)
+        # (re)lower every time: the element's fields may have changed since the last call
+        line.build_tracker(_device=particles.device,
+                           **({'_tracker_class': _tracker_class} if _tracker_class else {}))
+        at_element = particles.get('at_element').copy()
+        state_before = particles.get('state').copy()
+        line.track(particles, ele_start=0, num_elements=1, _force_no_end_turn_actions=True)
+        if not increment_at_element:
+            new = particles.get('at_element').copy()
+            moved = (state_before > 0) & (particles.get('state') > 0)
+            new[moved] = at_element[moved]
+            particles.at_element = new
+
     def get_length(self):
         return float(getattr(self, 'length', 0.0)) if self.isthick_now else 0.0
 
