@@ -155,6 +155,10 @@ int64_t xtb_launch_count(void);
 const char* xtb_last_error_string(void);
 const char* xtb_version(void);
 
+/* Version of the op-stream format this library interprets (csrc/xtb_ops.h
+ * XTB_OPS_ABI_VERSION); the host lowering refuses a library that reports another one. */
+int xtb_ops_abi_version(void);
+
 #ifdef __cplusplus
 }
 #endif

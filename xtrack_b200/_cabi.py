@@ -69,6 +69,17 @@ def load():
     lib.xtb_last_error_string.restype = ct.c_char_p
     lib.xtb_version.restype = ct.c_char_p
     lib.xtb_launch_count.restype = ct.c_int64
+    # a stale library must not interpret a newer op stream (the op set is mirrored by hand
+    # between lowering.py and csrc/xtb_ops.h)
+    from . import lowering
+    try:
+        lib.xtb_ops_abi_version.restype = ct.c_int
+        got = int(lib.xtb_ops_abi_version())
+    except AttributeError:
+        got = None
+    if got != lowering.OPS_ABI_VERSION:
+        raise XtbError(f'{_build.LIB} interprets op-stream format {got}, the host lowering '
+                       f'emits {lowering.OPS_ABI_VERSION}: rebuild with `python -m xtrack_b200.build -f`')
     lib.xtb_lattice_create.argtypes = [ct.c_void_p, ct.c_size_t, ct.c_void_p,
                                        ct.c_void_p, ct.c_size_t, ct.c_void_p, ct.c_size_t,
                                        ct.c_double, ct.c_int, ct.POINTER(ct.c_void_p)]

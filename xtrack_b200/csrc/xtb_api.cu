@@ -15,8 +15,8 @@
 #include "xtb_ops.h"
 #include "xtb_state.cuh"
 
-extern "C" cudaError_t xtb_launch_track_fast(unsigned, const XtbTrackArgs*, cudaStream_t);
-extern "C" cudaError_t xtb_launch_track_exact(unsigned, const XtbTrackArgs*, cudaStream_t);
+extern "C" cudaError_t xtb_launch_track_fast(unsigned, const XtbTrackArgs*, int, int*, cudaStream_t);
+extern "C" cudaError_t xtb_launch_track_exact(unsigned, const XtbTrackArgs*, int, int*, cudaStream_t);
 
 
 static thread_local char g_err[512] = "";
@@ -55,6 +55,7 @@ struct xtb_program {
 
 struct xtb_lattice {
     int device;
+    int n_sm;
     size_t n_elements;
     double line_length;
     xtb_program fused, plain;
@@ -63,7 +64,8 @@ struct xtb_lattice {
 };
 
 extern "C" const char* xtb_last_error_string(void) { return g_err; }
-extern "C" const char* xtb_version(void) { return "xtb200 0.2 (sm_100a)"; }
+extern "C" const char* xtb_version(void) { return "xtb200 0.3 (sm_100a)"; }
+extern "C" int xtb_ops_abi_version(void) { return XTB_OPS_ABI_VERSION; }
 extern "C" int64_t xtb_launch_count(void) { return g_launches.load(); }
 
 // Validates the op stream and cuts it into tiles at addressable element boundaries.
@@ -160,6 +162,7 @@ extern "C" int xtb_lattice_create(const uint64_t* fused_words, size_t n_fused_wo
     int prev = 0;
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&L->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = program_upload(L->plain, plain_words);
     if (e == cudaSuccess && fused_words) e = program_upload(L->fused, fused_words);
     cudaSetDevice(prev);
@@ -279,15 +282,16 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     int prev = 0;
     cudaGetDevice(&prev);
     if (prev != L->device) CUDA_TRY(cudaSetDevice(L->device));
+    int n_launched = 0;
     cudaError_t e = (variant_flags & XTB_VARIANT_EXACT)
-                        ? xtb_launch_track_exact(variant, &a, (cudaStream_t) cuda_stream)
-                        : xtb_launch_track_fast(variant, &a, (cudaStream_t) cuda_stream);
+                        ? xtb_launch_track_exact(variant, &a, L->n_sm, &n_launched, (cudaStream_t) cuda_stream)
+                        : xtb_launch_track_fast(variant, &a, L->n_sm, &n_launched, (cudaStream_t) cuda_stream);
     if (prev != L->device) cudaSetDevice(prev);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "track kernel launch: %s", cudaGetErrorString(e));
         return e == cudaErrorNotSupported ? XTB_E_UNSUPPORTED : XTB_E_CUDA;
     }
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(n_launched);
     return XTB_OK;
 }
 

@@ -94,13 +94,14 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     bool chi_one = true;
 #pragma unroll
     for (int k = 0; k < NPT; ++k) {
-        const int64_t slot = ((int64_t) blockIdx.x * NPT + k) * XTB_THREADS + threadIdx.x;
+        // (the block size is a launch parameter: XTB_THREADS or a smaller power of two)
+        const int64_t slot = a.slot_begin + ((int64_t) blockIdx.x * NPT + k) * blockDim.x + threadIdx.x;
         G[k].p = &a.part;
         G[k].i = (uint32_t) slot;
         G[k].c = &lanes.C[k];
         lanes.slot[k] = (uint32_t) slot;
         live[k] = false;
-        if (slot < a.part.capacity) {
+        if (slot < a.slot_end) {
             // check_is_active (GPU), local_particle_custom_api.h:188
             live[k] = G[k].ldi(F_STATE) > 0;
         }
@@ -125,7 +126,7 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     if (!HEAVY) {
         __shared__ int s_first_tid;
         __shared__ double s_ref_sh;
-        if (threadIdx.x == 0) s_first_tid = XTB_THREADS;
+        if (threadIdx.x == 0) s_first_tid = (int) blockDim.x;
         __syncthreads();
         int first_live = -1;
 #pragma unroll
@@ -229,7 +230,12 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
             }
             if (!resident) {
                 __syncthreads();       // every warp is done with buffer b
-                if (threadIdx.x == 0 && step + XTB_NUM_BUF < total_steps) issue(step + XTB_NUM_BUF);
+                if (threadIdx.x == 0 && step + XTB_NUM_BUF < total_steps) {
+                    // buffer b was read (and, for a range that stops inside the tile, written)
+                    // through the generic proxy; the bulk copy writes it through the async proxy
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(step + XTB_NUM_BUF);
+                }
             }
         }
         eidx = a.num_ele_track;        // (warps that skipped dead tiles did not count)

@@ -46,6 +46,12 @@
 #ifndef XTB_OPS_H
 #define XTB_OPS_H
 
+/* Version of the op-stream format.  Bumped whenever an opcode, a flag or a parameter
+ * layout changes; xtrack_b200/lowering.py carries the same number (OPS_ABI_VERSION) and
+ * _cabi.load() refuses a library whose xtb_ops_abi_version() differs: a stale libxtb200.so
+ * cannot silently interpret a newer program. */
+#define XTB_OPS_ABI_VERSION 3
+
 #define XTB_F_START   0x01u
 #define XTB_F_END     0x02u
 #define XTB_F_GLOBAL  0x04u

@@ -37,6 +37,9 @@ struct XtbTrackArgs {
     int32_t ignore_global, ignore_local, kill_cavity_kick;
     double line_length;
     double global_xy_limit;
+    // particle slots [slot_begin, slot_end) of the caller's SoA handled by this grid (a
+    // track call may be split into several grids, see xtb_kernel_inst.cu::launch)
+    int64_t slot_begin, slot_end;
 };
 
 // Full per-particle state: what the generic / thick-magnet op bodies work on.

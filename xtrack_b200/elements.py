@@ -97,6 +97,40 @@ def _rel_arrays(kwargs):
             np.asarray(ksl_rel, dtype=np.float64))
 
 
+# Every write to an element field bumps this counter; a `Tracker` remembers the value its
+# lattice was lowered at and lowers again when it has moved (in the reference the elements are
+# views into the tracker's buffer, so an edit -- a cavity voltage scan, `el.knl[1] = ...` --
+# takes effect at the next `track()`; here the op stream is a frozen copy of the values).
+_MUTATIONS = [0]
+_UNTRACKED_ATTRS = frozenset(('_data', '_device', '_host', '_standalone_line'))
+
+
+def mutation_count():
+    return _MUTATIONS[0]
+
+
+class _TrackedArray(np.ndarray):
+    """Coefficient array of an element (knl, ksl, ...): item assignment and in-place
+    arithmetic count as element mutations."""
+
+    def __setitem__(self, key, value):
+        _MUTATIONS[0] += 1
+        np.ndarray.__setitem__(self, key, value)
+
+    def _inplace(name):
+        def op(self, other):
+            _MUTATIONS[0] += 1
+            return getattr(np.ndarray, name)(self, other)
+        op.__name__ = name
+        return op
+
+    __iadd__ = _inplace('__iadd__')
+    __isub__ = _inplace('__isub__')
+    __imul__ = _inplace('__imul__')
+    __itruediv__ = _inplace('__itruediv__')
+    del _inplace
+
+
 class BeamElement:
     """Base class: class-level flags have the meaning of base_element.py:410-419."""
     isthick = False              # *static* thickness (drives the global-aperture check)
@@ -105,6 +139,17 @@ class BeamElement:
     has_backtrack = False
     needs_rng = False
     iscollective = False
+
+    # monitors opt out: their parameters reach the kernel at launch / `set_inline_monitors`
+    # time, and `track(turn_by_turn_monitor=True)` creates one per call
+    _mutation_tracked = True
+
+    def __setattr__(self, name, value):
+        if self._mutation_tracked and name not in _UNTRACKED_ATTRS:
+            _MUTATIONS[0] += 1
+            if type(value) is np.ndarray and value.dtype == np.float64:
+                value = value.view(_TrackedArray)
+        object.__setattr__(self, name, value)
 
     def _init_misalign(self, kwargs):
         if self.allow_rot_and_shift:
@@ -329,9 +374,17 @@ class _BendCommon(_Magnet):
     def k0(self):
         return self._k0
 
+    @k0.setter
+    def k0(self, value):
+        self._set_k0(value)
+
     @property
     def k0_from_h(self):
         return bool(self._k0_from_h)
+
+    @k0_from_h.setter
+    def k0_from_h(self, value):
+        self._set_k0_from_h(value)
 
     def _set_k0(self, value):
         # _common.py:660-670
@@ -370,25 +423,28 @@ class Bend(_BendCommon):
         self._init_bend_fields(kwargs)
         self._finish(kwargs)
         for nn, val in props:
-            if nn == 'length':
-                # _common.py:634-643
-                self._length = float(val)
-                self._h = self._angle / self._length if self._length != 0 else 0.0
-                if self._k0_from_h:
-                    self._k0 = self._h
-            elif nn == 'angle':
-                # _common.py:622-628
-                self._angle = float(val)
-                if self._length != 0:
-                    self._h = self._angle / self._length
-                    if self._k0_from_h:
-                        self._k0 = self._h
-            elif nn == 'k0_from_h':
-                self._set_k0_from_h(val)
-            elif nn == 'k0':
-                self._set_k0(val)
+            if nn in ('length', 'angle', 'k0_from_h', 'k0'):
+                setattr(self, nn, val)
             else:
                 setattr(self, nn, _enum(val, EDGE_MODEL, nn))
+
+    def _set_length(self, val):
+        # _common.py:634-643
+        self._length = float(val)
+        self._h = self._angle / self._length if self._length != 0 else 0.0
+        if self._k0_from_h:
+            self._k0 = self._h
+
+    def _set_angle(self, val):
+        # _common.py:622-628
+        self._angle = float(val)
+        if self._length != 0:
+            self._h = self._angle / self._length
+            if self._k0_from_h:
+                self._k0 = self._h
+
+    length = property(lambda self: self._length, _set_length)
+    angle = property(lambda self: self._angle, _set_angle)
 
 
 class RBend(_BendCommon):
@@ -408,30 +464,30 @@ class RBend(_BendCommon):
                  if nn in kwargs]
         self._init_knl_ksl(kwargs)
         self._init_bend_fields(kwargs)
-        self.length_straight = 0.0
+        self._length_straight = 0.0
         self.rbend_model = 0
         self.rbend_compensate_sagitta = int(bool(kwargs.pop('rbend_compensate_sagitta', 1)))
         self.rbend_shift = float(kwargs.pop('rbend_shift', 0.0))
-        self.rbend_angle_diff = 0.0
+        self._rbend_angle_diff = 0.0
         self._finish(kwargs)
         for nn, val in props:
-            if nn == 'length_straight':
-                self.length_straight = float(val)
-                self._update_rbend_h_length_k0()
-            elif nn == 'angle':
-                self._angle = float(val)
-                self._update_rbend_h_length_k0()
-            elif nn == 'rbend_angle_diff':
-                self.rbend_angle_diff = float(val)
-                self._update_rbend_h_length_k0()
-            elif nn == 'k0_from_h':
-                self._set_k0_from_h(val)
-            elif nn == 'k0':
-                self._set_k0(val)
+            if nn in ('length_straight', 'angle', 'rbend_angle_diff', 'k0_from_h', 'k0'):
+                setattr(self, nn, val)
             elif nn == 'rbend_model':
                 self.rbend_model = _enum(val, RBEND_MODEL, nn)
             else:
                 setattr(self, nn, _enum(val, EDGE_MODEL, nn))
+
+    def _set_geometry(name):
+        def setter(self, val):
+            setattr(self, name, float(val))
+            self._update_rbend_h_length_k0()
+        return setter
+
+    length_straight = property(lambda self: self._length_straight, _set_geometry('_length_straight'))
+    rbend_angle_diff = property(lambda self: self._rbend_angle_diff, _set_geometry('_rbend_angle_diff'))
+    angle = property(lambda self: self._angle, _set_geometry('_angle'))
+    del _set_geometry
 
     def _update_rbend_h_length_k0(self):
         # rbend.py:192-213
@@ -514,17 +570,24 @@ class DipoleEdge(BeamElement):
         kwargs.pop('r43', None)
         self._init_misalign(kwargs)
         self._finish(kwargs)
-        self._update_r21_r43()
 
-    def _update_r21_r43(self):
-        # dipole_edge.py:127-134 (numpy scalar math in the reference)
+    def _r21_r43(self):
+        # dipole_edge.py:127-134 (numpy scalar math in the reference); evaluated on access so
+        # that edits of k / e1 / e1_fd / hgap / fint are followed, as the reference's setters do
         corr = np.float64(2.0) * self.k * self.hgap * self.fint
         r21 = self.k * np.tan(self.e1)
         e1_v = self.e1 + self.e1_fd
         temp = corr / np.cos(e1_v) * (np.float64(1) + np.sin(e1_v) * np.sin(e1_v))
         r43 = -self.k * np.tan(e1_v - temp)
-        self.r21 = float(r21)
-        self.r43 = float(r43)
+        return float(r21), float(r43)
+
+    @property
+    def r21(self):
+        return self._r21_r43()[0]
+
+    @property
+    def r43(self):
+        return self._r21_r43()[1]
 
 
 class SRotation(BeamElement):

@@ -60,6 +60,7 @@ class Line:
                             'XS_FLAG_SR_TAPER': False,
                             'XS_FLAG_SR_KICK_SAME_AS_FIRST': False}
         self.tracker = None
+        self._tracker_kwargs = {}
         self.record_last_track = None
         self.time_last_track = None
         self.unsupported_replaced = {}
@@ -70,9 +71,19 @@ class Line:
         """Loads the `elements` / `element_names` / `particle_ref` / `config`
         sections of an xtrack line dictionary.  The xdeps `_var_manager`
         section (deferred expressions) is ignored: element values are taken as
-        stored.  Classes outside the hot-path contract raise, unless
-        `replace_unsupported=True`, in which case they become markers and are
-        counted in `line.unsupported_replaced`."""
+        stored.  Classes outside the hot-path contract raise.  `replace_unsupported`
+        is an ALLOW-LIST of class-name patterns (fnmatch) that may be turned into
+        markers instead -- `True` stands for `('BeamBeam*',)`, the collective
+        beam-beam lenses of xfields that sit in the LHC fixtures as placeholders;
+        what was replaced is counted in `line.unsupported_replaced`.  Anything
+        else outside the contract still raises: physics is never dropped silently."""
+        import fnmatch
+        if replace_unsupported is True:
+            replace_unsupported = ('BeamBeam*',)
+        elif not replace_unsupported:
+            replace_unsupported = ()
+        elif isinstance(replace_unsupported, str):
+            replace_unsupported = (replace_unsupported,)
         if dct.get('__class__', 'Line') != 'Line':
             raise ValueError(f"Expected __class__ to be 'Line', got {dct['__class__']!r}")
         eld = dct['elements']
@@ -91,13 +102,13 @@ class Line:
                 elements[nn] = _el.ELEMENT_CLASSES[cname].from_dict(ed)
             elif cname in _MONITOR_CLASSES:
                 elements[nn] = _MONITOR_CLASSES[cname].from_dict(ed)
-            elif replace_unsupported:
+            elif any(fnmatch.fnmatchcase(cname, pat) for pat in replace_unsupported):
                 replaced[cname] = replaced.get(cname, 0) + 1
                 elements[nn] = _el.Marker()
             else:
                 raise NotImplementedError(
-                    f'element class {cname} ({nn}) is outside the hot-path contract; '
-                    'load with replace_unsupported=True to turn it into a Marker')
+                    f'element class {cname} ({nn}) is outside the hot-path contract '
+                    f'(replace_unsupported allows only {tuple(replace_unsupported)})')
         pref = None
         if dct.get('particle_ref') is not None:
             pref = Particles.from_dict(dct['particle_ref'])
@@ -202,7 +213,7 @@ class Line:
         dev = self.tracker.device if self.tracker is not None else None
         optimize.optimize_for_tracking(self, keep_markers=keep_markers, verbose=verbose)
         if dev is not None and compile and dev.type == 'cuda':
-            self.build_tracker(_device=dev)
+            self.build_tracker(_device=dev, **self._tracker_kwargs)
         return self
 
     def remove_markers(self, inplace=True, keep=None):
@@ -235,6 +246,9 @@ class Line:
         """Lowers the lattice and uploads it to the GPU (replaces
         `Tracker.__init__` + JIT compile, tracker.py:38-147)."""
         from .tracker import Tracker
+        # remembered for the implicit rebuilds (device change, configure_radiation,
+        # optimize_for_tracking): they keep the user's choices
+        self._tracker_kwargs = dict(kwargs)
         tracker_class = kwargs.pop('_tracker_class', Tracker)
         self.tracker = tracker_class(self, device=_device, **kwargs)
         return self.tracker
@@ -302,7 +316,7 @@ class Line:
         if kwargs.get('backtrack', False):
             raise NotImplementedError('backtracking is not part of the contract')
         if self.tracker is None or self.tracker.device != particles.device:
-            self.build_tracker(_device=particles.device)
+            self.build_tracker(_device=particles.device, **self._tracker_kwargs)
         if with_progress:
             return self._track_in_batches(
                 particles, with_progress, ele_start=ele_start, ele_stop=ele_stop,

@@ -27,6 +27,7 @@ import math
 import numpy as np
 
 # ---- opcodes / flags: mirror of csrc/xtb_ops.h ----------------------------
+OPS_ABI_VERSION = 3          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
 F_START, F_END, F_GLOBAL, F_DRIFT = 0x01, 0x02, 0x04, 0x08
 
 # fast set (fused program only): one whole element per op

@@ -20,6 +20,7 @@ from .particles import PER_PARTICLE_VARS, U32_VARS, _TORCH_DTYPE
 
 
 class ParticlesMonitor(BeamElement):
+    _mutation_tracked = False
     allow_rot_and_shift = False
     behaves_like_drift = True
     has_backtrack = True
@@ -117,6 +118,7 @@ class ParticlesMonitor(BeamElement):
 
 
 class LastTurnsMonitor(BeamElement):
+    _mutation_tracked = False
     allow_rot_and_shift = False
     behaves_like_drift = True
 
@@ -186,6 +188,7 @@ class LastTurnsMonitor(BeamElement):
 
 
 class _BeamSlotMonitor(BeamElement):
+    _mutation_tracked = False
     """Common part of BeamPositionMonitor / BeamSizeMonitor: per time slot
     `i = round(sampling_frequency * ((at_turn - start_at_turn) / frev - zeta / beta0 / c0))`
     the count and the sums of x, y (, x^2, y^2) of the particles crossing the monitor
@@ -278,6 +281,7 @@ class BeamSizeMonitor(_BeamSlotMonitor):
 
 
 class BeamProfileMonitor(BeamElement):
+    _mutation_tracked = False
     """Transverse profiles per time sample (xtrack/monitors/beam_profile_monitor.py:20-207,
     beam_profile_monitor.h:15-80): `x_intensity` / `y_intensity` of shape (sample_size, n).
     The counts live on the tracking device as two float64 tensors, like the reference's record."""

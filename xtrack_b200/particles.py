@@ -44,6 +44,15 @@ _TORCH_DTYPE = {np.float64: torch.float64, np.int64: torch.int64,
                 np.uint32: torch.int32}
 
 
+def normalise_device(device):
+    """torch.device with an explicit index for CUDA ('cuda' -> 'cuda:<current>'), so that the
+    devices of particles, trackers and monitors compare equal when they are the same GPU."""
+    device = torch.device(device)
+    if device.type == 'cuda' and device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    return device
+
+
 def _as_array(v, n, dtype):
     if np.isscalar(v) or (hasattr(v, '__len__') and len(v) == 1):
         return np.full(n, np.asarray(v).reshape(-1)[0], dtype=dtype)
@@ -210,7 +219,7 @@ class Particles:
         for nn in U32_VARS:
             h[nn] = arr(nn, 0, np.uint32)
 
-        self._device = torch.device(_device)
+        self._device = normalise_device(_device)
         self._fields = {}
         for nn, dt in PER_PARTICLE_VARS:
             full = np.full(self._capacity, 0 if nn.startswith('_rng') else LAST_INVALID_STATE,
@@ -375,7 +384,7 @@ class Particles:
         are made unique as in the reference (particles.py:1002-1088): an object whose ids
         collide with the ones before it is shifted behind them."""
         first = lst[0]
-        dev = torch.device(_device) if _device is not None else first._device
+        dev = normalise_device(_device) if _device is not None else first._device
         for pp in lst[1:]:
             if pp.q0 != first.q0 or pp.mass0 != first.mass0:
                 raise ValueError('Cannot merge particles with different q0 / mass0')
@@ -409,14 +418,15 @@ class Particles:
         """Move the SoA to `device` (host<->device copy of all 32 fields)."""
         new = object.__new__(Particles)
         new.__dict__.update({k: v for k, v in self.__dict__.items() if k != '_fields'})
-        new.__dict__['_device'] = torch.device(device)
+        device = normalise_device(device)
+        new.__dict__['_device'] = device
         new.__dict__['_fields'] = {nn: tt.to(device) for nn, tt in self._fields.items()}
         return new
 
     def copy(self, _device=None):
         new = object.__new__(Particles)
         new.__dict__.update({k: v for k, v in self.__dict__.items() if k != '_fields'})
-        dev = self._device if _device is None else torch.device(_device)
+        dev = self._device if _device is None else normalise_device(_device)
         new.__dict__['_device'] = dev
         new.__dict__['_fields'] = {nn: tt.detach().clone().to(dev)
                                    for nn, tt in self._fields.items()}

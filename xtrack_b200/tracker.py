@@ -13,19 +13,77 @@ import torch
 
 from . import _cabi
 from . import lowering
+from .elements import mutation_count
 from .monitors import ParticlesMonitor
+from .particles import normalise_device
+
+
+class TurnPlan:
+    """How one `track()` call is cut into kernel launches: `head` elements from `ele_start`
+    (one launch), `full_turns` whole turns (one launch), `tail` elements from the start of
+    the line (one launch)."""
+    __slots__ = ('head', 'full_turns', 'tail', 'head_ends_turn', 'full_turns_end_turn',
+                 'monitor_turns')
+
+    def __repr__(self):
+        return 'TurnPlan(' + ', '.join(f'{k}={getattr(self, k)}' for k in self.__slots__) + ')'
+
+
+def split_turns(n_line, ele_start, *, ele_stop=None, num_elements=None, num_turns=None,
+                skip_end_turn_actions=False):
+    """Launch plan of a `track()` call; same results as the branch tree of the reference
+    (xtrack/tracker.py:1270-1342), expressed on the absolute position `end` = number of
+    elements from the start of turn 0 at which tracking stops."""
+    if num_elements is not None:
+        if num_elements < 0:
+            raise ValueError('num_elements must not be negative')
+        if ele_stop is not None:
+            raise ValueError('Cannot use both num_elements and ele_stop!')
+        if num_turns is not None:
+            raise ValueError('Cannot use both num_elements and num_turns!')
+        end = ele_start + num_elements
+        stops_inside_first_turn = end <= n_line
+        last_is_partial = True            # a remainder of `end` is an unfinished turn
+    else:
+        turns = 1 if num_turns is None else int(num_turns)
+        if turns <= 0:
+            raise ValueError('num_turns must be positive')
+        if ele_stop is None:
+            end = turns * n_line
+        else:
+            if not 0 <= ele_stop <= n_line:
+                raise ValueError('ele_stop outside the line')
+            if ele_stop <= ele_start:
+                turns += 1                # the stop lies in the following turn
+            end = (turns - 1) * n_line + ele_stop
+        stops_inside_first_turn = (turns == 1)
+        last_is_partial = ele_stop is not None
+    plan = TurnPlan()
+    if stops_inside_first_turn:
+        plan.head, plan.full_turns, plan.tail = end - ele_start, 0, 0
+    else:
+        plan.head = n_line - ele_start
+        rest = end - n_line               # elements after the first (partial) turn
+        if last_is_partial and n_line > 0:
+            # the stretch up to `end` of the last turn runs without end-of-turn actions,
+            # even when it happens to cover the whole line (ele_stop == len(line))
+            plan.tail = rest % n_line if num_elements is not None else ele_stop
+            plan.full_turns = (rest - plan.tail) // n_line
+        else:
+            plan.tail = 0
+            plan.full_turns = rest // n_line if n_line > 0 else 0
+    assert plan.head >= 0
+    plan.head_ends_turn = (not skip_end_turn_actions) and (ele_start + plan.head == n_line)
+    plan.full_turns_end_turn = not skip_end_turn_actions
+    plan.monitor_turns = plan.full_turns + (2 if plan.tail > 0 else 1)
+    return plan
 
 
 class Tracker:
 
     def __init__(self, line, device=None, exact_arithmetic=True, compact_every=None, fuse=True):
         self.line = line
-        if device is None:
-            device = 'cuda'
-        device = torch.device(device)
-        if device.type == 'cuda' and device.index is None:
-            device = torch.device('cuda', torch.cuda.current_device())
-        self.device = device
+        self.device = normalise_device('cuda' if device is None else device)
         # exact_arithmetic=True (default): kernel built without FMA contraction, rounds like
         # the reference's CPU build (bit-identical wherever no libm call is involved);
         # False: FMA-contracted build, ~1e-11 relative from the reference after 10 LHC turns.
@@ -42,8 +100,12 @@ class Tracker:
 
     # -- lattice ------------------------------------------------------------
     def _current_config_key(self):
+        # compile-time configuration of the reference kernel + everything the lowered op
+        # stream is a frozen copy of: the element sequence and the element field values
+        # (elements.mutation_count moves with every field write)
         return (not self.line.config.get('XTRACK_MULTIPOLE_NO_SYNRAD', True),
-                bool(self.line.config.get('XTRACK_USE_EXACT_DRIFTS', False)))
+                bool(self.line.config.get('XTRACK_USE_EXACT_DRIFTS', False)),
+                hash(tuple(self.line.element_names)), mutation_count())
 
     def _ensure_lattice(self):
         """One lowered lattice per distinct compile-time config, like the
@@ -51,7 +113,8 @@ class Tracker:
         key = self._current_config_key()
         if self._lattice is not None and key == self._config_key:
             return
-        synrad, exact_drifts = key
+        synrad, exact_drifts = key[:2]
+        self.num_elements = len(self.line.element_names)
         prog = lowering.lower_line(self.line.elements, synrad=synrad, exact_drifts=exact_drifts,
                                    device=self.device)
         fused = prog.finish(fused=True) if self.fuse else (None, None)
@@ -65,7 +128,8 @@ class Tracker:
         if prog.monitors or prog.last_turns_monitors:
             self._lattice.set_inline_monitors(prog.monitors, prog.last_turns_monitors)
         self.program = prog
-        self._config_key = key
+        # (allocating the in-line monitors above may have written element fields)
+        self._config_key = key[:3] + (mutation_count(),)
 
     def _make_lattice(self, fused, plain):
         # the C-ABI handle; raises unless `self.device` is a CUDA device (no CPU fallback)
@@ -81,8 +145,9 @@ class Tracker:
                 particle_id_range=particles.get_active_particle_id_range())
             return 1, monitor
         if isinstance(turn_by_turn_monitor, str) and turn_by_turn_monitor == 'ONE_TURN_EBE':
-            _, monitor = self._get_monitor(particles, True, self.num_elements + 1)
-            monitor.ebe_mode = 1
+            monitor = ParticlesMonitor(
+                _device=particles.device, start_at_turn=0, stop_at_turn=self.num_elements + 1,
+                particle_id_range=particles.get_active_particle_id_range(), ebe_mode=1)
             return 2, monitor
         if isinstance(turn_by_turn_monitor, ParticlesMonitor):
             return (2 if turn_by_turn_monitor.ebe_mode == 1 else 1), turn_by_turn_monitor
@@ -112,58 +177,14 @@ class Tracker:
         assert ele_start >= 0
         assert ele_start <= self.num_elements
 
-        # turn splitting (tracker.py:1270-1333)
-        num_middle_turns = 0
-        num_elements_last_turn = 0
-        if num_elements is not None:
-            assert num_elements >= 0
-            if ele_stop is not None:
-                raise ValueError('Cannot use both num_elements and ele_stop!')
-            if num_turns is not None:
-                raise ValueError('Cannot use both num_elements and num_turns!')
-            if num_elements + ele_start <= self.num_elements:
-                num_elements_first_turn = num_elements
-            else:
-                num_elements_first_turn = self.num_elements - ele_start
-                num_middle_turns, ele_stop = divmod(ele_start + num_elements, self.num_elements)
-                num_elements_last_turn = ele_stop
-                num_middle_turns -= 1
-        else:
-            if num_turns is None:
-                num_turns = 1
-            else:
-                assert num_turns > 0
-            if ele_stop is None:
-                num_elements_first_turn = self.num_elements - ele_start
-                num_middle_turns = num_turns - 1
-            else:
-                if isinstance(ele_stop, str):
-                    ele_stop = line.element_names.index(ele_stop)
-                assert ele_stop >= 0
-                assert ele_stop <= self.num_elements
-                if ele_stop <= ele_start:
-                    num_turns += 1
-                if num_turns == 1:
-                    num_elements_first_turn = ele_stop - ele_start
-                else:
-                    num_elements_first_turn = self.num_elements - ele_start
-                    num_middle_turns = num_turns - 2
-                    num_elements_last_turn = ele_stop
+        if isinstance(ele_stop, str):
+            ele_stop = line.element_names.index(ele_stop)
+        plan = split_turns(self.num_elements, ele_start, ele_stop=ele_stop,
+                           num_elements=num_elements, num_turns=num_turns,
+                           skip_end_turn_actions=(line.skip_end_turn_actions
+                                                  or _force_no_end_turn_actions))
 
-        if line.skip_end_turn_actions or _force_no_end_turn_actions:
-            flag_end_first_turn_actions = False
-            flag_end_middle_turn_actions = False
-        else:
-            flag_end_first_turn_actions = (
-                num_elements_first_turn + ele_start == self.num_elements)
-            flag_end_middle_turn_actions = True
-
-        if num_elements_last_turn > 0:
-            monitor_turns = num_middle_turns + 2
-        else:
-            monitor_turns = num_middle_turns + 1
-
-        flag_monitor, monitor = self._get_monitor(particles, turn_by_turn_monitor, monitor_turns)
+        flag_monitor, monitor = self._get_monitor(particles, turn_by_turn_monitor, plan.monitor_turns)
         if monitor is not None:
             monitor.allocate(self.device)
 
@@ -188,19 +209,14 @@ class Tracker:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(self.device))
 
-        # first turn (tracker.py:1372-1390)
-        assert num_elements_first_turn >= 0
+        # at most three launches, as the reference issues them (tracker.py:1372-1436)
         self._lattice.track(particles, num_turns=1, ele_start=ele_start,
-                            num_ele_track=num_elements_first_turn,
-                            flag_end_turn_actions=flag_end_first_turn_actions, **common)
-        # middle turns (:1393-1413)
-        if num_middle_turns > 0:
-            assert self.num_elements > 0
-            self._track_middle(particles, num_middle_turns, flag_end_middle_turn_actions, common)
-        # last, incomplete turn (:1416-1436)
-        if num_elements_last_turn > 0:
-            self._lattice.track(particles, num_turns=1, ele_start=0,
-                                num_ele_track=num_elements_last_turn,
+                            num_ele_track=plan.head, flag_end_turn_actions=plan.head_ends_turn,
+                            **common)
+        if plan.full_turns > 0:
+            self._track_middle(particles, plan.full_turns, plan.full_turns_end_turn, common)
+        if plan.tail > 0:
+            self._lattice.track(particles, num_turns=1, ele_start=0, num_ele_track=plan.tail,
                                 flag_end_turn_actions=False, **common)
 
         if time:
