@@ -191,7 +191,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='hllhc_da', choices=sorted(WORKLOADS))
-    ap.add_argument('--particles', type=int, default=1_000_000, help='per GPU')
+    ap.add_argument('--particles', type=int, default=1_000_000,
+                    help='per GPU (weak scaling) or in total (--scaling strong)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --particles per GPU; strong: --particles in total, sharded over '
+                         'the GPUs (BASELINE.json configs[1] as quoted: 10^6 particles on 8 GPUs)')
     ap.add_argument('--turns', type=int, default=20, help='turns per step')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -220,9 +224,19 @@ def main():
         os.dup2(2, 1)
 
     fixture, descr = WORKLOADS[args.workload]
-    config = {'workload': f'{args.workload}: {descr}; {args.particles} particles/GPU x '
-                          f'{args.turns} turns/step', 'fixture': fixture,
-              'particles_per_gpu': args.particles, 'turns_per_step': args.turns,
+    if args.scaling == 'strong':
+        # contiguous particle_id blocks, the first ranks take the remainder
+        n_rank = args.particles // world + (1 if rank < args.particles % world else 0)
+        first_id = rank * (args.particles // world) + min(rank, args.particles % world)
+        what = f'{args.particles} particles in total over {world} GPU(s)'
+    else:
+        n_rank, first_id = args.particles, rank * args.particles
+        what = f'{args.particles} particles/GPU'
+    config = {'workload': f'{args.workload}: {descr}; {what} x {args.turns} turns/step',
+              'fixture': fixture, 'scaling': args.scaling,
+              'particles_per_gpu': args.particles if args.scaling == 'weak' else args.particles / world,
+              'particles_total': args.particles * (world if args.scaling == 'weak' else 1),
+              'turns_per_step': args.turns,
               'l2_policy': 'particle SoA (240 B/particle) larger than L2; program streamed per turn',
               'parallelism': f'particles sharded over {world} GPU(s), no per-turn communication'}
 
@@ -231,6 +245,10 @@ def main():
             return
         line = load_line(fixture, RADIATION.get(args.workload))
         config['n_elements'] = len(line)
+        config['replaced_by_markers'] = dict(line.unsupported_replaced)
+        from xtrack_b200 import lowering
+        config['flop_per_pet'] = lowering.lower_line(
+            line.elements, synrad=args.workload in RADIATION).flops / len(line)
         vals = []
         for ii in range(args.warmup + args.steps):
             res, dt, turns = cpu_reference_run(args.workload, line, 20000,
@@ -240,11 +258,13 @@ def main():
         value = float(np.mean([r['value'] for r, _ in vals]))
         res = dict(vals[-1][0])
         res['value'] = value
-        emit(({
+        # `config` is the workload both arms are quoted on; what this arm timed per step is a
+        # bounded sample of it (PET/s is size-normalised), stated in `sample`
+        emit(({'sample': res['sample'],
             'impl': 'reference', 'metric': 'particle-element-turns/s', 'value': value,
             'unit': 'particle-element-turns/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean([d for _, d in vals])),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': config, 'cpu_baseline': res,
             'e2e': {'value': value, 'unit': 'particle-element-turns/s',
                     'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
@@ -265,10 +285,12 @@ def main():
     line = load_line(fixture, RADIATION.get(args.workload))
     n_el = len(line)
     config['n_elements'] = n_el
+    config['replaced_by_markers'] = dict(line.unsupported_replaced)
     ref = line.particle_ref
-    n = args.particles
+    n = n_rank
     ic = initial_conditions(args.workload, line, n, rank)
-    p_host = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0, **ic)
+    p_host = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0,
+                          particle_id=first_id + np.arange(n), **ic)
     tracker = line.build_tracker(_device=dev, exact_arithmetic=not args.fma)
     flop_per_turn = tracker.program.flops          # algorithmic flop per particle-turn
     config['flop_per_pet'] = flop_per_turn / n_el
@@ -471,7 +493,7 @@ def main():
         'metric': 'particle-element-turns/s', 'value': value,
         'unit': 'particle-element-turns/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'config': config, 'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'particle-element-turns/s',
                 'h2d_bytes_per_step': bytes_io, 'd2h_bytes_per_step': bytes_io},
