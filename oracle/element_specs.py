@@ -133,7 +133,42 @@ SPECS = {
                          isthick=False, rot_shift=True),
 }
 
-CLASS_ORDER = sorted(SPECS)           # tracker.py:517-519 sorts classes by name
+# ---- slices (slice_base.py:9-14; slice_elements_{thin,thick,drift,edge}.py): a reference to
+# the parent element + four fields of their own; the generated wrappers read everything else
+# through `XData_get__parent_<field>`
+SLICE_FIELDS = [('radiation_flag', 'i64'), ('delta_taper', 'f64'), ('weight', 'f64'),
+                ('slice_offset', 'f64')]
+
+
+def _snake(parent):
+    return {'RBend': 'rbend'}.get(parent, parent.lower())
+
+
+def _add_slices():
+    for parent in ('Bend', 'RBend', 'Quadrupole', 'Sextupole', 'Octupole', 'Multipole', 'Cavity'):
+        kinds = [('ThinSlice' + parent, f'thin_slice_{_snake(parent)}.h', False, True, True),
+                 ('ThickSlice' + parent, f'thick_slice_{_snake(parent)}.h', True, True, False),
+                 ('DriftSlice' + parent, f'drift_slice_{_snake(parent)}.h', True, False, False)]
+        if parent not in ('Multipole', 'Cavity'):
+            kinds += [('ThinSlice' + parent + 'Entry', f'thin_slice_{_snake(parent)}_entry.h',
+                       False, True, False),
+                      ('ThinSlice' + parent + 'Exit', f'thin_slice_{_snake(parent)}_exit.h',
+                       False, True, False)]
+        for cname, header, thick, from_parent, is_thin in kinds:
+            SPECS[cname] = dict(header=header, fields=list(SLICE_FIELDS), parent=parent,
+                                isthick=thick, rot_shift=False, rot_shift_from_parent=from_parent,
+                                thin_slice=is_thin, curved=SPECS[parent].get('curved', False))
+    SPECS['DriftSlice'] = dict(header='drift_slice.h', fields=list(SLICE_FIELDS), parent='Drift',
+                               isthick=True, rot_shift=False, rot_shift_from_parent=False)
+    SPECS['DriftExactSlice'] = dict(header='drift_exact_slice.h', fields=list(SLICE_FIELDS),
+                                    parent='DriftExact', isthick=True, rot_shift=False,
+                                    rot_shift_from_parent=False)
+
+
+_add_slices()
+
+# parents before their slices in the generated header; ids as tracker.py:517-519 (sorted names)
+CLASS_ORDER = sorted(SPECS, key=lambda nn: ('parent' in SPECS[nn], nn))
 TYPE_ID = {name: ii for ii, name in enumerate(CLASS_ORDER)}
 
 

@@ -101,7 +101,31 @@ def gen_particles_api():
     return '\n'.join(L)
 
 
+def gen_slice_struct(name):
+    """Slice: `_parent` reference + own fields; `XData_get__parent_<f>` forwards to the parent's
+    accessor (what xobjects generates for an `xo.Ref` field)."""
+    spec = SPECS[name]
+    parent = spec['parent']
+    L = [f'/* ---- {name}Data (slice of {parent}) ---- */', f'typedef struct {name}Data_s {{',
+         f'    {parent}Data _parent;']
+    for fn, kind in spec['fields']:
+        L.append(f'    {CTYPE[kind]} {fn};')
+    L.append(f'}} *{name}Data;')
+    for fn, kind in spec['fields']:
+        L.append(f'GPUFUN {CTYPE[kind]} {name}Data_get_{fn}({name}Data el){{ return el->{fn}; }}')
+    for fn, kind in all_fields(parent):
+        if kind == 'arr':
+            L.append(f'GPUFUN double {name}Data_get__parent_{fn}({name}Data el, int64_t i){{ return el->_parent->{fn}[i]; }}')
+            L.append(f'GPUFUN double* {name}Data_getp1__parent_{fn}({name}Data el, int64_t i){{ return el->_parent->{fn} + i; }}')
+            L.append(f'GPUFUN int64_t {name}Data_len__parent_{fn}({name}Data el){{ return el->_parent->{fn}__len; }}')
+        else:
+            L.append(f'GPUFUN {CTYPE[kind]} {name}Data_get__parent_{fn}({name}Data el){{ return el->_parent->{fn}; }}')
+    return '\n'.join(L)
+
+
 def gen_element_struct(name):
+    if 'parent' in SPECS[name]:
+        return gen_slice_struct(name)
     L = [f'/* ---- {name}Data ---- */', f'typedef struct {name}Data_s {{']
     ff = all_fields(name)
     for fn, kind in ff:
@@ -126,10 +150,14 @@ def gen_with_transformations(name):
     """Mirror of base_element.py:83-127."""
     spec = SPECS[name]
     opts = [('ELEMENT_NAME', name)]
-    if spec.get('rot_shift'):
+    if spec.get('rot_shift') or spec.get('rot_shift_from_parent'):
         opts.append(('ALLOW_ROT_AND_SHIFT', 1))
-    if spec.get('curved'):
+    if spec.get('rot_shift_from_parent'):
+        opts.append(('IS_SLICE', 1))
+    if spec.get('curved') and (spec.get('rot_shift_from_parent') or 'parent' not in spec):
         opts.append(('CURVED', 1))
+    if spec.get('thin_slice') and spec.get('curved'):
+        opts.append(('THIN_SLICE_OF_CURVED_ELEMENT', 1))
     if spec.get('dyn_thick'):
         opts.append(('IS_THICK_DYNAMIC', 1))
     elif spec.get('isthick'):

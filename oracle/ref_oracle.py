@@ -92,7 +92,7 @@ _STRUCTS = {}
 
 def _struct_for(name):
     if name not in _STRUCTS:
-        ff = []
+        ff = [('_parent', ct.c_void_p)] if 'parent' in SPECS[name] else []
         for fn, kind in all_fields(name):
             if kind == 'arr':
                 ff += [(fn, ct.POINTER(ct.c_double)), (fn + '__len', ct.c_int64)]
@@ -200,12 +200,15 @@ class RefElements:
         n = len(elements)
         self.ptrs = (ct.c_void_p * n)()
         self.type_ids = (ct.c_int64 * n)()
-        cache = {}
+        self._cache = {}
         for ii, el in enumerate(elements):
-            key = id(el)
-            if key not in cache:
-                cache[key] = self._make(el)
-            self.ptrs[ii], self.type_ids[ii] = cache[key]
+            self.ptrs[ii], self.type_ids[ii] = self._get(el)
+
+    def _get(self, el):
+        key = id(el)
+        if key not in self._cache:
+            self._cache[key] = self._make(el)
+        return self._cache[key]
 
     def _make(self, el):
         name = type(el).__name__
@@ -220,6 +223,10 @@ class RefElements:
         if name not in SPECS:
             raise NotImplementedError(f'oracle: element class {name} not supported')
         st = _struct_for(name)()
+        if 'parent' in SPECS[name]:
+            # (the parent's struct is shared by all its slices, as in the reference's buffer)
+            assert type(el.parent).__name__ == SPECS[name]['parent']
+            st._parent = self._get(el.parent)[0]
         for fn, kind in all_fields(name):
             vv = _attr(el, name, fn)
             if kind == 'arr':

@@ -50,8 +50,69 @@ def slim(name, dd):
     return out
 
 
+def ring_fixtures():
+    """examples/lattice_design/ring.json: a line of `Replica`s of thick elements, whose element
+    dictionary also holds the slices that `cut_at_s` made of every element of the first arc
+    cells (ThickSliceBend / ThinSliceBendEntry / Exit / ThickSliceQuadrupole / ThickSliceSextupole
+    / DriftSlice: `<name>..entry_map`, `<name>..0`, ..., `<name>..exit_map`).
+      ring         the line as stored;
+      ring_sliced  the same line with every element that has a complete set of slices in the
+                   dictionary replaced by them (weights add up to one)."""
+    with open(os.path.join(REF, 'examples/lattice_design/ring.json')) as fid:
+        dd = json.load(fid)
+    els, names = dd['elements'], dd['element_names']
+
+    def closure(used):
+        used = set(used)
+        todo = list(used)
+        while todo:
+            ed = els[todo.pop()]
+            pn = ed.get('parent_name')
+            if pn is not None and pn not in used:
+                used.add(pn)
+                todo.append(pn)
+        return used
+
+    def pack(nn, src):
+        used = closure(nn)
+        return {'__class__': 'Line', 'elements': {k: v for k, v in els.items() if k in used},
+                'element_names': nn, 'particle_ref': dd['particle_ref'], 'source': src}
+
+    out = {'ring': pack(names, 'examples/lattice_design/ring.json')}
+    by_prefix = {}
+    for kk in els:
+        if '..' in kk:
+            by_prefix.setdefault(kk.rsplit('..', 1)[0], []).append(kk)
+    sliced, n_sliced = [], 0
+    for nn in names:
+        parts = by_prefix.get(nn)
+        if not parts:
+            sliced.append(nn)
+            continue
+        body = sorted((kk for kk in parts if kk.rsplit('..', 1)[1].isdigit()),
+                      key=lambda kk: int(kk.rsplit('..', 1)[1]))
+        wsum = sum(els[kk].get('weight', 0.0) for kk in body)
+        if abs(wsum - 1.0) > 1e-9:
+            sliced.append(nn)
+            continue
+        seq = ([nn + '..entry_map'] if nn + '..entry_map' in els else []) + body + (
+            [nn + '..exit_map'] if nn + '..exit_map' in els else [])
+        sliced += seq
+        n_sliced += 1
+    out['ring_sliced'] = pack(sliced, 'examples/lattice_design/ring.json (elements replaced by '
+                                      'their slices from the same file)')
+    out['ring_sliced']['n_elements_sliced'] = n_sliced
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    for name, data in ring_fixtures().items():
+        raw = json.dumps(data, separators=(',', ':')).encode()
+        with open(os.path.join(OUT, name + '.json.gz'), 'wb') as fid:
+            fid.write(gzip.compress(raw, 9, mtime=0))
+        print(name, len(data['element_names']), 'elements', len(raw), '->',
+              os.path.getsize(os.path.join(OUT, name + '.json.gz')))
     for name, rel in SOURCES.items():
         with open(os.path.join(REF, rel)) as fid:
             dd = json.load(fid)

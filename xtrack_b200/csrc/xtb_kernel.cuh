@@ -233,7 +233,9 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
                 if (threadIdx.x == 0 && step + XTB_NUM_BUF < total_steps) {
                     // buffer b was read (and, for a range that stops inside the tile, written)
                     // through the generic proxy; the bulk copy writes it through the async proxy
+#ifndef XTB_NO_PROXY_FENCE
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
                     issue(step + XTB_NUM_BUF);
                 }
             }

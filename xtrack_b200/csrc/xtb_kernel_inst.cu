@@ -27,83 +27,65 @@
 #ifndef XTB_NPT_SYNRAD
 #define XTB_NPT_SYNRAD 1
 #endif
+// small beams: particles per SM below which the thin kernel runs with 1 / 2 particles per thread
+// (0: never; set from the measurements in profiles/r02_history.md)
+#ifndef XTB_NPT1_BELOW
+#define XTB_NPT1_BELOW 0
+#endif
+#ifndef XTB_NPT2_BELOW
+#define XTB_NPT2_BELOW 0
+#endif
 
 // ---- launch shape ------------------------------------------------------------------------
-// A block carries T * NPT particles through all turns, so the unit of scheduling is coarse:
-// B blocks of 128 threads are resident per SM (B * 128 * NPT particles in flight), and a beam
-// of w.f "waves" of them takes ceil(w.f) wave times -- 10^6 particles on 148 SMs are 4.4
-// waves (the last one 40 % full), 125 000 particles (one eighth of the 10^6-particle
-// dynamic-aperture beam on each of 8 GPUs) are 326 blocks for 592 slots: 2 or 3 per SM.
-// The FP64 pipe does not care how many threads feed it, only that all SMs hold EQUAL work:
-//   * the full waves go out as one grid of 128-thread blocks;
-//   * the rest (everything, for a small beam) goes out as a second grid on the same stream
-//     whose block size T in {128, 64, 32} is chosen so that the blocks spread evenly over
-//     the SMs -- T minimises ceil(blocks / n_sm) * T, the largest number of threads any SM
-//     ends up with; all of them are resident at once (registers allow B * 128 / T blocks
-//     per SM, the two tile buffers of a block 13).  It runs as long as its fill, not as
-//     long as a full wave.
-// XTB_LAUNCH_SHAPE=legacy in the environment restores the single 128-thread grid (A/B runs).
-struct XtbGridPlan {
-    int64_t n_main;          // slots in the grid of full waves (0: none)
-    unsigned grid_main;
-    int64_t n_rest;
-    unsigned grid_rest, threads_rest;
-};
-
-static XtbGridPlan plan_grids(const int64_t n, const int npt, const int blocks_per_sm, const int n_sm) {
-    XtbGridPlan g = {0, 0, 0, 0, XTB_THREADS};
-    const int64_t per_block = (int64_t) XTB_THREADS * npt;
-    static const bool legacy = [] {
-        const char* e = getenv("XTB_LAUNCH_SHAPE");
-        return e && !strcmp(e, "legacy");
+// One grid of XTB_THREADS-thread blocks, block b carrying slots [b * T * NPT, (b + 1) * T * NPT).
+// Measured alternatives that LOST (profiles/r02_history.md): full waves + a balanced second
+// grid of smaller blocks for the rest (the hardware scheduler already overlaps the ragged last
+// wave: 10^6 particles = 4.4 waves run within 1.4 % of the 4.0-wave rate), and 32 / 64-thread
+// blocks for small beams (same per-SM work, fewer warps to hide latency with).
+// What a SMALL beam needs is more warps, not smaller blocks: with fewer than ~1500 particles per
+// SM the NPT = 3 kernel leaves the schedulers with 2 warps each; NPT = 1 / 2 spread the same
+// particles over 3x / 1.5x the warps (at the price of one op decode per 1 / 2 particles instead
+// of 3).  `xtb_pick_npt` chooses by particles per SM; XTB_NPT_FORCE overrides (experiments).
+static int xtb_pick_npt(const int64_t n, const int n_sm) {
+    static const int forced = [] {
+        const char* e = getenv("XTB_NPT_FORCE");
+        return e ? atoi(e) : 0;
     }();
-    if (legacy || n_sm <= 0) {
-        g.n_main = n;
-        g.grid_main = (unsigned) ((n + per_block - 1) / per_block);
-        return g;
-    }
-    const int64_t wave = (int64_t) n_sm * blocks_per_sm * per_block;
-    const int64_t full = n / wave;
-    g.n_main = full * wave;
-    g.grid_main = (unsigned) (full * n_sm * blocks_per_sm);
-    g.n_rest = n - g.n_main;
-    if (g.n_rest > 0) {
-        int64_t best = -1;
-        for (unsigned t = XTB_THREADS; t >= 32; t >>= 1) {
-            const int64_t blocks = (g.n_rest + (int64_t) t * npt - 1) / ((int64_t) t * npt);
-            const int64_t resident = min((int64_t) blocks_per_sm * XTB_THREADS / t, (int64_t) 13);
-            if (blocks > resident * n_sm) continue;             // would not fit one wave
-            const int64_t load = ((blocks + n_sm - 1) / n_sm) * t;
-            if (best < 0 || load < best) { best = load;  g.threads_rest = t; }
-        }
-        g.grid_rest = (unsigned) ((g.n_rest + (int64_t) g.threads_rest * npt - 1)
-                                  / ((int64_t) g.threads_rest * npt));
-    }
-    return g;
+    if (forced >= 1 && forced <= 3) return forced;
+    if (n_sm <= 0) return XTB_NPT_THIN;
+    const double per_sm = (double) n / n_sm;
+    if (per_sm < XTB_NPT1_BELOW) return 1;
+    if (per_sm < XTB_NPT2_BELOW) return 2;
+    return XTB_NPT_THIN;
 }
 
 // QUANTUM: the program contains photon-emission (radiation_flag 2) bodies.  Radiation with the
 // deterministic mean model only runs like the other thick kernels (XTB_NPT_HEAVY lanes).
-template <bool HEAVY, bool SYNRAD, bool FRZ, bool BMON = HEAVY, bool QUANTUM = true>
-static cudaError_t launch(const XtbTrackArgs& a0, int n_sm, int* n_launched, cudaStream_t stream) {
-    constexpr int NPT = HEAVY ? ((SYNRAD && QUANTUM) ? XTB_NPT_SYNRAD : XTB_NPT_HEAVY) : XTB_NPT_THIN;
-    constexpr int BPS = HEAVY ? ((SYNRAD && NPT == 1) ? XTB_SYNRAD_BLOCKS_PER_SM : XTB_HEAVY_BLOCKS_PER_SM)
-                              : XTB_THIN_BLOCKS_PER_SM;
-    const XtbGridPlan g = plan_grids(a0.part.capacity, NPT, BPS, n_sm);
+template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool BMON>
+static cudaError_t launch_npt(const XtbTrackArgs& a0, int* n_launched, cudaStream_t stream) {
     XtbTrackArgs a = a0;
-    if (g.grid_main) {
-        a.slot_begin = 0;
-        a.slot_end = g.n_main;
-        xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0), BMON><<<g.grid_main, XTB_THREADS, 0, stream>>>(a);
-        *n_launched += 1;
-    }
-    if (g.grid_rest) {
-        a.slot_begin = g.n_main;
-        a.slot_end = g.n_main + g.n_rest;
-        xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0), BMON><<<g.grid_rest, g.threads_rest, 0, stream>>>(a);
-        *n_launched += 1;
-    }
+    a.slot_begin = 0;
+    a.slot_end = a.part.capacity;
+    const int64_t per_block = (int64_t) XTB_THREADS * NPT;
+    const unsigned grid = (unsigned) ((a.part.capacity + per_block - 1) / per_block);
+    xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0), BMON><<<grid, XTB_THREADS, 0, stream>>>(a);
+    *n_launched += 1;
     return cudaGetLastError();
+}
+
+template <bool HEAVY, bool SYNRAD, bool FRZ, bool BMON = HEAVY, bool QUANTUM = true>
+static cudaError_t launch(const XtbTrackArgs& a, int n_sm, int* n_launched, cudaStream_t stream) {
+    if constexpr (!HEAVY && !FRZ && !BMON) {
+        // the production thin kernel exists for 1, 2 and 3 particles per thread
+        switch (xtb_pick_npt(a.part.capacity, n_sm)) {
+        case 1: return launch_npt<1, false, false, false, false>(a, n_launched, stream);
+        case 2: return launch_npt<2, false, false, false, false>(a, n_launched, stream);
+        default: return launch_npt<XTB_NPT_THIN, false, false, false, false>(a, n_launched, stream);
+        }
+    } else {
+        constexpr int NPT = HEAVY ? ((SYNRAD && QUANTUM) ? XTB_NPT_SYNRAD : XTB_NPT_HEAVY) : XTB_NPT_THIN;
+        return launch_npt<NPT, HEAVY, SYNRAD, FRZ, BMON>(a, n_launched, stream);
+    }
 }
 
 // variant bits: 1 = heavy ops present, 2 = synrad, 4 = freeze longitudinal,

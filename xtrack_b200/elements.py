@@ -416,6 +416,10 @@ class Bend(_BendCommon):
         if kwargs.get('k0_from_h', False) and 'k0' not in kwargs:
             kwargs['k0'] = 'from_h'
             kwargs.pop('k0_from_h')
+        for nn in ('edge_entry_model', 'edge_exit_model'):
+            if '_' + nn in kwargs:          # the xofield's own name, as `to_dict` may store it
+                kwargs.setdefault(nn, kwargs['_' + nn])
+                kwargs.pop('_' + nn)
         props = [(nn, kwargs.pop(nn)) for nn in
                  ('length', 'angle', 'k0_from_h', 'edge_entry_model',
                   'edge_exit_model', 'k0') if nn in kwargs]
@@ -458,6 +462,10 @@ class RBend(_BendCommon):
         if kwargs.get('k0_from_h', False) and 'k0' not in kwargs:
             kwargs['k0'] = 'from_h'
             kwargs.pop('k0_from_h')
+        for nn in ('edge_entry_model', 'edge_exit_model'):
+            if '_' + nn in kwargs:
+                kwargs.setdefault(nn, kwargs['_' + nn])
+                kwargs.pop('_' + nn)
         props = [(nn, kwargs.pop(nn)) for nn in
                  ('length_straight', 'angle', 'k0_from_h', 'edge_entry_model',
                   'edge_exit_model', 'rbend_angle_diff', 'rbend_model', 'k0')
@@ -714,7 +722,113 @@ class _Placeholder(Marker):
         pass
 
 
+class Replica:
+    """base_element.py:619-656: a place in the line that stands for another element (by
+    name); `Line.elements` hands out the element at the end of the chain."""
+
+    def __init__(self, parent_name):
+        self.parent_name = parent_name
+
+    def __repr__(self):
+        return f'Replica(parent_name="{self.parent_name}")'
+
+    def to_dict(self):
+        return {'__class__': 'Replica', 'parent_name': self.parent_name}
+
+    @classmethod
+    def from_dict(cls, dct):
+        return cls(parent_name=dct['parent_name'])
+
+    def resolve(self, element_container, get_name=False):
+        target = self.parent_name
+        visited = {target}
+        while isinstance(element_container[target], Replica):
+            target = element_container[target].parent_name
+            if target in visited:
+                raise RecursionError(f'Resolving replica of `{self.parent_name}` leads to a '
+                                     'circular reference: check the correctness of your line.')
+            visited.add(target)
+        return target if get_name else element_container[target]
+
+
+# ---- slices (beam_elements/slice_base.py:7-14, slice_elements_{thin,thick,drift,edge}.py) ----
+ID_RADIATION_FROM_PARENT = 10
+
+
+class _Slice(BeamElement):
+    """A slice of a thick parent element: holds `weight` (fraction of the parent),
+    `slice_offset`, its own `radiation_flag` (10 = the parent's) and `delta_taper`; every
+    other parameter, the misalignment included, is the parent's (`_parent`, resolved by
+    name when the line is assembled: tracker_data.py:160-172)."""
+    has_backtrack = True
+    allow_rot_and_shift = False          # no fields of its own ...
+    rot_and_shift_from_parent = True     # ... the parent's apply (not for drift slices)
+    _slice_kind = None                   # 'thin' | 'thick' | 'drift' | 'entry' | 'exit'
+    _parent_class = None
+
+    def __init__(self, parent_name=None, _parent=None, weight=0.0, slice_offset=0.0,
+                 radiation_flag=ID_RADIATION_FROM_PARENT, delta_taper=0.0, **kwargs):
+        self.parent_name = parent_name
+        self._parent = _parent
+        self.weight = float(weight)
+        self.slice_offset = float(slice_offset)
+        self.radiation_flag = int(radiation_flag)
+        self.delta_taper = float(delta_taper)
+        self._finish(kwargs)
+
+    @property
+    def parent(self):
+        if self._parent is None:
+            raise RuntimeError(f'{type(self).__name__}: parent `{self.parent_name}` not resolved '
+                               '(slices are resolved when they are part of a Line)')
+        return self._parent
+
+    @property
+    def length(self):
+        if self._slice_kind in ('entry', 'exit') or not self.isthick:
+            return 0.0
+        par = self.parent
+        if (type(par).__name__ == 'RBend' and self._slice_kind == 'drift'
+                and par.rbend_model == 2):
+            # drift_slice_rbend.h: a straight-body drift advances s by the curved length
+            return par.length * self.weight
+        return par.length * self.weight
+
+    @property
+    def has_misalignment(self):
+        return self.rot_and_shift_from_parent and self.parent.has_misalignment
+
+
+def _make_slice_classes():
+    out = {}
+    parents = {'Bend': Bend, 'RBend': RBend, 'Quadrupole': Quadrupole, 'Sextupole': Sextupole,
+               'Octupole': Octupole, 'Multipole': Multipole, 'Cavity': Cavity}
+    for pname, pcls in parents.items():
+        kinds = [('ThinSlice' + pname, 'thin', False, True),
+                 ('ThickSlice' + pname, 'thick', True, True),
+                 ('DriftSlice' + pname, 'drift', True, False)]
+        if pname not in ('Multipole', 'Cavity'):
+            kinds += [('ThinSlice' + pname + 'Entry', 'entry', False, True),
+                      ('ThinSlice' + pname + 'Exit', 'exit', False, True)]
+        for cname, kind, thick, from_parent in kinds:
+            out[cname] = type(cname, (_Slice,), dict(
+                isthick=thick, _slice_kind=kind, _parent_class=pcls,
+                rot_and_shift_from_parent=from_parent,
+                behaves_like_drift=(kind == 'drift'),
+                __doc__=f'{kind} slice of a {pname} (generated wrapper '
+                        f'elements_src/{kind if kind in ("thin", "thick", "drift") else "thin"}'
+                        f'_slice_*.h of the reference)'))
+    for cname, pcls in (('DriftSlice', Drift), ('DriftExactSlice', DriftExact)):
+        out[cname] = type(cname, (_Slice,), dict(
+            isthick=True, _slice_kind='drift', _parent_class=pcls,
+            rot_and_shift_from_parent=False, behaves_like_drift=True))
+    return out
+
+
+SLICE_CLASSES = _make_slice_classes()
+globals().update(SLICE_CLASSES)
+
 ELEMENT_CLASSES = {cls.__name__: cls for cls in (
     Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupole, Octupole, Bend,
     RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation, LimitRect, LimitEllipse,
-    LimitPolygon)}
+    LimitPolygon, *SLICE_CLASSES.values())}

@@ -93,12 +93,24 @@ class Line:
             eld = dict(zip(names, eld))
         replaced = {}
         used = set(names) if names is not None else set(eld)
+        # ... plus what the line refers to by name: parents of slices, targets of replicas
+        todo = [nn for nn in used if 'parent_name' in eld.get(nn, {})]
+        while todo:
+            pn = eld[todo.pop()]['parent_name']
+            if pn not in used:
+                if pn not in eld:
+                    raise KeyError(f'parent element `{pn}` is not in the dictionary')
+                used.add(pn)
+                if 'parent_name' in eld[pn]:
+                    todo.append(pn)
         elements = {}
         for nn, ed in eld.items():
             if nn not in used:
                 continue
             cname = ed['__class__']
-            if cname in _el.ELEMENT_CLASSES:
+            if cname == 'Replica':
+                elements[nn] = _el.Replica.from_dict(ed)
+            elif cname in _el.ELEMENT_CLASSES:
                 elements[nn] = _el.ELEMENT_CLASSES[cname].from_dict(ed)
             elif cname in _MONITOR_CLASSES:
                 elements[nn] = _MONITOR_CLASSES[cname].from_dict(ed)
@@ -114,6 +126,7 @@ class Line:
             pref = Particles.from_dict(dct['particle_ref'])
         self = cls(elements=elements, element_names=names or list(elements),
                    particle_ref=pref)
+        self._resolve_parents()
         self.unsupported_replaced = replaced
         if 'config' in dct:
             for kk in ('XTRACK_MULTIPOLE_NO_SYNRAD', 'XTRACK_GLOBAL_XY_LIMIT'):
@@ -141,7 +154,25 @@ class Line:
     # -- introspection -----------------------------------------------------
     @property
     def elements(self):
-        return tuple(self.element_dict[nn] for nn in self.element_names)
+        """The elements in line order; a `Replica` is followed to the element it stands for
+        (base_element.py:636-653)."""
+        dd = self.element_dict
+        return tuple(ee.resolve(dd) if isinstance(ee, _el.Replica) else ee
+                     for ee in (dd[nn] for nn in self.element_names))
+
+    def _resolve_parents(self):
+        """Slices find their parent element by name (tracker_data.py:160-172)."""
+        dd = self.element_dict
+        for ee in dd.values():
+            if isinstance(ee, _el._Slice) and ee.parent_name is not None:
+                par = dd[ee.parent_name]
+                if isinstance(par, _el.Replica):
+                    par = par.resolve(dd)
+                if not isinstance(par, ee._parent_class):
+                    raise TypeError(f'{type(ee).__name__}: parent `{ee.parent_name}` is a '
+                                    f'{type(par).__name__}')
+                if ee._parent is not par:
+                    ee._parent = par
 
     def __len__(self):
         return len(self.element_names)
@@ -249,6 +280,7 @@ class Line:
         # remembered for the implicit rebuilds (device change, configure_radiation,
         # optimize_for_tracking): they keep the user's choices
         self._tracker_kwargs = dict(kwargs)
+        self._resolve_parents()
         tracker_class = kwargs.pop('_tracker_class', Tracker)
         self.tracker = tracker_class(self, device=_device, **kwargs)
         return self.tracker

@@ -1009,6 +1009,150 @@ def _magnet_common_kwargs(el):
                 radiation_flag=el.radiation_flag, delta_taper=el.delta_taper)
 
 
+_MAGNET_CLASSES = ('Multipole', 'Quadrupole', 'Sextupole', 'Octupole', 'Bend', 'RBend')
+_EDGE_KEYS = ('edge_entry_active', 'edge_exit_active', 'edge_entry_model', 'edge_exit_model',
+              'edge_entry_angle', 'edge_exit_angle', 'edge_entry_angle_fdown',
+              'edge_exit_angle_fdown', 'edge_entry_fint', 'edge_exit_fint', 'edge_entry_hgap',
+              'edge_exit_hgap')
+
+
+def _magnet_call(el):
+    """Arguments of the `track_magnet_particles` call that the element's wrapper header makes
+    (multipole.h:16-75, quadrupole.h:15-75, sextupole.h, octupole.h, bend.h:15-76,
+    rbend.h:15-75), as keywords of `_lower_magnet` (weight excluded)."""
+    name = type(el).__name__
+    if name == 'Multipole':
+        thick = el._isthick_field > 0
+        return dict(length=el.length, **_magnet_common_kwargs(el),
+                    rel_ref_strength=float(el.main_strength),
+                    model=(el.model if thick else -1), default_model=6, default_integrator=3,
+                    h=0., hxl=el.hxl, k0=0., k1=0., k2=0., k3=0., k0s=0., k1s=0., k2s=0., k3s=0.)
+    if name in ('Quadrupole', 'Sextupole', 'Octupole'):
+        kk = dict(k1=0., k2=0., k3=0., k1s=0., k2s=0., k3s=0.)
+        kn, ks = el._main
+        kk[kn], kk[ks] = getattr(el, kn), getattr(el, ks)
+        main = getattr(el, ks) if el.main_is_skew else getattr(el, kn)
+        return dict(length=el.length, **_magnet_common_kwargs(el),
+                    rel_ref_strength=el.length * main, model=el.model,
+                    default_model=4 if name == 'Quadrupole' else 6, default_integrator=3,
+                    h=0., hxl=0., k0=0., k0s=0., **kk,
+                    edge_entry_active=el.edge_entry_active, edge_exit_active=el.edge_exit_active,
+                    edge_entry_model=1, edge_exit_model=1)
+    assert name in ('Bend', 'RBend')
+    extra = {}
+    if name == 'RBend':
+        extra = dict(rbend_model=el.rbend_model,
+                     rbend_compensate_sagitta=el.rbend_compensate_sagitta,
+                     rbend_shift=el.rbend_shift, rbend_angle_diff=el.rbend_angle_diff,
+                     length_straight=el.length_straight)
+    return dict(length=el.length, **_magnet_common_kwargs(el),
+                rel_ref_strength=el.k0 * el.length, model=el.model, default_model=3,
+                default_integrator=2, h=el.h, hxl=0., k0=el.k0, k1=el.k1, k2=el.k2, k3=0.,
+                k0s=0., k1s=0., k2s=0., k3s=0.,
+                edge_entry_active=el.edge_entry_active, edge_exit_active=el.edge_exit_active,
+                edge_entry_model=el.edge_entry_model, edge_exit_model=el.edge_exit_model,
+                edge_entry_angle=el.edge_entry_angle, edge_exit_angle=el.edge_exit_angle,
+                edge_entry_angle_fdown=el.edge_entry_angle_fdown,
+                edge_exit_angle_fdown=el.edge_exit_angle_fdown,
+                edge_entry_fint=el.edge_entry_fint, edge_exit_fint=el.edge_exit_fint,
+                edge_entry_hgap=el.edge_entry_hgap, edge_exit_hgap=el.edge_exit_hgap, **extra)
+
+
+def _cavity_call(el):
+    """Arguments of the `track_rf_particles` call of cavity.h:12-48 (weight excluded)."""
+    return dict(length=el.length, voltage=el.voltage, frequency=el.frequency,
+                harmonic=el.harmonic, lag=el.lag, phase=el.phase,
+                absolute_time=el.absolute_time, order=-1, knl=None, ksl=None, pn=None, ps=None,
+                phase_n=None, phase_s=None, num_kicks=el.num_kicks, model=el.model,
+                default_model=6, integrator=el.integrator, default_integrator=3,
+                lag_taper=el.lag_taper, phase_taper=el.phase_taper)
+
+
+def _lower_slice(prog, el, cfg):
+    """Slices of thick elements (slice_elements_{thin,thick,drift,edge}.py).  Their C wrappers
+    are GENERATED from the parent's wrapper (elements_src/_generate_slice_elements_c_code.py):
+    the parent's call with
+      thick  weight = slice weight, radiation_flag / delta_taper of the slice, edges off;
+      thin   as thick, and kick only: model -1, uniform integrator, one kick;
+      entry  (exit)  body off, the parent's entry (exit) edge only, weight unused;
+      drift  an expanded drift (exact under XTRACK_USE_EXACT_DRIFTS) of weight * length
+             (drift_slice_*.h; the straight-body RBend: exact drift of the straight length and
+             the path-length difference to the curved frame, drift_slice_rbend.h).
+    The misalignment is the parent's, the anchor moved by the slice's offset
+    (track_local_particle_with_transformations.h:99-162)."""
+    par = el.parent
+    pname = type(par).__name__
+    kind = el._slice_kind
+    if kind == 'drift':
+        ll = el.weight * par.length
+        if pname == 'DriftExact':
+            prog.op(OP_DRIFT_EXACT, [ll])
+        elif pname == 'RBend' and par.rbend_model == 2:
+            ls = par.length_straight * el.weight
+            ds_corr = (par.length - par.length_straight) * el.weight
+            prog.op(OP_DRIFT_EXACT, [ls])
+            prog.op(OP_ADD_S_ZETA, [ds_corr])
+        else:
+            model = 2 if cfg.get('exact_drifts') else 1
+            if pname == 'Drift' and not cfg.get('exact_drifts'):
+                model = par.model or 1
+            prog.op(OP_DRIFT if model == 1 else OP_DRIFT_EXACT, [ll])
+        return True
+
+    if pname == 'Cavity':
+        kw = _cavity_call(par)
+        if kind == 'thin':
+            kw.update(num_kicks=1, model=-1, integrator=3)
+
+        def body():
+            _lower_rf(prog, cfg, weight=el.weight, **kw)
+    else:
+        kw = _magnet_call(par)
+        kw.update(radiation_flag=el.radiation_flag, radiation_flag_parent=par.radiation_flag,
+                  delta_taper=el.delta_taper)
+        weight = el.weight
+        if kind in ('thin', 'thick'):
+            for kk in _EDGE_KEYS:
+                if kk in kw:
+                    kw[kk] = 0
+            if kind == 'thin':
+                kw.update(num_multipole_kicks=1, model=-1, integrator=3)
+        else:
+            off = 'edge_exit' if kind == 'entry' else 'edge_entry'
+            for kk in _EDGE_KEYS:
+                if kk in kw and kk.startswith(off):
+                    kw[kk] = 0
+            kw.update(num_multipole_kicks=0, model=0, integrator=0, body_active=0)
+            weight = 0.0
+
+        def body():
+            _lower_magnet(prog, cfg, weight=weight, **kw)
+
+    if not (el.rot_and_shift_from_parent and par.has_misalignment):
+        body()
+        return bool(el.isthick)
+    curved = pname in ('Bend', 'RBend')
+    if kind == 'thin' and curved and (par.rot_x_rad != 0.0 or par.rot_y_rad != 0.0
+                                       or par.rot_s_rad_no_frame != 0.0):
+        # XT_INVALID_THIN_SLICE_TRANSFORM: the element is not tracked, the particle is lost
+        prog.op(OP_SET_STATE, aux=-42)
+        return bool(el.isthick)
+    length = par.length if el.isthick else 0.0
+    args = [par.shift_x, par.shift_y, par.shift_s, par.rot_y_rad, par.rot_x_rad,
+            par.rot_s_rad_no_frame, par.rot_shift_anchor - el.slice_offset, length * el.weight]
+    if curved:
+        cargs = args + [par.angle * el.weight, par.h, par.rot_s_rad]
+        _misalign_entry_curved(prog, *cargs)
+        body()
+        _misalign_exit_curved(prog, *cargs)
+    else:
+        sargs = args + [par.rot_s_rad]
+        _misalign_entry_straight(prog, *sargs)
+        body()
+        _misalign_exit_straight(prog, *sargs)
+    return bool(el.isthick)
+
+
 def lower_element(prog, el, cfg):
     """Appends the ops of one element; returns True if the class is statically
     thick (global aperture check after it, tracker.py:681-689)."""
@@ -1029,69 +1173,21 @@ def lower_element(prog, el, cfg):
         prog.op(OP_DRIFT_EXACT, [el.length])
         return True
 
-    if name == 'Multipole':
-        thick = el._isthick_field > 0
-
-        def body():
-            _lower_magnet(
-                prog, cfg, weight=1., length=el.length, **_magnet_common_kwargs(el),
-                rel_ref_strength=float(el.main_strength),
-                model=(el.model if thick else -1), default_model=6, default_integrator=3,
-                h=0., hxl=el.hxl, k0=0., k1=0., k2=0., k3=0., k0s=0., k1s=0., k2s=0., k3s=0.)
-        _with_transformations(prog, el, body, length=(el.length if thick else 0.0))
-        return False
-
-    if name in ('Quadrupole', 'Sextupole', 'Octupole'):
-        kk = dict(k1=0., k2=0., k3=0., k1s=0., k2s=0., k3s=0.)
-        kn, ks = el._main
-        kk[kn], kk[ks] = getattr(el, kn), getattr(el, ks)
-        main = getattr(el, ks) if el.main_is_skew else getattr(el, kn)
-
-        def body():
-            _lower_magnet(
-                prog, cfg, weight=1., length=el.length, **_magnet_common_kwargs(el),
-                rel_ref_strength=el.length * main, model=el.model,
-                default_model=4 if name == 'Quadrupole' else 6, default_integrator=3,
-                h=0., hxl=0., k0=0., k0s=0., **kk,
-                edge_entry_active=el.edge_entry_active, edge_exit_active=el.edge_exit_active,
-                edge_entry_model=1, edge_exit_model=1)
-        _with_transformations(prog, el, body, length=el.length)
-        return True
-
-    if name in ('Bend', 'RBend'):
-        extra = {}
-        if name == 'RBend':
-            extra = dict(rbend_model=el.rbend_model,
-                         rbend_compensate_sagitta=el.rbend_compensate_sagitta,
-                         rbend_shift=el.rbend_shift, rbend_angle_diff=el.rbend_angle_diff,
-                         length_straight=el.length_straight)
-
-        def body():
-            _lower_magnet(
-                prog, cfg, weight=1., length=el.length, **_magnet_common_kwargs(el),
-                rel_ref_strength=el.k0 * el.length, model=el.model, default_model=3,
-                default_integrator=2, h=el.h, hxl=0., k0=el.k0, k1=el.k1, k2=el.k2, k3=0.,
-                k0s=0., k1s=0., k2s=0., k3s=0.,
-                edge_entry_active=el.edge_entry_active, edge_exit_active=el.edge_exit_active,
-                edge_entry_model=el.edge_entry_model, edge_exit_model=el.edge_exit_model,
-                edge_entry_angle=el.edge_entry_angle, edge_exit_angle=el.edge_exit_angle,
-                edge_entry_angle_fdown=el.edge_entry_angle_fdown,
-                edge_exit_angle_fdown=el.edge_exit_angle_fdown,
-                edge_entry_fint=el.edge_entry_fint, edge_exit_fint=el.edge_exit_fint,
-                edge_entry_hgap=el.edge_entry_hgap, edge_exit_hgap=el.edge_exit_hgap, **extra)
-        _with_transformations(prog, el, body, length=el.length, curved=True)
-        return True
+    if name in _MAGNET_CLASSES:
+        kw = _magnet_call(el)
+        thick_len = el.length if (name != 'Multipole' or el._isthick_field > 0) else 0.0
+        _with_transformations(prog, el, lambda: _lower_magnet(prog, cfg, weight=1., **kw),
+                              length=thick_len, curved=name in ('Bend', 'RBend'))
+        return name != 'Multipole'
 
     if name == 'Cavity':
-        def body():
-            _lower_rf(prog, cfg, weight=1., length=el.length, voltage=el.voltage,
-                      frequency=el.frequency, harmonic=el.harmonic, lag=el.lag, phase=el.phase,
-                      absolute_time=el.absolute_time, order=-1, knl=None, ksl=None, pn=None,
-                      ps=None, phase_n=None, phase_s=None, num_kicks=el.num_kicks,
-                      model=el.model, default_model=6, integrator=el.integrator,
-                      default_integrator=3, lag_taper=el.lag_taper, phase_taper=el.phase_taper)
-        _with_transformations(prog, el, body, length=el.length)
+        kw = _cavity_call(el)
+        _with_transformations(prog, el, lambda: _lower_rf(prog, cfg, weight=1., **kw),
+                              length=el.length)
         return True
+
+    if getattr(el, '_slice_kind', None) is not None:
+        return _lower_slice(prog, el, cfg)
 
     if name == 'RFMultipole':
         def body():
