@@ -164,3 +164,32 @@ def test_particles_device_is_normalised():
     assert normalise_device('cuda:1') == torch.device('cuda', 1)
     if torch.cuda.is_available():
         assert normalise_device('cuda').index is not None
+
+
+@pytest.mark.parametrize('name', ['hllhc_14', 'sps', 'lep', 'clic_dr', 'ring', 'ring_sliced'])
+def test_line_to_dict_round_trip(name, tmp_path):
+    """`Line.to_dict / to_json` (line.py:775, 899) -> `from_dict / from_json`: the reloaded
+    line lowers to the same op stream, word for word; slices find their parents again."""
+    from xtrack_b200 import lowering
+    line = common.load_line(name)
+    if name == 'lep':
+        line.configure_radiation(model='mean')
+    path = tmp_path / (name + '.json.gz')
+    line.to_json(path)
+    line2 = xb.Line.from_json(path, replace_unsupported=True)
+    assert line2.element_names == line.element_names
+    assert line2.config == line.config
+    assert line2._extra_config['_radiation_model'] == line._extra_config['_radiation_model']
+    synrad = name == 'lep'
+    pa = lowering.lower_line(line.elements, synrad=synrad)
+    pb = lowering.lower_line(line2.elements, synrad=synrad)
+    for fused in (False, True):
+        wa, oa = pa.finish(fused=fused)
+        wb, ob = pb.finish(fused=fused)
+        assert np.array_equal(wa, wb) and np.array_equal(oa, ob)
+    for ff in ('p0c', 'beta0', 'gamma0'):
+        assert np.array_equal(line2.particle_ref.get(ff), line.particle_ref.get(ff))
+    assert line2.particle_ref.mass0 == line.particle_ref.mass0
+    line3 = line.copy()
+    assert np.array_equal(lowering.lower_line(line3.elements, synrad=synrad).finish()[0],
+                          pa.finish()[0])

@@ -77,10 +77,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // EXACT only distinguishes the symbols of the two builds of this translation unit
 // (template instantiations are COMDAT: identical names would be merged at link time).
+// resident blocks per SM the register allocation aims at.  Thin kernels with fewer particles
+// per thread (the small-beam variants, xtb_kernel_inst.cu::xtb_pick_npt) need fewer registers
+// and exist to put MORE warps on an SM: 6 blocks (85 registers) at NPT 2, 8 (64) at NPT 1.
+template <int NPT, bool HEAVY, bool SYNRAD>
+constexpr int xtb_blocks_per_sm() {
+    return HEAVY ? ((SYNRAD && NPT == 1) ? XTB_SYNRAD_BLOCKS_PER_SM : XTB_HEAVY_BLOCKS_PER_SM)
+                 : (NPT >= 3 ? XTB_THIN_BLOCKS_PER_SM : (NPT == 2 ? 6 : 8));
+}
+
 template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool EXACT, bool BMON>
-__global__ void __launch_bounds__(XTB_THREADS, HEAVY ? ((SYNRAD && NPT == 1) ? XTB_SYNRAD_BLOCKS_PER_SM
-                                                                               : XTB_HEAVY_BLOCKS_PER_SM)
-                                                      : XTB_THIN_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(XTB_THREADS, xtb_blocks_per_sm<NPT, HEAVY, SYNRAD>())
 xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
     using S = typename std::conditional<HEAVY, PState, PHot>::type;
     __shared__ __align__(128) uint64_t tile[XTB_NUM_BUF][XTB_TILE_BUF_WORDS];

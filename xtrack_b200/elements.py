@@ -176,6 +176,37 @@ class BeamElement:
         dct.pop('__class__', None)
         return cls(**dct)
 
+    # names of the constructor arguments that `to_dict` stores (per class)
+    _dict_fields = ()
+
+    def to_dict(self):
+        """Dictionary form read back by `from_dict` (and by xtrack's own `from_dict`: the keys
+        are the reference's field names, base_element.py `to_dict`).  Misalignment fields are
+        stored when they are set."""
+        out = {'__class__': type(self).__name__}
+        for nn in self._dict_fields:
+            vv = getattr(self, nn)
+            if isinstance(vv, np.ndarray):
+                vv = [float(v) for v in vv]
+            table = self._enum_table(nn)
+            if table is not None:       # enumerations are stored by name, as xtrack does
+                vv = next(kk for kk, ii in table.items() if ii == vv)
+            out[nn] = vv
+        if self.allow_rot_and_shift:
+            for nn in MISALIGN_FIELDS:
+                if getattr(self, nn) != 0.0:
+                    out[nn] = getattr(self, nn)
+        return out
+
+    def _enum_table(self, field):
+        if field == 'model':
+            return getattr(self, '_model_table', None)
+        return {'integrator': INTEGRATOR, 'edge_entry_model': EDGE_MODEL,
+                'edge_exit_model': EDGE_MODEL, 'rbend_model': RBEND_MODEL}.get(field)
+
+    def copy(self):
+        return type(self).from_dict(self.to_dict())
+
     def track(self, particles=None, increment_at_element=False, _tracker_class=None):
         """Stand-alone tracking of this element (base_element.py:455-480): the element's map on
         every active particle, no end-of-turn action and -- as in the reference's per-element
@@ -225,6 +256,8 @@ class Marker(BeamElement):
 
 
 class Drift(BeamElement):
+    _dict_fields = ('length', 'model')
+    _model_table = MODEL_DRIFT
     isthick = True
     allow_rot_and_shift = False
     behaves_like_drift = True
@@ -237,6 +270,7 @@ class Drift(BeamElement):
 
 
 class DriftExact(BeamElement):
+    _dict_fields = ('length',)
     isthick = True
     allow_rot_and_shift = False
     behaves_like_drift = True
@@ -277,7 +311,11 @@ class _Magnet(BeamElement):
 
 
 class Multipole(_Magnet):
-    isthick = False          # dynamic: field `isthick`
+    _dict_fields = ('order', 'knl', 'ksl', 'knl_rel', 'ksl_rel', 'model', 'integrator', 'num_multipole_kicks', 'radiation_flag', 'delta_taper', 'length', 'hxl', 'main_order', 'main_is_skew', 'isthick')
+
+    @property
+    def isthick(self):          # the dynamic `isthick` field (multipole.py:181)
+        return bool(self._isthick_field > 0)
 
     def __init__(self, **kwargs):
         if 'bal' in kwargs:
@@ -322,14 +360,17 @@ class _StraightMagnet(_Magnet):
 
 
 class Quadrupole(_StraightMagnet):
+    _dict_fields = ('order', 'knl', 'ksl', 'knl_rel', 'ksl_rel', 'model', 'integrator', 'num_multipole_kicks', 'radiation_flag', 'delta_taper', 'k1', 'k1s', 'length', 'main_is_skew', 'edge_entry_active', 'edge_exit_active')
     _main = ('k1', 'k1s')
 
 
 class Sextupole(_StraightMagnet):
+    _dict_fields = ('order', 'knl', 'ksl', 'knl_rel', 'ksl_rel', 'model', 'integrator', 'num_multipole_kicks', 'radiation_flag', 'delta_taper', 'k2', 'k2s', 'length', 'main_is_skew', 'edge_entry_active', 'edge_exit_active')
     _main = ('k2', 'k2s')
 
 
 class Octupole(_StraightMagnet):
+    _dict_fields = ('order', 'knl', 'ksl', 'knl_rel', 'ksl_rel', 'model', 'integrator', 'num_multipole_kicks', 'radiation_flag', 'delta_taper', 'k3', 'k3s', 'length', 'main_is_skew', 'edge_entry_active', 'edge_exit_active')
     _main = ('k3', 'k3s')
 
 
@@ -396,6 +437,14 @@ class _BendCommon(_Magnet):
             self._set_k0_from_h(False)
             self._k0 = float(value)
 
+    def to_dict(self):
+        out = super().to_dict()
+        if self._k0_from_h:
+            out['k0_from_h'] = True
+        else:
+            out['k0'] = self._k0
+        return out
+
     def _set_k0_from_h(self, value):
         # _common.py:676-682
         if value:
@@ -406,6 +455,7 @@ class _BendCommon(_Magnet):
 
 
 class Bend(_BendCommon):
+    _dict_fields = ('order', 'knl', 'ksl', 'knl_rel', 'ksl_rel', 'model', 'integrator', 'num_multipole_kicks', 'radiation_flag', 'delta_taper', 'length', 'angle', 'k1', 'k2', 'edge_entry_active', 'edge_exit_active', 'edge_entry_model', 'edge_exit_model', 'edge_entry_angle', 'edge_exit_angle', 'edge_entry_angle_fdown', 'edge_exit_angle_fdown', 'edge_entry_fint', 'edge_exit_fint', 'edge_entry_hgap', 'edge_exit_hgap')
 
     def __init__(self, **kwargs):
         if 'h' in kwargs:
@@ -452,6 +502,7 @@ class Bend(_BendCommon):
 
 
 class RBend(_BendCommon):
+    _dict_fields = ('order', 'knl', 'ksl', 'knl_rel', 'ksl_rel', 'model', 'integrator', 'num_multipole_kicks', 'radiation_flag', 'delta_taper', 'length_straight', 'angle', 'rbend_angle_diff', 'rbend_model', 'rbend_compensate_sagitta', 'rbend_shift', 'k1', 'k2', 'edge_entry_active', 'edge_exit_active', 'edge_entry_model', 'edge_exit_model', 'edge_entry_angle', 'edge_exit_angle', 'edge_entry_angle_fdown', 'edge_exit_angle_fdown', 'edge_entry_fint', 'edge_exit_fint', 'edge_entry_hgap', 'edge_exit_hgap')
 
     def __init__(self, **kwargs):
         if 'h' in kwargs:
@@ -520,6 +571,8 @@ class RBend(_BendCommon):
 
 
 class Cavity(BeamElement):
+    _model_table = MODEL_RF
+    _dict_fields = ('length', 'voltage', 'frequency', 'lag', 'phase', 'harmonic', 'lag_taper', 'phase_taper', 'absolute_time', 'num_kicks', 'model', 'integrator')
     isthick = True
     has_backtrack = True
 
@@ -536,6 +589,7 @@ class Cavity(BeamElement):
 
 
 class RFMultipole(BeamElement):
+    _dict_fields = ('order', 'knl', 'ksl', 'pn', 'ps', 'phase_n', 'phase_s', 'voltage', 'frequency', 'lag', 'phase', 'absolute_time')
     """rf_multipole.py:51-65; constructor `_HasKnlKsl.__init__` with the phase
     arrays (pn/ps in degrees, phase_n/phase_s in radians)."""
     has_backtrack = True
@@ -559,6 +613,8 @@ class RFMultipole(BeamElement):
 
 
 class DipoleEdge(BeamElement):
+    _model_table = {'linear': 0, 'full': 1, 'suppressed': -1}
+    _dict_fields = ('k', 'e1', 'e1_fd', 'hgap', 'fint', 'model', 'side', 'delta_taper')
     has_backtrack = True
 
     def __init__(self, k=None, e1=None, e1_fd=None, hgap=None, fint=None,
@@ -571,7 +627,7 @@ class DipoleEdge(BeamElement):
         self.e1_fd = float(e1_fd or 0.0)
         self.hgap = float(hgap or 0.0)
         self.fint = float(fint or 0.0)
-        self.model = _enum(model, {'linear': 0, 'full': 1, 'suppressed': -1}, 'model')
+        self.model = _enum(model, self._model_table, 'model')
         self.side = _enum(side, {'entry': 0, 'exit': 1}, 'side')
         self.delta_taper = float(kwargs.pop('delta_taper', 0.0))
         kwargs.pop('r21', None)
@@ -599,6 +655,7 @@ class DipoleEdge(BeamElement):
 
 
 class SRotation(BeamElement):
+    _dict_fields = ('cos_z', 'sin_z')
     allow_rot_and_shift = False
     has_backtrack = True
 
@@ -618,6 +675,7 @@ class SRotation(BeamElement):
 
 
 class XYShift(BeamElement):
+    _dict_fields = ('dx', 'dy')
     allow_rot_and_shift = False
     has_backtrack = True
 
@@ -628,6 +686,7 @@ class XYShift(BeamElement):
 
 
 class Translation(BeamElement):
+    _dict_fields = ('shift_x', 'shift_y')
     """beam_elements/translation.py:15-40, elements_src/translation.h:13-26 (supersedes the
     deprecated XYShift)."""
     allow_rot_and_shift = False
@@ -640,6 +699,7 @@ class Translation(BeamElement):
 
 
 class Rotation(BeamElement):
+    _dict_fields = ('rot_s_rad', 'rot_x_rad', 'rot_y_rad', 'seq')
     """beam_elements/rotation.py:14-100, elements_src/rotation.h:13-60: up to three frame
     rotations about x, y, s in the order `seq` (default 'yxs'); zero angles are skipped."""
     allow_rot_and_shift = False
@@ -669,6 +729,7 @@ class Rotation(BeamElement):
 
 
 class LimitRect(BeamElement):
+    _dict_fields = ('min_x', 'max_x', 'min_y', 'max_y')
     has_backtrack = True
 
     def __init__(self, min_x=-UNLIMITED, max_x=UNLIMITED, min_y=-UNLIMITED,
@@ -680,6 +741,7 @@ class LimitRect(BeamElement):
 
 
 class LimitEllipse(BeamElement):
+    _dict_fields = ('a_squ', 'b_squ', 'a_b_squ')
     has_backtrack = True
 
     def __init__(self, a=None, b=None, a_squ=None, b_squ=None, **kwargs):
@@ -701,6 +763,7 @@ class LimitEllipse(BeamElement):
 
 
 class LimitPolygon(BeamElement):
+    _dict_fields = ('x_vertices', 'y_vertices')
     has_backtrack = True
 
     def __init__(self, x_vertices=None, y_vertices=None, **kwargs):
@@ -775,6 +838,8 @@ class _Slice(BeamElement):
         self.radiation_flag = int(radiation_flag)
         self.delta_taper = float(delta_taper)
         self._finish(kwargs)
+
+    _dict_fields = ('parent_name', 'weight', 'slice_offset', 'radiation_flag', 'delta_taper')
 
     @property
     def parent(self):

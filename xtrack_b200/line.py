@@ -129,11 +129,13 @@ class Line:
         self._resolve_parents()
         self.unsupported_replaced = replaced
         if 'config' in dct:
-            for kk in ('XTRACK_MULTIPOLE_NO_SYNRAD', 'XTRACK_GLOBAL_XY_LIMIT'):
+            for kk in ('XTRACK_MULTIPOLE_NO_SYNRAD', 'XTRACK_GLOBAL_XY_LIMIT',
+                       'XTRACK_USE_EXACT_DRIFTS'):
                 if kk in dct['config']:
                     self.config[kk] = dct['config'][kk]
         if '_extra_config' in dct:
-            for kk in ('skip_end_turn_actions', 'reset_s_at_end_turn'):
+            for kk in ('skip_end_turn_actions', 'reset_s_at_end_turn', '_radiation_model',
+                       '_needs_rng'):
                 if kk in dct['_extra_config']:
                     self._extra_config[kk] = dct['_extra_config'][kk]
         return self
@@ -150,6 +152,50 @@ class Line:
         if 'line' in dct and 'elements' not in dct:
             dct = dct['line']
         return cls.from_dict(dct, **kwargs)
+
+    def to_dict(self, include_var_management=False):
+        """line.py:775-838: `elements` (every entry of the element dictionary that the line
+        uses, parents of slices and targets of replicas included), `element_names`,
+        `particle_ref`, `config`, `_extra_config`.  There is no xdeps variable manager here,
+        so nothing else is written."""
+        used = set(self.element_names)
+        todo = list(used)
+        while todo:
+            pn = getattr(self.element_dict[todo.pop()], 'parent_name', None)
+            if pn is not None and pn not in used:
+                used.add(pn)
+                todo.append(pn)
+        out = {'__class__': 'Line',
+               'elements': {nn: ee.to_dict() for nn, ee in self.element_dict.items() if nn in used},
+               'element_names': list(self.element_names),
+               'config': dict(self.config),
+               '_extra_config': dict(self._extra_config)}
+        if self.particle_ref is not None:
+            out['particle_ref'] = self.particle_ref.to_dict()
+        return out
+
+    def to_json(self, path, indent=1, **kwargs):
+        """line.py:899-931 (numpy arrays are written as lists; `.gz` paths are compressed)."""
+        class _Encoder(json.JSONEncoder):
+            def default(self, obj):
+                if isinstance(obj, np.ndarray):
+                    return obj.tolist()
+                if isinstance(obj, np.generic):
+                    return obj.item()
+                return json.JSONEncoder.default(self, obj)
+        dct = self.to_dict(**kwargs)
+        if str(path).endswith('.gz'):
+            import gzip
+            with gzip.open(path, 'wt') as fid:
+                json.dump(dct, fid, cls=_Encoder, indent=indent)
+        else:
+            with open(path, 'w') as fid:
+                json.dump(dct, fid, cls=_Encoder, indent=indent)
+
+    def copy(self):
+        new = Line.from_dict(self.to_dict(), replace_unsupported=True)
+        new.track_flags = dict(self.track_flags)
+        return new
 
     # -- introspection -----------------------------------------------------
     @property

@@ -152,6 +152,12 @@ class LastTurnsMonitor(BeamElement):
             dct['particle_id_range'] = (ps, ps + dct.pop('num_particles'))
         return cls(**dct)
 
+    def to_dict(self):
+        """Parameters only, no `data` (last_turns_monitor.py:18-44)."""
+        return {'__class__': 'LastTurnsMonitor', 'particle_id_start': self.particle_id_start,
+                'num_particles': self.num_particles, 'n_last_turns': self.n_last_turns,
+                'every_n_turns': self.every_n_turns}
+
     def allocate(self, device=None):
         if device is not None:
             self._device = torch.device(device)
