@@ -149,6 +149,13 @@ int xtb_measure_dfma_peak(int device, double seconds, double* flops_out);
 int xtb_selftest_math(int device, int64_t n_samples, uint64_t seed, int exponent_range,
                       uint64_t* mismatches_out);
 
+/* Self-test: the device sin / cos that reproduce the C library's results to the bit
+ * (csrc/xtb_libm.cuh; used for the RF phases of cavities and RF multipoles, whose reference is
+ * glibc's sin / cos) evaluated on `n` HOST arguments; results to host arrays, for the caller to
+ * compare with its libm. */
+int xtb_eval_libm(int device, const double* x_host, int64_t n, double* sin_out_host,
+                  double* cos_out_host);
+
 /* Kernel launches issued by this library since load (bench bookkeeping). */
 int64_t xtb_launch_count(void);
 

@@ -65,6 +65,7 @@ static void run(const XtbTrackArgs& a) {
                 chi_one = chi_one && (P[k].chi == 1.0);
             } else {
                 pstate_benign(P[k]);
+                pcold_benign(lanes.C[k]);
             }
             any_live = any_live || live[k];
         }

@@ -375,3 +375,25 @@ def test_with_progress_batches_equal_one_call(ele_start, ele_stop):
         assert np.array_equal(mon_a.get(ff), mon_b.get(ff)), ff
     with pytest.raises(ValueError):
         line.track(pb, with_progress=True)
+
+
+def test_host_build_of_device_sin_cos_gives_libm_bits():
+    """csrc/xtb_libm.cuh (glibc's sin / cos algorithm restated, FMA placement of the library's
+    x86-64 FMA build) against the installed libm: scripts/glibc/check_libm.c, 2 x 10^6 arguments
+    per branch here (10^9 in the session log, profiles/r02_history.md)."""
+    import os
+    import subprocess
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+    if ' fma ' not in open('/proc/cpuinfo').read():
+        pytest.skip('host without FMA: its libm runs the non-FMA build of sin / cos')
+    exe = os.path.join(root, 'tests', 'hostsim', '_build', 'check_libm')
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(['g++', '-O2', '-mfma', '-ffp-contract=off', '-fopenmp', '-x', 'c++',
+                    os.path.join(root, 'scripts', 'glibc', 'check_libm.c'), '-o', exe, '-lm'],
+                   check=True)
+    out = subprocess.run([exe, '2000000'], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    # the table is what the generator writes (mathematical values + the library's 18 deviations)
+    gen = subprocess.run(['python', os.path.join(root, 'scripts', 'glibc', 'gen_sincostab.py'),
+                          '--check'], capture_output=True, text=True)
+    assert gen.returncode == 0, gen.stdout + gen.stderr

@@ -103,6 +103,7 @@ def load():
     lib.xtb_measure_dfma_peak.argtypes = [ct.c_int, ct.c_double, ct.POINTER(ct.c_double)]
     lib.xtb_selftest_math.argtypes = [ct.c_int, ct.c_int64, ct.c_uint64, ct.c_int,
                                       ct.POINTER(ct.c_uint64)]
+    lib.xtb_eval_libm.argtypes = [ct.c_int, ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p]
     _lib = lib
     return lib
 
@@ -271,6 +272,14 @@ def selftest_math(device=0, n_samples=1 << 28, seed=1, exponent_range=30):
     out = (ct.c_uint64 * 3)()
     _check(load().xtb_selftest_math(int(device), int(n_samples), int(seed), int(exponent_range), out))
     return tuple(int(v) for v in out)
+
+
+def eval_libm(x, device=0):
+    """(sin, cos) of the host array `x` by the device functions of csrc/xtb_libm.cuh."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    ss, cc = np.empty_like(x), np.empty_like(x)
+    _check(load().xtb_eval_libm(int(device), x.ctypes.data, len(x), ss.ctypes.data, cc.ctypes.data))
+    return ss, cc
 
 
 def launch_count():

@@ -892,6 +892,16 @@ __device__ XTB_RUN_TILE_INLINE void xtb_run_tile(const xtb_tile_t tb, XtbLanes<N
         slow_main:
             const int32_t aux = (int32_t) (hw.x >> 32);
             const double* __restrict__ q = reinterpret_cast<const double*>(xtb_tile_ptr(tb, cur + 2));
+            if (((op == XTB_OP_CAVITY && aux != 1) || op == XTB_OP_RFMULT) && a.flag_monitor != 2) {
+                // RF elements: all the lanes of the thread at once (xtb_thin.cuh::cavity_lanes)
+                if (op == XTB_OP_CAVITY) cavity_lanes<NPT, FRZ>(lanes.P, lanes.C, lanes.live, q, a);
+                else rfmult_lanes<NPT, FRZ>(lanes.P, lanes.C, lanes.live, q, aux, a);
+                if (h & (XTB_F_GLOBAL << 8)) global_check();
+                if (h & (XTB_F_END << 8)) lanes.eidx += 1;
+                lanes.off = cur + (h >> 16);
+                skip_prefix = 0;
+                break;
+            }
             for (int k = 0; k < NPT; ++k) {
                 if (!lanes.live[k]) continue;      // these bodies touch the caller's SoA
                 const PSlot Gk{&a.part, lanes.slot[k], &lanes.C[k]};

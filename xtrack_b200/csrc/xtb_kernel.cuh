@@ -119,6 +119,7 @@ xtb_track_kernel(const __grid_constant__ XtbTrackArgs a) {
             chi_one = chi_one && (P[k].chi == 1.0);
         } else {
             pstate_benign(P[k]);
+            pcold_benign(lanes.C[k]);
         }
         any_live = any_live || live[k];
     }

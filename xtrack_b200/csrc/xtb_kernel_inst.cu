@@ -28,12 +28,19 @@
 #define XTB_NPT_SYNRAD 1
 #endif
 // small beams: particles per SM below which the thin kernel runs with 1 / 2 particles per thread
-// (0: never; set from the measurements in profiles/r02_history.md)
+// (measured on hllhc_14 and SPS, 62 500 ... 500 000 particles on 148 SMs, profiles/r02_history.md:
+// NPT 1 wins up to ~310 000 particles per GPU, NPT 2 around 375 000, NPT 3 from 500 000 on)
 #ifndef XTB_NPT1_BELOW
-#define XTB_NPT1_BELOW 0
+#define XTB_NPT1_BELOW 2100
 #endif
 #ifndef XTB_NPT2_BELOW
-#define XTB_NPT2_BELOW 0
+#define XTB_NPT2_BELOW 2900
+#endif
+#ifndef XTB_SMALL_GRID_BLOCKS_PER_SM
+#define XTB_SMALL_GRID_BLOCKS_PER_SM 0      /* 0: always XTB_THREADS */
+#endif
+#ifndef XTB_MIN_THREADS
+#define XTB_MIN_THREADS 64
 #endif
 
 // ---- launch shape ------------------------------------------------------------------------
@@ -59,16 +66,35 @@ static int xtb_pick_npt(const int64_t n, const int n_sm) {
     return XTB_NPT_THIN;
 }
 
+// Block size: XTB_THREADS, halved while the beam is so small that whole blocks are a coarse
+// unit of SM load (fewer than XTB_SMALL_GRID_BLOCKS_PER_SM blocks per SM): 326 blocks on 148
+// SMs leave SMs with 2 and SMs with 3 (ncu: SMs active 82 % of the launch), 652 half-size
+// blocks spread as 4 and 5.  XTB_THREADS_FORCE overrides (experiments).
+static unsigned xtb_pick_threads(const int64_t n, const int npt, const int n_sm) {
+    static const int forced = [] {
+        const char* e = getenv("XTB_THREADS_FORCE");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == 32 || forced == 64 || forced == 128) return (unsigned) forced;
+    unsigned t = XTB_THREADS;
+    if (n_sm <= 0) return t;
+    while (t > XTB_MIN_THREADS
+           && (double) n / ((double) t * npt) < (double) XTB_SMALL_GRID_BLOCKS_PER_SM * n_sm)
+        t >>= 1;
+    return t;
+}
+
 // QUANTUM: the program contains photon-emission (radiation_flag 2) bodies.  Radiation with the
 // deterministic mean model only runs like the other thick kernels (XTB_NPT_HEAVY lanes).
 template <int NPT, bool HEAVY, bool SYNRAD, bool FRZ, bool BMON>
-static cudaError_t launch_npt(const XtbTrackArgs& a0, int* n_launched, cudaStream_t stream) {
+static cudaError_t launch_npt(const XtbTrackArgs& a0, int n_sm, int* n_launched, cudaStream_t stream) {
     XtbTrackArgs a = a0;
     a.slot_begin = 0;
     a.slot_end = a.part.capacity;
-    const int64_t per_block = (int64_t) XTB_THREADS * NPT;
+    const unsigned threads = xtb_pick_threads(a.part.capacity, NPT, n_sm);
+    const int64_t per_block = (int64_t) threads * NPT;
     const unsigned grid = (unsigned) ((a.part.capacity + per_block - 1) / per_block);
-    xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0), BMON><<<grid, XTB_THREADS, 0, stream>>>(a);
+    xtb_track_kernel<NPT, HEAVY, SYNRAD, FRZ, (XTB_EXACT != 0), BMON><<<grid, threads, 0, stream>>>(a);
     *n_launched += 1;
     return cudaGetLastError();
 }
@@ -78,13 +104,13 @@ static cudaError_t launch(const XtbTrackArgs& a, int n_sm, int* n_launched, cuda
     if constexpr (!HEAVY && !FRZ && !BMON) {
         // the production thin kernel exists for 1, 2 and 3 particles per thread
         switch (xtb_pick_npt(a.part.capacity, n_sm)) {
-        case 1: return launch_npt<1, false, false, false, false>(a, n_launched, stream);
-        case 2: return launch_npt<2, false, false, false, false>(a, n_launched, stream);
-        default: return launch_npt<XTB_NPT_THIN, false, false, false, false>(a, n_launched, stream);
+        case 1: return launch_npt<1, false, false, false, false>(a, n_sm, n_launched, stream);
+        case 2: return launch_npt<2, false, false, false, false>(a, n_sm, n_launched, stream);
+        default: return launch_npt<XTB_NPT_THIN, false, false, false, false>(a, n_sm, n_launched, stream);
         }
     } else {
         constexpr int NPT = HEAVY ? ((SYNRAD && QUANTUM) ? XTB_NPT_SYNRAD : XTB_NPT_HEAVY) : XTB_NPT_THIN;
-        return launch_npt<NPT, HEAVY, SYNRAD, FRZ, BMON>(a, n_launched, stream);
+        return launch_npt<NPT, HEAVY, SYNRAD, FRZ, BMON>(a, n_sm, n_launched, stream);
     }
 }
 

@@ -81,6 +81,15 @@ struct PCold {
     uint32_t rng[4];
 };
 
+// cold fields of a lane without a particle: the lane-parallel RF maps compute on every lane
+__device__ __forceinline__ void pcold_benign(PCold& c) {
+    c.beta0 = c.gamma0 = c.p0c = c.charge_ratio = c.rvv = 1.;
+    c.ptau = 0.;
+    c.at_turn0 = 0;
+    c.at_element0 = 0;
+    c.rng_cached = 0;
+}
+
 // Access to one particle slot: the cached cold fields through `c`, everything else in
 // place in the caller's SoA.  The field index is a compile-time constant at every call
 // site, so the selection below folds away.

@@ -90,9 +90,9 @@ __device__ __forceinline__ void trig_of(const TrigTab& tt, const int idx, const 
 #ifdef XTB_COUNT_TRIG_MISS
     xtb_trig_misses++;
 #endif
-    ca = cos(h * s);
-    sa = sin(h * s);
-    sa2 = sin(0.5 * h * s);
+    ca = xtb_cos_glibc(h * s);
+    sa = xtb_sin_glibc(h * s);
+    sa2 = xtb_sin_glibc(0.5 * h * s);
     rca = 1. / ca;
 }
 
@@ -175,8 +175,8 @@ static __device__ __noinline__ void focusing_terms(const double K, const double 
                                                    double& C) {
     if (K > 0.0) {
         const double sqrt_K = sqrt(K);
-        S = sin(sqrt_K * length) / sqrt_K;
-        C = cos(sqrt_K * length);
+        S = xtb_sin_glibc(sqrt_K * length) / sqrt_K;
+        C = xtb_cos_glibc(sqrt_K * length);
     } else if (K < 0.0) {
         const double sqrt_K = sqrt(-K);
         S = sinh(sqrt_K * length) / sqrt_K;
@@ -906,7 +906,7 @@ __device__ __noinline__ void dipole_fringe(PState& P, const PSlot& G, const doub
     const double xp2 = XTB_POW2(xp);
     const double _yp2 = 1. / yp2;
     const double fi0 = atan((xp * _yp2)) - c2 * (1 + xp2 * (1 + yp2)) * _pz;
-    const double co2 = b0 / XTB_POW2(cos(fi0));
+    const double co2 = b0 / XTB_POW2(xtb_cos_glibc(fi0));
     const double co1 = co2 / (1 + XTB_POW2(xp * _yp2)) * _yp2;
     const double co3 = co2 * c2;
     const double fi1 = co1 - co3 * 2 * xp * (1 + yp2) * _pz;
@@ -1004,13 +1004,15 @@ __device__ __noinline__ void mult_fringe(PState& P, const PSlot& G, const double
     if (!FRZ) P.zeta = (t + delta_t) * beta0;
 }
 
-// Wedge_single_particle, track_wedge.h:14-74
+// Wedge_single_particle, track_wedge.h:14-74.  sin_t, cos_t, tan_t: sin / cos / tan of theta, an
+// element constant, from the host (sin and tan are odd to the bit, cos even: the lowering's
+// values of the face angle serve theta = -face_angle).
 template <bool FRZ>
-__device__ __noinline__ void wedge(PState& P, const PSlot& G, const double theta, const double k0) {
+__device__ __noinline__ void wedge(PState& P, const PSlot& G, const double theta, const double k0,
+                                   const double sin_t, const double cos_t, const double tan_t) {
     const double b1 = k0 * P.chi;
     if (fabs(b1) < 10e-10) {
-        const double sin_ = sin(theta), cos_ = cos(theta), tan_ = tan(theta);
-        yrotation<FRZ>(P, G, -sin_, cos_, -tan_);
+        yrotation<FRZ>(P, G, -sin_t, cos_t, -tan_t);
         return;
     }
     const double rvv = P.rvv;
@@ -1018,11 +1020,11 @@ __device__ __noinline__ void wedge(PState& P, const PSlot& G, const double theta
     const double one_plus_delta = P.delta + 1.0;
     const double A = 1.0 / sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(py));
     const double pz = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(px) - XTB_POW2(py));
-    const double new_px = px * cos(theta) + (pz - b1 * x) * sin(theta);
+    const double new_px = px * cos_t + (pz - b1 * x) * sin_t;
     const double new_pz = sqrt(XTB_POW2(one_plus_delta) - XTB_POW2(new_px) - XTB_POW2(py));
-    const double new_x = x * cos(theta)
-        + (x * px * sin(2 * theta) + XTB_POW2(sin(theta)) * (2 * x * pz - b1 * XTB_POW2(x)))
-              / (new_pz + pz * cos(theta) - px * sin(theta));
+    const double new_x = x * cos_t
+        + (x * px * xtb_sin_glibc(2 * theta) + XTB_POW2(sin_t) * (2 * x * pz - b1 * XTB_POW2(x)))
+              / (new_pz + pz * cos_t - px * sin_t);
     const double D = asin(A * px) - asin(A * new_px);
     const double delta_y = py * (theta + D) / b1;
     const double delta_ell = one_plus_delta * (theta + D) / b1;
@@ -1064,9 +1066,9 @@ __device__ __noinline__ void magnet_edge(PState& P, const PSlot& G, const double
             mult_fringe<FRZ>(P, G, knorm, kskew, 3, knl, ksl, nkl - 1, length_eff, is_exit, 1);
             if (should_rotate) quad_wedge(P, -face_angle, knorm[1]);
         }
-        if (should_rotate) wedge<FRZ>(P, G, -face_angle, knorm[0]);
+        if (should_rotate) wedge<FRZ>(P, G, -face_angle, knorm[0], -sin_, cos_, -tan_);
     } else {
-        if (should_rotate) wedge<FRZ>(P, G, -face_angle, knorm[0]);
+        if (should_rotate) wedge<FRZ>(P, G, -face_angle, knorm[0], -sin_, cos_, -tan_);
         if (model == 1) {
             if (should_rotate) quad_wedge(P, -face_angle, knorm[1]);
             mult_fringe<FRZ>(P, G, knorm, kskew, 3, knl, ksl, nkl - 1, length_eff, is_exit, 1);
@@ -1085,9 +1087,9 @@ __device__ __noinline__ void dipole_edge_nonlinear(PState& P, const PSlot& G, co
     if (side == 0) {
         if (sin_ > -99.) yrotation<FRZ>(P, G, -sin_, cos_, -tan_);
         dipole_fringe<FRZ>(P, G, fint, hgap, k);
-        if (sin_ > -99.) wedge<FRZ>(P, G, -e1, k);
+        if (sin_ > -99.) wedge<FRZ>(P, G, -e1, k, -sin_, cos_, -tan_);
     } else if (side == 1) {
-        if (sin_ > -99.) wedge<FRZ>(P, G, -e1, k);
+        if (sin_ > -99.) wedge<FRZ>(P, G, -e1, k, -sin_, cos_, -tan_);
         dipole_fringe<FRZ>(P, G, fint, hgap, -k);
         if (sin_ > -99.) yrotation<FRZ>(P, G, -sin_, cos_, -tan_);
     }

@@ -7,7 +7,10 @@
 // element parameters) is done once by the host lowering (xtrack_b200/lowering.py)
 // with the same IEEE operations, so only per-particle arithmetic remains here.
 #pragma once
+#include <type_traits>
 #include "xtb_state.cuh"
+#include "xtb_libm.cuh"
+#include "xtb_math.cuh"
 
 // 1 + t/2 as the reference writes it (track_drift.h:19).  t/2 is exact, so the fused
 // multiply-add rounds the same real number once: bit-identical, one FP64 instruction less.
@@ -201,8 +204,9 @@ __device__ __forceinline__ void cavity_kick(PState& P, const PSlot& G, const Xtb
     const double q = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
     const double tau = P.zeta / beta0;
     // voltage == 0 (block-uniform): q*0*sin(.) is an exact zero, the sine is not evaluated
+    // (xtb_sin_glibc: the C library's sine to the bit, xtb_libm.cuh)
     const double energy_kick = (voltage == 0.) ? 0. : q * voltage
-        * sin(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
+        * xtb_sin_glibc(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
     if (!a.kill_cavity_kick) {
         add_to_energy<FRZ>(P, G, beta0, energy_kick + 0., 1);
     }
@@ -214,21 +218,21 @@ __device__ __forceinline__ void cavity_kick(PState& P, const PSlot& G, const Xtb
 // non-zero strength (-1: none).  Terms whose strength is a literal zero are exact zeros in
 // the reference (cos * (0 * z)); they, and the sin/cos that only they use, are left out --
 // the branches are on element constants, hence uniform over the block.
-template <bool FRZ>
-__device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const XtbTrackArgs& a,
-                                            const double* __restrict__ q, const int order) {
+// (the transverse kick and the energy change, before they are applied)
+__device__ __forceinline__ void rfmult_terms(const double x, const double y, const double zeta,
+                                             const double beta0, const double p0c, const double qq,
+                                             const double* __restrict__ q, const int order,
+                                             double& dpx, double& dpy, double& delta_energy) {
     const double voltage = q[0], frequency = q[1], lag = q[2], phase = q[3];
     const double* __restrict__ t = q + 5;
     const double phase0 = 0;
-    const double beta0 = G.ld(F_BETA0);
-    const double qq = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
-    const double tau = P.zeta / beta0;
+    const double tau = zeta / beta0;
     const double energy_kick = (voltage == 0.) ? 0. : qq * voltage
-        * sin(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
+        * xtb_sin_glibc(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
 
-    double dpx = 0.0, dpy = 0.0, dptr = 0.0, zre = 1.0, zim = 0.0;
-    const double x = P.x, y = P.y;
-    const double p0c = G.ld(F_P0C);
+    double dptr = 0.0, zre = 1.0, zim = 0.0;
+    dpx = 0.0;
+    dpy = 0.0;
     for (int kk = 0; kk <= order; kk++) {
         const double* __restrict__ e = t + 6 * kk;
         const double bal_n_kk = e[0];
@@ -237,10 +241,10 @@ __device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const Xtb
         const double pn_kk = phase0 + XTB_DEG2RAD * e[2] + e[4] - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau;
         const double ps_kk = phase0 + XTB_DEG2RAD * e[3] + e[5] - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau;
         double cn = 0., cs = 0., sn = 0., ss = 0.;
-        if (has_n) { cn = cos(pn_kk);  sn = sin(pn_kk); }
+        if (has_n) { cn = xtb_cos_glibc(pn_kk);  sn = xtb_sin_glibc(pn_kk); }
         if (has_s) {
             if (has_n && ps_kk == pn_kk) { cs = cn;  ss = sn; }
-            else { cs = cos(ps_kk);  ss = sin(ps_kk); }
+            else { cs = xtb_cos_glibc(ps_kk);  ss = xtb_sin_glibc(ps_kk); }
         }
         if (has_n && has_s) {
             dpx += cn * (bal_n_kk * zre) - cs * (bal_s_kk * zim);
@@ -260,11 +264,104 @@ __device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const Xtb
         else if (has_s) dptr += -(ss * (bal_s_kk * zim));
     }
     const double rf_energy_kick = -qq * ((frequency * (2.0 * XTB_PI / XTB_C_LIGHT) * p0c) * dptr);
+    delta_energy = energy_kick + rf_energy_kick;
+}
+
+template <bool FRZ>
+__device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const XtbTrackArgs& a,
+                                            const double* __restrict__ q, const int order) {
+    const double beta0 = G.ld(F_BETA0);
+    const double qq = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
+    double dpx, dpy, delta_energy;
+    rfmult_terms(P.x, P.y, P.zeta, beta0, G.ld(F_P0C), qq, q, order, dpx, dpy, delta_energy);
     P.px += -P.chi * dpx;
     P.py += P.chi * dpy;
     if (!a.kill_cavity_kick) {
-        add_to_energy<FRZ>(P, G, beta0, energy_kick + rf_energy_kick, 1);
+        add_to_energy<FRZ>(P, G, beta0, delta_energy, 1);
     }
+}
+
+// ---- RF elements on all the particles of a thread at once -------------------------------------
+// A ring has a handful of RF elements per turn, yet they took ~10 % of the thin kernel: each
+// went through the generic out-of-line path once per particle -- full state assembled and
+// taken apart again, a square root, two reciprocals and five divisions with their slow-path
+// guards, one dependency chain at a time.  These work on the thread's N particles together,
+// straight on their hot state and cached cold fields, the energy update (LocalParticle_
+// add_to_energy with pz_only = 1 -> LocalParticle_update_ptau, local_particle_custom_api.h:
+// 196-216, 21-32) written step by step ACROSS the particles with the guard-free IEEE sequences
+// of xtb_math.cuh: N interleaved chains, identical bits.  Only lanes with a real particle are
+// written back (a lane without one keeps its benign state).
+template <int N, bool FRZ, class S>
+__device__ __forceinline__ void add_to_energy_lanes(S (&P)[N], PCold (&C)[N], const bool (&live)[N],
+                                                    const double (&delta_energy)[N]) {
+    if (FRZ) return;
+    double cr[N], chi[N], p0c[N], b0[N], mr[N], t1[N], t2[N], ptau[N], tp[N], u[N], arg[N], irpp[N],
+        rpp[N], den[N], rvv[N], rv0v[N];
+    XTB_LANES { cr[k] = C[k].charge_ratio;  chi[k] = P[k].chi;  p0c[k] = C[k].p0c;  b0[k] = C[k].beta0; }
+    xtb_vdiv<N>(mr, cr, chi);                       // mass_ratio = charge_ratio / chi
+    xtb_vdiv<N>(t1, delta_energy, p0c);             // ptau += delta_energy / p0c / mass_ratio
+    xtb_vdiv<N>(t2, t1, mr);
+    XTB_LANES ptau[k] = C[k].ptau + t2[k];
+    XTB_LANES tp[k] = 2 * ptau[k];
+    xtb_vdiv<N>(u, tp, b0);
+    XTB_LANES arg[k] = ptau[k] * ptau[k] + u[k] + 1;
+    xtb_vsqrt<N>(irpp, arg);                        // irpp = sqrt(ptau^2 + 2 ptau / beta0 + 1)
+    xtb_vrcp<N>(rpp, irpp);
+    XTB_LANES den[k] = 1 + b0[k] * ptau[k];
+    xtb_vdiv<N>(rvv, irpp, den);
+    xtb_vrcp<N>(rv0v, rvv);
+    XTB_LANES {
+        if (live[k]) {
+            P[k].delta = irpp[k] - 1;
+            P[k].rpp = rpp[k];
+            P[k].rv0v = rv0v[k];
+            if constexpr (std::is_same<S, PState>::value) P[k].rvv = rvv[k];
+            C[k].rvv = rvv[k];
+            C[k].ptau = ptau[k];
+        }
+    }
+}
+
+// Cavity (not absolute_time) on the thread's particles: cavity_kick above, lane-parallel
+template <int N, bool FRZ, class S>
+static __device__ __noinline__ void cavity_lanes(S (&P)[N], PCold (&C)[N], const bool (&live)[N],
+                                                 const double* __restrict__ q, const XtbTrackArgs& a) {
+    const double voltage = q[0], harmonic = q[2], lag = q[3], phase = q[4];
+    const double phase0 = 0;
+    double dE[N];
+    XTB_LANES {
+        double frequency = q[1];
+        const double beta0 = C[k].beta0;
+        if (harmonic != 0) {
+            const double t_rev0 = a.line_length / (beta0 * XTB_C_LIGHT);
+            frequency += (harmonic / t_rev0);
+        }
+        const double qk = fabs(a.part.q0) * C[k].charge_ratio;
+        const double tau = P[k].zeta / beta0;
+        const double energy_kick = (voltage == 0.) ? 0. : qk * voltage
+            * xtb_sin_glibc(phase0 + XTB_DEG2RAD * lag + phase - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau);
+        dE[k] = energy_kick + 0.;
+    }
+    if (!a.kill_cavity_kick) add_to_energy_lanes<N, FRZ>(P, C, live, dE);
+}
+
+// RF multipole on the thread's particles: rfmult_kick above, the energy update lane-parallel
+template <int N, bool FRZ, class S>
+static __device__ __noinline__ void rfmult_lanes(S (&P)[N], PCold (&C)[N], const bool (&live)[N],
+                                                 const double* __restrict__ q, const int order,
+                                                 const XtbTrackArgs& a) {
+    double dE[N];
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const double qq = fabs(a.part.q0) * C[k].charge_ratio;
+        double dpx, dpy;
+        rfmult_terms(P[k].x, P[k].y, P[k].zeta, C[k].beta0, C[k].p0c, qq, q, order, dpx, dpy, dE[k]);
+        if (live[k]) {
+            P[k].px += -P[k].chi * dpx;
+            P[k].py += P[k].chi * dpy;
+        }
+    }
+    if (!a.kill_cavity_kick) add_to_energy_lanes<N, FRZ>(P, C, live, dE);
 }
 
 // DipoleEdgeLinear_single_particle, track_dipole_edge_linear.h:30-39
