@@ -46,6 +46,9 @@ extern "C" {
 #define XTB_VARIANT_SYNRAD       2u   /* reference built WITHOUT XTRACK_MULTIPOLE_NO_SYNRAD      */
 #define XTB_VARIANT_FREEZE_LONG  4u   /* FREEZE_VAR_{zeta,delta,ptau,rpp,rvv,s} (line.py:4446)   */
 #define XTB_VARIANT_PLAIN_PROGRAM 8u  /* force the unfused program (diagnostics / tests)         */
+#define XTB_VARIANT_PHILOX      16u   /* _rng_s1..4 hold key + draw counter of Philox4x32-10     */
+                                      /* (production generator) instead of the reference's       */
+                                      /* Tausworthe / LCG state (rng_src/base_rng.h:23-31)       */
 
 /* track flags: bit positions of xtrack/track_flags.py:5-12 */
 #define XTB_FLAG_BACKTRACK              0
@@ -155,6 +158,11 @@ int xtb_selftest_math(int device, int64_t n_samples, uint64_t seed, int exponent
  * compare with its libm. */
 int xtb_eval_libm(int device, const double* x_host, int64_t n, double* sin_out_host,
                   double* cos_out_host);
+
+/* Self-test: `n` blocks of Philox4x32-10 (counter = c0 + i, c1, 0, 0; key k0, k1) evaluated on
+ * the device into the host array out[4 n] (known-answer and cross-implementation tests). */
+int xtb_eval_philox(int device, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, int64_t n,
+                    uint32_t* out_host);
 
 /* Kernel launches issued by this library since load (bench bookkeeping). */
 int64_t xtb_launch_count(void);

@@ -113,6 +113,13 @@ static void run(const XtbTrackArgs& a) {
     }
 }
 
+// (test hook) one block of the counter-based generator, as the device code computes it
+extern "C" void xtb_hostsim_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t* out) {
+    uint32_t b[4];
+    philox4x32_10(k0, k1, c0, c1, b);
+    for (int j = 0; j < 4; ++j) out[j] = b[j];
+}
+
 extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_offset,
                                   const xtb_particles_t* p, int64_t num_turns, int32_t ele_start,
                                   int32_t num_ele_track, int32_t flag_end_turn_actions,
@@ -151,6 +158,7 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
     a.ignore_global = (int32_t) ((track_flags >> XTB_FLAG_IGNORE_GLOBAL_APERTURE) & 1);
     a.ignore_local = (int32_t) ((track_flags >> XTB_FLAG_IGNORE_LOCAL_APERTURE) & 1);
     a.kill_cavity_kick = (int32_t) ((track_flags >> XTB_FLAG_KILL_CAVITY_KICK) & 1);
+    a.rng_philox = (variant & XTB_VARIANT_PHILOX) ? 1 : 0;
     a.line_length = line_length;
     a.global_xy_limit = global_xy_limit;
     const bool synrad = variant & XTB_VARIANT_SYNRAD, frz = variant & XTB_VARIANT_FREEZE_LONG;

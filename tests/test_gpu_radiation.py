@@ -175,3 +175,41 @@ def test_last_turns_monitor_golden():
                                                for n in (2, 4, 6, 9)]))
     assert np.all(monitor.x == np.array([[0, 0, 2, 1, 0], [3, 5, 7, 9, 11], [0, -2, -4, -6, -8],
                                          [20, 23, 26, 29, 32]]))
+
+
+@pytest.mark.parametrize('mode', ['tausworthe', 'philox'])
+def test_clic_dr_quantum_moments_vs_reference_run(mode):
+    """BASELINE.json north star: "radiation runs match emittances statistically".  512 electrons,
+    300 turns of the CLIC-DR stand-in under quantum radiation, beam started at the synchronous
+    phase (tests/golden/make_radiation_golden.py: the same run by the REFERENCE's C code, its
+    moments committed as tests/golden/clic_dr_quantum_stats.json) -- the energy spread is rebuilt
+    by the quantum excitation while the betatron amplitudes damp.  Both generators must
+    reproduce the reference's beam sizes within 10 % (the statistical error of a standard
+    deviation of 512 particles is 3 %) and its centroid within 5 standard errors."""
+    import json
+    import os
+    with open(os.path.join(common.HERE, 'golden', 'clic_dr_quantum_stats.json')) as fid:
+        gold = json.load(fid)
+    n = gold['n_particles']
+    line = common.load_line('clic_dr')
+    line.configure_radiation(model='quantum')
+    p_host = common.gaussian_particles(line, n, gold['seed'], common.SIGMAS['clic_dr'])
+    p_host.zeta = p_host.get('zeta') + gold['zeta_offset']
+    p = p_host.copy(_device='cuda:0')
+    p._init_random_number_generator(seeds=np.arange(1, n + 1, dtype=np.uint32), mode=mode)
+    line.build_tracker(_device='cuda:0', exact_arithmetic=True)
+    done = 0
+    for tt in sorted(int(k) for k in gold['turns']):
+        line.track(p, num_turns=tt - done)
+        done = tt
+        gg = gold['turns'][str(tt)]
+        st = p.get('state')
+        alive = st > 0
+        assert alive.sum() == gg['n_alive']
+        for ff in ('x', 'px', 'y', 'py', 'zeta', 'delta'):
+            vv = p.get(ff)[alive]
+            assert abs(vv.std() / gg['std'][ff] - 1) < 0.10, (mode, tt, ff, vv.std(), gg['std'][ff])
+            err = gg['std'][ff] / np.sqrt(n)
+            assert abs(vv.mean() - gg['mean'][ff]) < 5 * np.sqrt(2) * err, (mode, tt, ff)
+        print(mode, tt, 'sigma_delta %.4e (ref %.4e) sigma_x %.4e (ref %.4e)' % (
+            p.get('delta')[alive].std(), gg['std']['delta'], p.get('x')[alive].std(), gg['std']['x']))

@@ -18,6 +18,7 @@ VARIANT_EXACT = 1
 VARIANT_SYNRAD = 2
 VARIANT_FREEZE_LONG = 4
 VARIANT_PLAIN_PROGRAM = 8
+VARIANT_PHILOX = 16
 
 
 class XtbParticles(ct.Structure):
@@ -103,6 +104,8 @@ def load():
     lib.xtb_measure_dfma_peak.argtypes = [ct.c_int, ct.c_double, ct.POINTER(ct.c_double)]
     lib.xtb_selftest_math.argtypes = [ct.c_int, ct.c_int64, ct.c_uint64, ct.c_int,
                                       ct.POINTER(ct.c_uint64)]
+    lib.xtb_eval_philox.argtypes = [ct.c_int, ct.c_uint32, ct.c_uint32, ct.c_uint32, ct.c_uint32,
+                                    ct.c_int64, ct.c_void_p]
     lib.xtb_eval_libm.argtypes = [ct.c_int, ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p]
     _lib = lib
     return lib
@@ -272,6 +275,14 @@ def selftest_math(device=0, n_samples=1 << 28, seed=1, exponent_range=30):
     out = (ct.c_uint64 * 3)()
     _check(load().xtb_selftest_math(int(device), int(n_samples), int(seed), int(exponent_range), out))
     return tuple(int(v) for v in out)
+
+
+def eval_philox(k0, k1, c0, c1, n, device=0):
+    """n blocks of Philox4x32-10 from the device: counter (c0 + i, c1, 0, 0), key (k0, k1)."""
+    out = np.empty((n, 4), dtype=np.uint32)
+    _check(load().xtb_eval_philox(int(device), int(k0), int(k1), int(c0), int(c1), int(n),
+                                  out.ctypes.data))
+    return out
 
 
 def eval_libm(x, device=0):

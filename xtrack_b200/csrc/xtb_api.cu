@@ -15,6 +15,7 @@
 #include "xtb_libm.cuh"
 #include "xtb_ops.h"
 #include "xtb_state.cuh"
+#include "xtb_rng.cuh"
 
 extern "C" cudaError_t xtb_launch_track_fast(unsigned, const XtbTrackArgs*, int, int*, cudaStream_t);
 extern "C" cudaError_t xtb_launch_track_exact(unsigned, const XtbTrackArgs*, int, int*, cudaStream_t);
@@ -270,6 +271,7 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     a.ignore_global = (int32_t) ((track_flags >> XTB_FLAG_IGNORE_GLOBAL_APERTURE) & 1);
     a.ignore_local = (int32_t) ((track_flags >> XTB_FLAG_IGNORE_LOCAL_APERTURE) & 1);
     a.kill_cavity_kick = (int32_t) ((track_flags >> XTB_FLAG_KILL_CAVITY_KICK) & 1);
+    a.rng_philox = (variant_flags & XTB_VARIANT_PHILOX) ? 1 : 0;
     a.line_length = L->line_length;
     a.global_xy_limit = global_xy_limit;
 
@@ -667,6 +669,34 @@ extern "C" int xtb_eval_libm(int device, const double* x_host, int64_t n, double
     cudaFree(d);
     cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(XTB_E_CUDA, "libm self-test: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return XTB_OK;
+}
+
+// ---- self-test of the counter-based generator (xtb_thick.cuh::philox4x32_10) ------------------
+__global__ void xtb_eval_philox_kernel(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, int64_t n,
+                                       uint32_t* __restrict__ out) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t b[4];
+    philox4x32_10(k0, k1, c0 + (uint32_t) i, c1, b);
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = b[j];
+}
+
+extern "C" int xtb_eval_philox(int device, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, int64_t n,
+                               uint32_t* out_host) {
+    if (!out_host || n <= 0) return fail(XTB_E_INVALID, "bad argument");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(device));
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t) n * 4 * sizeof(uint32_t)));
+    xtb_eval_philox_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(k0, k1, c0, c1, n, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d, (size_t) n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(XTB_E_CUDA, "philox self-test: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1);
     return XTB_OK;
 }

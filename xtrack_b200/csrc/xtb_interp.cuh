@@ -769,6 +769,37 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
 #pragma unroll
             for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(T[k], len);
             end_thick();
+        } else if ((op & ~(uint32_t) XTB_OPBIT_DRIFT) < XTB_NUM_FAST && !ebe_monitor
+                   && (op & ~(uint32_t) XTB_OPBIT_DRIFT) != XTB_OP_RECT
+                   && (op & ~(uint32_t) XTB_OPBIT_DRIFT) != XTB_OP_ELLIPSE) {
+            // the thin fast ops between the bodies (dipole edges, markers, thin correctors ...):
+            // a radiating thin ring (CLIC-DR: drift, edge, wiggler pole, edge, drift ...) went
+            // back to xtb_run_fast for every one of them -- two round trips of the lanes through
+            // thread-local memory per pole.  Same arithmetic as the handlers of xtb_run_fast.
+            if (op & XTB_OPBIT_DRIFT) {
+#pragma unroll
+                for (int k = 0; k < NPT; ++k) drift_expanded<FRZ>(T[k], L);
+                end_thick();
+            }
+            const uint32_t fop = op & ~(uint32_t) XTB_OPBIT_DRIFT;
+            const double* __restrict__ c = reinterpret_cast<const double*>(xtb_tile_ptr(tb, off + 2));
+            const uint32_t order = (uint32_t) (hw.x >> 32);
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                switch (fop) {
+                case XTB_OP_MULT0: { const double cc[2] = {c[0], c[1]};  mult_kick_c<0, false>(T[k], cc);  break; }
+                case XTB_OP_MULT1: { const double cc[4] = {c[0], c[1], c[2], c[3]};  mult_kick_c<1, false>(T[k], cc);  break; }
+                case XTB_OP_MULTN: mult_kick(T[k], c, (int) order);  break;
+                case XTB_OP_MULTPN: mult_kick_pn<false>(T[k], c[0], order);  break;
+                case XTB_OP_MULTP1: mult_kick_p1<false>(T[k], c[0]);  break;
+                case XTB_OP_MULTH0: mult_kick_h0<FRZ, false>(T[k], c[0], c[1], c[2], c[3]);  break;
+                case XTB_OP_MULTH0N: mult_kick_h0n<FRZ, false>(T[k], c[0], c[1], c[2]);  break;
+                case XTB_OP_MULTH1N: mult_kick_h1n<FRZ, false>(T[k], c[0], c[1], c[2], c[3], c[4]);  break;
+                case XTB_OP_EDGE: edge_linear_c<false>(T[k], c[0], c[1]);  break;
+                default: break;      // XTB_OP_NOP
+                }
+            }
+            eidx += 1;               // (these ops cannot lose a particle)
         } else {
             break;
         }

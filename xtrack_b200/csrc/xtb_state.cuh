@@ -35,6 +35,7 @@ struct XtbTrackArgs {
     uint32_t num_ele_track;          // elements per pass
     int32_t flag_end_turn_actions, flag_reset_s, flag_monitor;
     int32_t ignore_global, ignore_local, kill_cavity_kick;
+    int32_t rng_philox;          // the particles' generator state is (key, counter) of Philox4x32-10
     double line_length;
     double global_xy_limit;
     // particle slots [slot_begin, slot_end) of the caller's SoA handled by this grid (a

@@ -16,6 +16,7 @@
 #include "xtb_state.cuh"
 #include "xtb_thin.cuh"
 #include "xtb_math.cuh"
+#include "xtb_rng.cuh"
 
 #define XTB_QELEM 1.60217662e-19
 #define XTB_EPSILON_0 8.854187817620e-12
@@ -480,33 +481,36 @@ __device__ __forceinline__ void magnet_kick_n(PState (&P)[N], const BodyPar& b, 
 }
 
 // ------------------------------------------------------------- radiation ----
-// rng_get_int32 / rng_get, rng_src/base_rng.h:23-42 (state in the SoA, as in the reference)
-struct Rng {
-    uint32_t s1, s2, s3, s4;
-};
-#define XTB_TAUSW(s, a, b, c, d) ((((s) & (c)) << (d)) ^ ((((s) << (a)) ^ (s)) >> (b)))
-__device__ __forceinline__ uint32_t rng_u32(Rng& r) {
-    r.s1 = XTB_TAUSW(r.s1, 13, 19, 4294967294u, 12);
-    r.s2 = XTB_TAUSW(r.s2, 2, 25, 4294967288u, 4);
-    r.s3 = XTB_TAUSW(r.s3, 3, 11, 4294967280u, 17);
-    r.s4 = 1664525u * r.s4 + 1013904223u;
-    return r.s1 ^ r.s2 ^ r.s3 ^ r.s4;
-}
-
 struct RadCtx {      // per-call context: rng state + failure flag
     Rng r;
+    Philox ph;
+    bool philox;
     bool seeded;
     bool rng_error;
 };
 
+__device__ __forceinline__ uint32_t rng_next_u32(RadCtx& c) {
+    if (!c.philox) return rng_u32(c.r);
+    const uint32_t w = c.r.s3 & 3u;
+    if (!c.ph.have || w == 0u) {
+        // block number = draw counter >> 2 (62 bits)
+        philox4x32_10(c.r.s1, c.r.s2, (c.r.s3 >> 2) | (c.r.s4 << 30), c.r.s4 >> 2, c.ph.blk);
+        c.ph.have = true;
+    }
+    const uint32_t v = c.ph.blk[w];
+    c.r.s3 += 1u;
+    if (c.r.s3 == 0u) c.r.s4 += 1u;
+    return v;
+}
+
 // RandomUniform_generate, random_src/uniform.h:34-53
 __device__ __forceinline__ double rand_uniform(RadCtx& c) {
     if (!c.seeded) { c.rng_error = true;  return 0; }
-    return rng_u32(c.r) / 4294967296.0;
+    return rng_next_u32(c) / 4294967296.0;
 }
 __device__ __forceinline__ uint32_t rand_u32(RadCtx& c) {
     if (!c.seeded) { c.rng_error = true;  return 0; }
-    return rng_u32(c.r);
+    return rng_next_u32(c);
 }
 // RandomUniformAccurate_generate, uniform_accurate.h:21-37
 __device__ __forceinline__ double rand_uniform_accurate(RadCtx& c) {
@@ -669,6 +673,8 @@ __device__ __noinline__ void synrad_emit_photons(PState& P, const PSlot& G, cons
     c.r.s3 = G.ldu(F_RNG_S3);  c.r.s4 = G.ldu(F_RNG_S4);
     c.seeded = !(c.r.s1 == 0 && c.r.s2 == 0 && c.r.s3 == 0 && c.r.s4 == 0);
     c.rng_error = false;
+    c.philox = a.rng_philox != 0;
+    c.ph.have = false;
 
     const double n_avg = synrad_average_number_of_photons(mass0, q0, beta0 * gamma0, B_T, lpath);
     double n = rand_exponential(c);

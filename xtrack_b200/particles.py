@@ -488,17 +488,31 @@ class Particles:
             zero &= self._fields[nn] == 0
         return not bool((zero & (state > 0)).any())
 
-    def _init_random_number_generator(self, seeds=None):
-        """Seeds the per-particle generator on the GPU (`xtb_rng_init`,
-        reference particles.py:1395-1418 + rng_src/particles_rng.h:12-28)."""
+    def _init_random_number_generator(self, seeds=None, mode='tausworthe'):
+        """Seeds the per-particle generator.
+        mode 'tausworthe': the reference's generator, seeded on the GPU with `xtb_rng_init`
+        (particles.py:1395-1418 + rng_src/particles_rng.h:12-28) -- the parity mode;
+        mode 'philox': the counter-based production generator (csrc/xtb_rng.cuh): the state
+        words become key = (seed, particle_id) and a zero draw counter."""
         from . import _cabi
+        if mode not in ('tausworthe', 'philox'):
+            raise ValueError(f'unknown generator mode {mode!r}')
         if seeds is None:
             seeds = np.random.randint(low=1, high=4e9, size=self._capacity,
                                       dtype=np.uint32)
         else:
             assert len(seeds) == self._capacity
             seeds = np.asarray(seeds, dtype=np.uint32)
-        _cabi.rng_init(self, seeds)
+        if mode == 'philox':
+            if np.any(seeds == 0):
+                raise ValueError('seeds must not be zero')
+            self._rng_s1 = seeds
+            self._rng_s2 = (self.get('particle_id') & 0xffffffff).astype(np.uint32)
+            self._rng_s3 = np.zeros(self._capacity, dtype=np.uint32)
+            self._rng_s4 = np.zeros(self._capacity, dtype=np.uint32)
+        else:
+            _cabi.rng_init(self, seeds)
+        object.__setattr__(self, '_rng_mode', mode)
 
     # -- (de)serialisation (particles.py:734-852) ----------------------------
     def to_dict(self):

@@ -81,7 +81,8 @@ def split_turns(n_line, ele_start, *, ele_stop=None, num_elements=None, num_turn
 
 class Tracker:
 
-    def __init__(self, line, device=None, exact_arithmetic=True, compact_every=None, fuse=True):
+    def __init__(self, line, device=None, exact_arithmetic=True, compact_every=None, fuse=True,
+                 rng='tausworthe'):
         self.line = line
         self.device = normalise_device('cuda' if device is None else device)
         # exact_arithmetic=True (default): kernel built without FMA contraction, rounds like
@@ -92,6 +93,12 @@ class Tracker:
         # fuse=True: full-turn launches run the FUSED program (drift-prefixed fast ops,
         # csrc/xtb_ops.h); False: everything runs the PLAIN one-element-per-op program
         self.fuse = bool(fuse)
+        # generator the tracker seeds unseeded particles with: 'tausworthe' (the reference's,
+        # parity mode) or 'philox' (counter-based, production); particles seeded by the caller
+        # carry their own mode (Particles._init_random_number_generator)
+        if rng not in ('tausworthe', 'philox'):
+            raise ValueError(f'unknown generator {rng!r}')
+        self.rng = rng
         self.num_elements = len(line.element_names)
         self._config_key = None
         self._lattice = None
@@ -189,7 +196,7 @@ class Tracker:
             monitor.allocate(self.device)
 
         if line._needs_rng and not particles._has_valid_rng_state():
-            particles._init_random_number_generator()
+            particles._init_random_number_generator(mode=self.rng)
 
         variant = 0
         if self.exact_arithmetic:
@@ -198,6 +205,8 @@ class Tracker:
             variant |= _cabi.VARIANT_SYNRAD
         if freeze_longitudinal:
             variant |= _cabi.VARIANT_FREEZE_LONG
+        if getattr(particles, '_rng_mode', 'tausworthe') == 'philox':
+            variant |= _cabi.VARIANT_PHILOX
         common = dict(flag_reset_s_at_end_turn=line.reset_s_at_end_turn,
                       flag_monitor=flag_monitor, monitor=monitor,
                       track_flags=line.get_flags_register(),
