@@ -89,6 +89,13 @@ SPECS = {
                            ('absolute_time', 'i64'), ('num_kicks', 'i64'),
                            ('model', 'i64'), ('integrator', 'i64')],
                    isthick=True, rot_shift=True),
+    # crab_cavity.py:51-63
+    'CrabCavity': dict(header='crab_cavity.h',
+                       fields=[('length', 'f64'), ('crab_voltage', 'f64'), ('frequency', 'f64'),
+                               ('lag', 'f64'), ('phase', 'f64'), ('lag_taper', 'f64'),
+                               ('phase_taper', 'f64'), ('absolute_time', 'i64'),
+                               ('num_kicks', 'i64'), ('model', 'i64'), ('integrator', 'i64')],
+                       isthick=True, rot_shift=True),
     # rf_multipole.py:51-65
     'RFMultipole': dict(header='rfmultipole.h',
                         fields=[('voltage', 'f64'), ('frequency', 'f64'), ('lag', 'f64'),
@@ -141,15 +148,16 @@ SLICE_FIELDS = [('radiation_flag', 'i64'), ('delta_taper', 'f64'), ('weight', 'f
 
 
 def _snake(parent):
-    return {'RBend': 'rbend'}.get(parent, parent.lower())
+    return {'RBend': 'rbend', 'CrabCavity': 'crab_cavity'}.get(parent, parent.lower())
 
 
 def _add_slices():
-    for parent in ('Bend', 'RBend', 'Quadrupole', 'Sextupole', 'Octupole', 'Multipole', 'Cavity'):
+    for parent in ('Bend', 'RBend', 'Quadrupole', 'Sextupole', 'Octupole', 'Multipole', 'Cavity',
+                   'CrabCavity'):
         kinds = [('ThinSlice' + parent, f'thin_slice_{_snake(parent)}.h', False, True, True),
                  ('ThickSlice' + parent, f'thick_slice_{_snake(parent)}.h', True, True, False),
                  ('DriftSlice' + parent, f'drift_slice_{_snake(parent)}.h', True, False, False)]
-        if parent not in ('Multipole', 'Cavity'):
+        if parent not in ('Multipole', 'Cavity', 'CrabCavity'):
             kinds += [('ThinSlice' + parent + 'Entry', f'thin_slice_{_snake(parent)}_entry.h',
                        False, True, False),
                       ('ThinSlice' + parent + 'Exit', f'thin_slice_{_snake(parent)}_exit.h',

@@ -7,7 +7,8 @@ only has to TRACK such lines; this helper exists so that the tests have some."""
 import xtrack_b200 as xb
 from xtrack_b200 import elements as _el
 
-_SLICEABLE = ('Bend', 'RBend', 'Quadrupole', 'Sextupole', 'Octupole', 'Multipole', 'Cavity')
+_SLICEABLE = ('Bend', 'RBend', 'Quadrupole', 'Sextupole', 'Octupole', 'Multipole', 'Cavity',
+              'CrabCavity')
 _WITH_EDGES = ('Bend', 'RBend', 'Quadrupole', 'Sextupole', 'Octupole')
 
 

@@ -71,6 +71,33 @@ def test_mean_radiation_ten_turns(name, exact):
                          floor=None if exact else 1e-11)
     for ff in ('state', 'at_turn', 'at_element'):
         assert np.array_equal(got[ff], ref[ff]), ff
+    if exact and name == 'clic_dr':
+        # thin ring, mean model: +, *, /, sqrt and the cavity's (C library) sine -- bit for bit
+        for ff in common.ALL_F64:
+            assert np.array_equal(got[ff], ref[ff]), ff
+
+
+def test_on_axis_particle_in_radiating_quadrupole():
+    """No field on the axis of a quadrupole: the guard-free square root of the thin radiating
+    kick must hand B = 0 to the radiation like the reference does (no NaN, no energy loss)."""
+    els = [xb.Multipole(knl=[0, 0.3], length=0.4), xb.Drift(length=1.0),
+           xb.Multipole(knl=[0, 0, 2.0], length=0.2), xb.Multipole(knl=[1e-3], hxl=1e-3, length=0.5)]
+    for model in ('mean', 'quantum'):
+        line = xb.Line(elements=els)
+        line.particle_ref = xb.Particles(p0c=5e9, mass0=xb.ELECTRON_MASS_EV)
+        line.configure_radiation(model=model)
+        p_host = xb.Particles(p0c=5e9, mass0=xb.ELECTRON_MASS_EV, x=[0., 0., 1e-3, 0.],
+                              y=[0., 0., 0., 1e-3], px=[0., 1e-5, 0., 0.])
+        if model == 'quantum':
+            common.seed_rng_host(p_host, np.arange(1, 5, dtype=np.uint32))
+        ref = common.oracle_track(line, p_host, 1, variant='synrad')
+        p = p_host.copy(_device='cuda:0')
+        line.build_tracker(_device='cuda:0')
+        line.track(p, num_turns=1)
+        got = common.by_id(p)
+        for ff in common.ALL_F64:
+            assert np.all(np.isfinite(got[ff])), (model, ff)
+            np.testing.assert_allclose(got[ff], ref[ff], rtol=1e-12, atol=1e-300, err_msg=ff)
 
 
 @pytest.mark.parametrize('name', ['clic_dr', 'lep'])

@@ -161,6 +161,30 @@ def test_rf_multipole(on_gpu):
     _compare(_track(line, p_host, on_gpu), ref, not on_gpu, 'rfmultipole')
 
 
+@pytest.mark.parametrize('on_gpu', BACKENDS)
+def test_crab_cavity(on_gpu):
+    """CrabCavity (crab_cavity.h -> track_rf.h:116-156): thin and thick
+    (drift-kick-drift with several kicks), misaligned, zero voltage, and sliced."""
+    import slicing_helper as sh
+    els = [xb.Drift(length=0.3),
+           xb.CrabCavity(crab_voltage=3e6, frequency=4e8, phase=0.3),
+           xb.CrabCavity(length=0.6, crab_voltage=-2e6, frequency=4e8, lag=20., num_kicks=3,
+                         integrator='teapot', shift_x=1e-3, rot_s_rad=0.4),
+           xb.CrabCavity(length=0.4, crab_voltage=0., frequency=4e8),
+           xb.CrabCavity(length=0.5, crab_voltage=1e6, frequency=8e8, model='drift-kick-drift-exact',
+                         integrator='yoshida4', num_kicks=2)]
+    line = _line(els, p0c=7e12 / 100)
+    p_host = common.gaussian_particles(line, 200, 4, common.SIGMAS['toy'], scale=3.)
+    ref = common.oracle_track(line, p_host, 2)
+    assert not np.array_equal(ref['px'], p_host.get('px'))
+    _compare(_track(line, p_host, on_gpu, num_turns=2), ref, True, 'crab cavity')
+    for mode in ('thin', 'thick'):
+        sl = sh.slice_line(line, n=3, mode=mode, only=('CrabCavity',))
+        assert any('SliceCrabCavity' in type(ee).__name__ for ee in sl.elements)
+        ref = common.oracle_track(sl, p_host, 1)
+        _compare(_track(sl, p_host, on_gpu), ref, True, 'crab cavity slices ' + mode)
+
+
 # ---- M-edge: full / dipole-only edges, fringes, wedge ------------------------------------------
 @pytest.mark.parametrize('on_gpu', BACKENDS)
 @pytest.mark.parametrize('model', ['rot-kick-rot', 'bend-kick-bend', 'mat-kick-mat',

@@ -8,7 +8,7 @@ library or a GPU is missing.
 """
 from .particles import Particles, LAST_INVALID_STATE, PROTON_MASS_EV, ELECTRON_MASS_EV
 from .elements import (Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupole,
-                       Octupole, Bend, RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation,
+                       Octupole, Bend, RBend, Cavity, CrabCavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation,
                        LimitRect, LimitEllipse, LimitPolygon)
 from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
                        BeamSizeMonitor, BeamProfileMonitor)

@@ -204,6 +204,9 @@ static __device__ __noinline__ void generic_op(const uint32_t op, const int32_t 
     case XTB_OP_RFMULT:
         rfmult_kick<FRZ>(P, G, a, q, aux);
         break;
+    case XTB_OP_CRAB:
+        crab_kick<FRZ>(P, G, a, q, aux);
+        break;
     case XTB_OP_EDGE_LIN:
         edge_linear(P, q[0], q[1]);
         break;

@@ -789,6 +789,135 @@ __device__ __forceinline__ void rad_end(const RadSnapshot& s, PState& P, const P
     }
 }
 
+// ---- thin radiating multipole: the whole element on N particles at once ----------------------
+// A thin ring with radiation (CLIC-DR: 8 596 wiggler / bend / quadrupole slices per turn) is made
+// of kick-only bodies (model -1, one uniform step without drifts) wrapped by WITH_RADIATION.
+// Through the generic body they cost ~750 instructions per particle (ncu, profiles/
+// r02_history.md): three Horner evaluations for the field where one has non-zero coefficients,
+// out-of-line calls per particle for rad_end / synrad_average_kick / update_delta, a dozen
+// guarded divisions and three guarded square roots, one dependency chain at a time.  This is
+// the same arithmetic, operation for operation (track_magnet.h:92-178, track_magnet_kick.h:
+// 265-370, track_magnet_radiation.h:64-94,233-267, synrad_spectrum.h:22-77,
+// local_particle_custom_api.h:36-50) -- the host build stays bit-identical to the oracle --
+// written across the particles of the thread with the guard-free IEEE sequences of
+// xtb_math.cuh; what depends on the beam alone (classical radius, 2 r0 c Q^2 ...) is formed once
+// per call, the products with literal-zero coefficient sets (main, relative strengths) are
+// left out as the exact identities they are.  Mean model: all here; quantum model: the field
+// and path length here, the photon loop per particle (synrad_emit_photons).
+template <int N, bool FRZ>
+__device__ __forceinline__ void thin_rad_kick_n(PState (&P)[N], const bool (&live)[N], const PSlot (&G)[N],
+                                                const XtbTrackArgs& a, const BodyPar& b) {
+    const double length = b.q[0];
+    double old_px[N], old_py[N], old_zeta[N];
+    XTB_LANES { old_px[k] = P[k].px;  old_py[k] = P[k].py;  old_zeta[k] = P[k].zeta; }
+    magnet_kick_n<N, FRZ>(P, b, 1.0);
+    if (!(b.radiation_flag() && length > 0)) return;
+
+    const double q0 = a.part.q0, mass0 = a.part.mass0;
+    // field at the mean position (x, y do not move in a thin kick): evaluate_field_from_strengths
+    // with the user coefficients; the main and relative sets are all zero here
+    double Bx[N], By[N], brho[N], pc[N], t0[N], t1[N];
+    {
+        double cl[N], qq[N];
+        XTB_LANES { pc[k] = G[k].ld(F_P0C);  cl[k] = XTB_C_LIGHT;  qq[k] = q0; }
+        xtb_vdiv<N>(t0, pc, cl);
+        xtb_vdiv<N>(brho, t0, qq);                        // brho_0 = p0c / C_LIGHT / q0
+    }
+    {
+        double len[N];
+        XTB_LANES {
+            double m = 0., n = 0.;
+            if (b.has_user()) horner_kick(0.5 * (P[k].x + P[k].x), 0.5 * (P[k].y + P[k].y), 1., b.cu(),
+                                          b.order_user(), m, n);
+            const double dpx = (-m + -0.) + 0.;           // dpx_mul + dpx_main + dpx_rel
+            const double dpy = (n + 0.) + 0.;
+            t0[k] = dpy * brho[k];
+            t1[k] = -dpx * brho[k];
+            len[k] = length;
+        }
+        xtb_vdiv<N>(Bx, t0, len);                         // Bx_T = dpy * brho_0 / length
+        xtb_vdiv<N>(By, t1, len);                         // By_T = -dpx * brho_0 / length
+    }
+    // compute_b_perp_mod (Bz = 0 * brho_0: its terms are exact zeros)
+    double opd[N], ropd[N], iix[N], iiy[N], iis[N], bperp[N], lpath[N];
+    XTB_LANES opd[k] = 1. + P[k].delta;
+    xtb_vrcp<N>(ropd, opd);
+    XTB_LANES {
+        iix[k] = div_by(0.5 * (old_px[k] + P[k].px), opd[k], ropd[k]);
+        iiy[k] = div_by(0.5 * (old_py[k] + P[k].py), opd[k], ropd[k]);
+        t0[k] = 1 - iix[k] * iix[k] + iiy[k] * iiy[k];
+    }
+    xtb_vsqrt<N>(iis, t0);
+    XTB_LANES {
+        const double B_par = Bx[k] * iix[k] + By[k] * iiy[k];
+        const double px_ = Bx[k] - B_par * iix[k];
+        const double py_ = By[k] - B_par * iiy[k];
+        const double pz_ = -(B_par * iis[k]);
+        t0[k] = px_ * px_ + py_ * py_ + pz_ * pz_;
+    }
+    xtb_vsqrt<N>(bperp, t0);
+    // (a particle on the axis of a quadrupole sees no field: zero, and anything below the range
+    // of the guard-free sequence, goes through the IEEE square root)
+    XTB_LANES { if (!(t0[k] > 1e-280)) bperp[k] = sqrt(t0[k]); }
+    XTB_LANES lpath[k] = P[k].rvv * (length - (P[k].zeta - old_zeta[k]));
+
+    if (b.radiation_flag() == 2) {
+#pragma unroll 1
+        for (int k = 0; k < N; ++k)
+            if (live[k]) synrad_emit_photons<FRZ>(P[k], G[k], a, bperp[k], lpath[k]);
+        return;
+    }
+    // synrad_average_kick (mean model)
+    const double Q0_coulomb = fabs(q0) * XTB_QELEM;
+    const double mass0_kg = mass0 / XTB_C_LIGHT / XTB_C_LIGHT * XTB_QELEM;
+    const double r0_m = Q0_coulomb * Q0_coulomb
+                        / (4 * XTB_PI * XTB_EPSILON_0 * mass0_kg * XTB_C_LIGHT * XTB_C_LIGHT);
+    const double K1 = 2 * r0_m * XTB_C_LIGHT * Q0_coulomb * Q0_coulomb;
+    const double K2 = 3 * mass0_kg;
+    double g0[N], den[N], ft[N], nd[N], b0[N];
+    XTB_LANES {
+        g0[k] = G[k].ld(F_GAMMA0);
+        b0[k] = G[k].ld(F_BETA0);
+        const double gamma = g0[k] * opd[k];
+        t0[k] = K1 * gamma * gamma * bperp[k] * bperp[k];
+        t1[k] = K2;
+    }
+    xtb_vdiv<N>(t0, t0, t1);                              // Ps_W
+    XTB_LANES { t0[k] = t0[k] * lpath[k];  t1[k] = XTB_C_LIGHT; }
+    xtb_vdiv<N>(t0, t0, t1);
+    XTB_LANES t1[k] = XTB_QELEM;
+    xtb_vdiv<N>(t0, t0, t1);                              // Delta_E_eV = Ps_W * lpath / C / QELEM
+    XTB_LANES den[k] = g0[k] * mass0 * opd[k];
+    xtb_vdiv<N>(t1, t0, den);
+    XTB_LANES {
+        ft[k] = 1 - t1[k];
+        nd[k] = opd[k] * ft[k] - 1;                       // (delta + 1) * f_t - 1
+    }
+    if (!FRZ) {
+        // LocalParticle_update_delta
+        double db0[N], pb0[N], nopd[N], rvv[N], rpp[N], ptau[N], rv0v[N];
+        XTB_LANES {
+            db0[k] = nd[k] * b0[k];
+            t0[k] = db0[k] * db0[k] + 2 * db0[k] * b0[k] + 1;
+        }
+        xtb_vsqrt<N>(pb0, t0);
+        XTB_LANES { pb0[k] = pb0[k] - 1;  nopd[k] = 1 + nd[k];  t0[k] = 1 + pb0[k]; }
+        xtb_vdiv<N>(rvv, nopd, t0);
+        xtb_vrcp<N>(rpp, nopd);
+        xtb_vdiv<N>(ptau, pb0, b0);
+        xtb_vrcp<N>(rv0v, rvv);
+        XTB_LANES {
+            if (live[k]) {
+                P[k].delta = nd[k];  P[k].rvv = rvv[k];  P[k].rv0v = rv0v[k];  P[k].rpp = rpp[k];
+                G[k].st(F_PTAU, ptau[k]);
+            }
+        }
+    }
+    XTB_LANES {
+        if (live[k]) { P[k].px *= ft[k];  P[k].py *= ft[k]; }
+    }
+}
+
 // track_magnet_body_single_particle, track_magnet.h:26-285, on N particles at once.
 // The three integrators are ONE loop nest -- radiation segments x sub-steps, each sub-step a
 // drift and (except the last of a segment) a kick -- so that the drift and kick bodies exist
@@ -808,6 +937,11 @@ __device__ __forceinline__ void magnet_body_n(PState (&P)[N], const bool (&live)
     const int dm = b.drift_model();
     const int nk = b.num_kicks();
     const int integ = b.drift_only() ? 0 : b.integrator();
+    if (SYNRAD && dm == -1 && integ == 3 && nk == 1 && !b.has_rel() && !b.has_main()
+        && !b.edge_in() && !b.edge_out()) {
+        thin_rad_kick_n<N, FRZ>(P, live, G, a, b);       // kick-only element, one step
+        return;
+    }
 
     int n_seg = 1, n_sub = 1;
     double seg_length = length;

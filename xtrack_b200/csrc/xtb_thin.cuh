@@ -281,6 +281,40 @@ __device__ __forceinline__ void rfmult_kick(PState& P, const PSlot& G, const Xtb
     }
 }
 
+// Crab cavity: track_rf_kick_single_particle (track_rf.h:18-167) with voltage = 0, order = -1 and
+// a transverse voltage: an RF dipole kick whose strength is transverse_voltage / p0c of the
+// particle.  q = [V_t, f, lag, phase].  (energy_kick = q * 0 * sin(.) is an exact zero.)
+template <bool FRZ>
+__device__ __forceinline__ void crab_kick(PState& P, const PSlot& G, const XtbTrackArgs& a,
+                                          const double* __restrict__ q, const int absolute_time) {
+    const double tv = q[0], frequency = q[1], tlag = q[2], tphase = q[3];
+    double phase0 = 0;
+    const double beta0 = G.ld(F_BETA0);
+    if (absolute_time == 1) phase0 += 2 * XTB_PI * P.at_turn * frequency * a.part.t_sim;
+    const double qq = fabs(a.part.q0) * G.ld(F_CHARGE_RATIO);
+    const double tau = P.zeta / beta0;
+    double delta_energy = 0.;
+    if (tv != 0) {
+        const double zre = 1.0, zim = 0.0;
+        const double x = P.x, y = P.y;
+        const double p0c = G.ld(F_P0C);
+        const double pn_kk = phase0 + XTB_DEG2RAD * (tlag + 90.) + tphase
+                             - (2.0 * XTB_PI) / XTB_C_LIGHT * frequency * tau;
+        const double k0l = tv / p0c;
+        const double cn = xtb_cos_glibc(pn_kk);
+        const double sn = xtb_sin_glibc(pn_kk);
+        double dpx = 0.0, dpy = 0.0, dptr = 0.0;
+        dpx += cn * (k0l * zre);
+        dpy += cn * (k0l * zim);
+        const double zret = zre * x - zim * y;
+        dptr += sn * (k0l * zret);
+        delta_energy += -qq * ((frequency * (2.0 * XTB_PI / XTB_C_LIGHT) * p0c) * dptr);
+        P.px += -P.chi * dpx;
+        P.py += P.chi * dpy;
+    }
+    if (!a.kill_cavity_kick) add_to_energy<FRZ>(P, G, beta0, 0. + delta_energy, 1);
+}
+
 // ---- RF elements on all the particles of a thread at once -------------------------------------
 // A ring has a handful of RF elements per turn, yet they took ~10 % of the thin kernel: each
 // went through the generic out-of-line path once per particle -- full state assembled and

@@ -588,6 +588,28 @@ class Cavity(BeamElement):
         self._finish(kwargs)
 
 
+class CrabCavity(BeamElement):
+    """beam_elements/crab_cavity.py:51-63, elements_src/crab_cavity.h: an RF dipole kick
+    (track_rf.h:116-156, `transverse_voltage`); `lag` in degrees (deprecated there), `phase` in
+    radians, both added."""
+    isthick = True
+    has_backtrack = True
+    _model_table = MODEL_RF
+    _dict_fields = ('length', 'crab_voltage', 'frequency', 'lag', 'phase', 'lag_taper',
+                    'phase_taper', 'absolute_time', 'num_kicks', 'model', 'integrator')
+
+    def __init__(self, **kwargs):
+        self.model = _enum(kwargs.pop('model', None), MODEL_RF, 'model')
+        self.integrator = _enum(kwargs.pop('integrator', None), INTEGRATOR, 'integrator')
+        for nn in ('length', 'crab_voltage', 'frequency', 'lag', 'phase', 'lag_taper',
+                   'phase_taper'):
+            setattr(self, nn, float(kwargs.pop(nn, 0.0)))
+        self.absolute_time = int(kwargs.pop('absolute_time', 0))
+        self.num_kicks = int(kwargs.pop('num_kicks', 0))
+        self._init_misalign(kwargs)
+        self._finish(kwargs)
+
+
 class RFMultipole(BeamElement):
     _dict_fields = ('order', 'knl', 'ksl', 'pn', 'ps', 'phase_n', 'phase_s', 'voltage', 'frequency', 'lag', 'phase', 'absolute_time')
     """rf_multipole.py:51-65; constructor `_HasKnlKsl.__init__` with the phase
@@ -867,12 +889,13 @@ class _Slice(BeamElement):
 def _make_slice_classes():
     out = {}
     parents = {'Bend': Bend, 'RBend': RBend, 'Quadrupole': Quadrupole, 'Sextupole': Sextupole,
-               'Octupole': Octupole, 'Multipole': Multipole, 'Cavity': Cavity}
+               'Octupole': Octupole, 'Multipole': Multipole, 'Cavity': Cavity,
+               'CrabCavity': CrabCavity}
     for pname, pcls in parents.items():
         kinds = [('ThinSlice' + pname, 'thin', False, True),
                  ('ThickSlice' + pname, 'thick', True, True),
                  ('DriftSlice' + pname, 'drift', True, False)]
-        if pname not in ('Multipole', 'Cavity'):
+        if pname not in ('Multipole', 'Cavity', 'CrabCavity'):
             kinds += [('ThinSlice' + pname + 'Entry', 'entry', False, True),
                       ('ThinSlice' + pname + 'Exit', 'exit', False, True)]
         for cname, kind, thick, from_parent in kinds:
@@ -895,5 +918,5 @@ globals().update(SLICE_CLASSES)
 
 ELEMENT_CLASSES = {cls.__name__: cls for cls in (
     Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupole, Octupole, Bend,
-    RBend, Cavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation, LimitRect, LimitEllipse,
+    RBend, Cavity, CrabCavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation, LimitRect, LimitEllipse,
     LimitPolygon, *SLICE_CLASSES.values())}

@@ -27,7 +27,7 @@ import math
 import numpy as np
 
 # ---- opcodes / flags: mirror of csrc/xtb_ops.h ----------------------------
-OPS_ABI_VERSION = 3          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
+OPS_ABI_VERSION = 4          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
 F_START, F_END, F_GLOBAL, F_DRIFT = 0x01, 0x02, 0x04, 0x08
 
 # fast set (fused program only): one whole element per op
@@ -73,6 +73,7 @@ OP_ADD_S_ZETA = 52
 OP_ADD_X = 53
 OP_BEAM_MON = 54
 OP_BEAM_PROFILE = 55
+OP_CRAB = 56
 # heavy set
 OP_MAGNET_BODY = 64
 OP_MAGNET_EDGE = 65
@@ -901,7 +902,8 @@ def _body_transc(drift_model, integrator, n_kicks, drift_only):
 # ---------------------------------------------------------------------------
 def _lower_rf(prog, cfg, *, weight, length, voltage, frequency, harmonic, lag, phase,
               absolute_time, order, knl, ksl, pn, ps, phase_n, phase_s, num_kicks, model,
-              default_model, integrator, default_integrator, lag_taper, phase_taper):
+              default_model, integrator, default_integrator, lag_taper, phase_taper,
+              transverse_voltage=0.0, transverse_lag=0.0, transverse_phase=0.0):
     if cfg['synrad']:
         lag += lag_taper
         phase += phase_taper
@@ -926,6 +928,7 @@ def _lower_rf(prog, cfg, *, weight, length, voltage, frequency, harmonic, lag, p
         raise NotImplementedError(f'RF element model {model} outside the contract')
     ll = body_length * weight
     vv = voltage * weight
+    tv = transverse_voltage * weight
     ff = factor_knl_ksl_body * weight
 
     def drift(dl):
@@ -934,6 +937,12 @@ def _lower_rf(prog, cfg, *, weight, length, voltage, frequency, harmonic, lag, p
         prog.op(OP_DRIFT if drift_model == 0 else OP_DRIFT_EXACT, [dl])
 
     def kick(kw):
+        if cfg.get('_crab'):
+            # CrabCavity (track_rf.h:116-156): no longitudinal voltage (its energy kick is an
+            # exact zero), the transverse kick needs the particle's p0c: evaluated on the device
+            prog.op(OP_CRAB, [tv * kw, frequency, transverse_lag, transverse_phase],
+                    aux=int(absolute_time), flops=40, transc=2)
+            return
         if order >= 0:
             # track_rf.h:65-115.  `bal = factor_knl_ksl * knl[kk] / factorial` is element
             # constant: folded here with the reference's operations (factorial accumulated
@@ -1068,6 +1077,16 @@ def _cavity_call(el):
                 lag_taper=el.lag_taper, phase_taper=el.phase_taper)
 
 
+def _crab_call(el):
+    """Arguments of the `track_rf_particles` call of crab_cavity.h (weight excluded)."""
+    return dict(length=el.length, voltage=0., frequency=el.frequency, harmonic=0., lag=0., phase=0.,
+                transverse_voltage=el.crab_voltage, transverse_lag=el.lag,
+                transverse_phase=el.phase, absolute_time=el.absolute_time, order=-1, knl=None,
+                ksl=None, pn=None, ps=None, phase_n=None, phase_s=None, num_kicks=el.num_kicks,
+                model=el.model, default_model=6, integrator=el.integrator, default_integrator=3,
+                lag_taper=el.lag_taper, phase_taper=el.phase_taper)
+
+
 def _lower_slice(prog, el, cfg):
     """Slices of thick elements (slice_elements_{thin,thick,drift,edge}.py).  Their C wrappers
     are GENERATED from the parent's wrapper (elements_src/_generate_slice_elements_c_code.py):
@@ -1099,13 +1118,14 @@ def _lower_slice(prog, el, cfg):
             prog.op(OP_DRIFT if model == 1 else OP_DRIFT_EXACT, [ll])
         return True
 
-    if pname == 'Cavity':
-        kw = _cavity_call(par)
+    if pname in ('Cavity', 'CrabCavity'):
+        kw = _cavity_call(par) if pname == 'Cavity' else _crab_call(par)
+        rf_cfg = cfg if pname == 'Cavity' else dict(cfg, _crab=True)
         if kind == 'thin':
             kw.update(num_kicks=1, model=-1, integrator=3)
 
         def body():
-            _lower_rf(prog, cfg, weight=el.weight, **kw)
+            _lower_rf(prog, rf_cfg, weight=el.weight, **kw)
     else:
         kw = _magnet_call(par)
         kw.update(radiation_flag=el.radiation_flag, radiation_flag_parent=par.radiation_flag,
@@ -1188,6 +1208,12 @@ def lower_element(prog, el, cfg):
 
     if getattr(el, '_slice_kind', None) is not None:
         return _lower_slice(prog, el, cfg)
+
+    if name == 'CrabCavity':
+        kw = _crab_call(el)
+        _with_transformations(prog, el, lambda: _lower_rf(prog, dict(cfg, _crab=True), weight=1., **kw),
+                              length=el.length)
+        return True
 
     if name == 'RFMultipole':
         def body():
