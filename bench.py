@@ -43,6 +43,11 @@ for pp in (ROOT, os.path.join(ROOT, 'tests')):
 
 WORKLOADS = {
     # name: (fixture, description)
+    # BASELINE.json configs[0]: the 16-element ring of examples/toy_ring/000_toy_ring.py (thick
+    # quadrupoles and sector bends), and the thin variant with multipoles and a cavity that the
+    # config's description names
+    'toy_ring': ('toy', 'toy ring (examples/toy_ring: 4 x [Quadrupole, Drift, Bend, Drift]), Gaussian beam'),
+    'toy_ring_thin': ('toy_thin', 'thin toy ring (drifts, thin multipoles, cavity), Gaussian beam'),
     'hllhc_da': ('hllhc_14', 'HL-LHC thin DA (hllhc_14 stand-in, BB->Marker), polar grid'),
     'sps_apertures': ('sps', 'SPS thin lattice with LimitRect/LimitEllipse, Gaussian beam'),
     'lep_thick': ('lep', 'LEP thick lattice (RBend/Quadrupole/Sextupole), Gaussian beam'),
@@ -59,9 +64,36 @@ RADIATION = {'clic_dr_quantum': 'quantum', 'lep_quantum': 'quantum',
              'clic_dr_mean': 'mean', 'lep_mean': 'mean'}
 
 
+def toy_ring(xb, thin=False):
+    """The 16-element ring of examples/toy_ring/000_toy_ring.py:13-36 of the reference (1.2 GeV
+    protons), or the thin variant with multipoles and one cavity (same as tests/common.py)."""
+    import math
+    if not thin:
+        els = []
+        for ii in range(4):
+            els += [xb.Quadrupole(length=0.3, k1=0.1 if ii % 2 == 0 else -0.7),
+                    xb.Drift(length=1.0),
+                    xb.Bend(length=3.0, angle=2 * math.pi / 4, k0='from_h', model='full',
+                            edge_entry_active=0, edge_exit_active=0),
+                    xb.Drift(length=1.0)]
+    else:
+        els = []
+        for ii in range(8):
+            els += [xb.Drift(length=1.0),
+                    xb.Multipole(knl=[0, 0.3 if ii % 2 == 0 else -0.3]),
+                    xb.Drift(length=1.0),
+                    xb.Multipole(knl=[2 * math.pi / 8], hxl=2 * math.pi / 8, length=0.5)]
+        els.append(xb.Cavity(voltage=1e5, frequency=1e7, lag=180.))
+    line = xb.Line(elements=els)
+    line.particle_ref = xb.Particles(p0c=1.2e9, mass0=xb.PROTON_MASS_EV)
+    return line
+
+
 def load_line(fixture, radiation=None):
     import gzip
     import xtrack_b200 as xb
+    if fixture in ('toy', 'toy_thin'):
+        return toy_ring(xb, thin=(fixture == 'toy_thin'))
     with gzip.open(os.path.join(ROOT, 'tests', 'golden', 'lattices', fixture + '.json.gz'),
                    'rt') as fid:
         dd = json.load(fid)
@@ -89,6 +121,8 @@ def initial_conditions(workload, line, n, rank):
     rng = np.random.default_rng(100 + rank)
     if workload == 'sps_apertures':
         sig = dict(x=4e-3, px=1e-4, y=2e-3, py=1e-4, zeta=0.2, delta=1e-3)
+    elif workload.startswith('toy_ring'):
+        sig = dict(x=1e-3, px=1e-4, y=1e-3, py=1e-4, zeta=5e-2, delta=1e-4)
     elif workload == 'clic_dr_quantum':
         sig = dict(x=1e-4, px=2e-5, y=2e-5, py=4e-6, zeta=2e-3, delta=1e-3)
     else:
@@ -196,7 +230,7 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --particles per GPU; strong: --particles in total, sharded over '
                          'the GPUs (BASELINE.json configs[1] as quoted: 10^6 particles on 8 GPUs)')
-    ap.add_argument('--turns', type=int, default=20, help='turns per step')
+    ap.add_argument('--turns', type=int, default=100, help='turns per step (one launch)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--quick', action='store_true',

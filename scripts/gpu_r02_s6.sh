@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 session 6: radiation -- tests (Philox, golden moments), benches of the four radiation
 # workloads, by-function profile of the CLIC-DR mean-model kernel.
-TAG=${1:-r02s6}
+TAG=${1:-r02s7}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 900 python -m pytest tests/test_gpu_radiation.py tests/test_philox.py -m gpu -q -s > $OUT/pytest_rad.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_rad.log

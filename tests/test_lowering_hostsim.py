@@ -397,3 +397,38 @@ def test_host_build_of_device_sin_cos_gives_libm_bits():
     gen = subprocess.run(['python', os.path.join(root, 'scripts', 'glibc', 'gen_sincostab.py'),
                           '--check'], capture_output=True, text=True)
     assert gen.returncode == 0, gen.stdout + gen.stderr
+
+
+def test_thick_fixture_derivation_physics_pins():
+    """The oracle's element structs for the thick rings are filled from this repository's own
+    reading of the JSON (RBend h / length from `length_straight` and `angle`, `k0 = 'from_h'`,
+    enumerations by name ...): a misreading would move oracle and product together.  These pins
+    do not depend on that reading being right twice -- they are physics the ring must satisfy:
+      * the bending angles of a ring add up to 2 pi (LEP, and the reference's lattice-design ring);
+      * with k0 == h in every bend, the on-momentum particle started on the design orbit stays
+        on it (any mis-derived strength, length or edge angle kicks it off by millimetres);
+      * the curved length of an RBend is angle / h with h = 2 sin(angle / 2) / length_straight;
+      * a ring cut into thick slices tracks like the unsliced ring (integrator accuracy)."""
+    import math
+    for name in ('lep', 'ring'):
+        line = common.load_line(name)
+        bends = [ee for ee in line.elements if type(ee).__name__ in ('Bend', 'RBend')]
+        assert abs(sum(ee.angle for ee in bends) / (2 * math.pi) - 1) < 1e-8, name
+        for ee in bends:
+            assert ee.k0 == ee.h or name == 'ring'
+            if type(ee).__name__ == 'RBend' and ee.angle != 0:
+                assert abs(ee.h - 2 * math.sin(ee.angle / 2) / ee.length_straight) < 1e-15
+                assert abs(ee.length * ee.h - ee.angle) < 1e-15
+        ref = line.particle_ref
+        p = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0,
+                         x=[0., 1e-4], px=[0., 0.], y=[0., 5e-5], delta=[0., 0.])
+        got = common.by_id(_track(line, p, 1))
+        assert abs(got['x'][0]) < 2e-7 and abs(got['y'][0]) < 1e-9 and abs(got['px'][0]) < 2e-8, \
+            (name, got['x'][0], got['px'][0])
+        assert abs(got['x'][1]) < 5e-3          # a betatron oscillation, not an escape
+    whole = common.load_line('ring')
+    sliced = common.load_line('ring_sliced')
+    p_host = common.gaussian_particles(whole, 20, 1, common.SIGMAS['toy'], scale=0.3)
+    a, b = common.by_id(_track(whole, p_host, 2)), common.by_id(_track(sliced, p_host, 2))
+    dev = common.max_rel_dev(a, b, fields=('x', 'px', 'y', 'py'))
+    assert max(dev.values()) < 1e-6, dev
