@@ -152,12 +152,12 @@ int xtb_measure_dfma_peak(int device, double seconds, double* flops_out);
 int xtb_selftest_math(int device, int64_t n_samples, uint64_t seed, int exponent_range,
                       uint64_t* mismatches_out);
 
-/* Self-test: the device sin / cos that reproduce the C library's results to the bit
- * (csrc/xtb_libm.cuh; used for the RF phases of cavities and RF multipoles, whose reference is
- * glibc's sin / cos) evaluated on `n` HOST arguments; results to host arrays, for the caller to
- * compare with its libm. */
-int xtb_eval_libm(int device, const double* x_host, int64_t n, double* sin_out_host,
-                  double* cos_out_host);
+/* Self-test: the device sin / cos / exp / expm1 / sinh / cosh that reproduce the C library's
+ * results to the bit (csrc/xtb_libm.cuh: the RF phases of cavities and RF multipoles, the
+ * focusing terms of the thick quadrupole map -- their reference is glibc) evaluated on `n` HOST
+ * arguments; out_host[6 n] receives sin, cos, exp, expm1, sinh, cosh (n values each) for the
+ * caller to compare with its libm. */
+int xtb_eval_libm(int device, const double* x_host, int64_t n, double* out_host);
 
 /* Self-test: `n` blocks of Philox4x32-10 (counter = c0 + i, c1, 0, 0; key k0, k1) evaluated on
  * the device into the host array out[4 n] (known-answer and cross-implementation tests). */

@@ -36,5 +36,26 @@ int main(int argc, char** argv) {
                bad_s, bad_c);
         bad_total += bad_s + bad_c;
     }
+    /* exp, expm1, sinh, cosh */
+    const double lo2[] = {0.0, 0.3465, 1.0397, 1e-9, 2.0, 0.0, 0.0};
+    const double hi2[] = {0.3466, 1.04, 2.0, 1e-3, 21.99, 21.99, 500.0};
+    for (int r = 0; r < 7; ++r) {
+        long be = 0, bm = 0, bs = 0, bc = 0;
+#pragma omp parallel for reduction(+ : be, bm, bs, bc)
+        for (long i = 0; i < n; ++i) {
+            const uint64_t h = mix64((uint64_t) i * 0x100000001B3ull + (uint64_t) (r + 100));
+            double x = lo2[r] + (hi2[r] - lo2[r]) * ((double) (h >> 11) * 0x1p-53);
+            if (h & 1) x = -x;
+            if (bits(xtb_exp_glibc(x)) != bits(exp(x))) be++;
+            if (r < 6) {
+                if (bits(xtb_expm1_glibc(x)) != bits(expm1(x))) bm++;
+                if (bits(xtb_sinh_glibc(x)) != bits(sinh(x))) bs++;
+                if (bits(xtb_cosh_glibc(x)) != bits(cosh(x))) bc++;
+            }
+        }
+        printf("range [%g, %g): %ld samples, mismatches exp %ld expm1 %ld sinh %ld cosh %ld\n", lo2[r],
+               hi2[r], n, be, bm, bs, bc);
+        bad_total += be + bm + bs + bc;
+    }
     return bad_total != 0;
 }

@@ -56,11 +56,12 @@ def test_ten_turns_vs_oracle(name, exact):
     common.assert_parity(got, ref, yard, exact, mask=alive, label=name)
     print(name, 'bit-identical fraction x:', float(np.mean(got['x'] == ref['x'])))
     _assert_int_fields(got, ref)
-    if exact and name != 'lep':
-        # the RF phases are evaluated with the C library's own sin / cos (csrc/xtb_libm.cuh) and
-        # everything else in these rings is +, *, /, sqrt in the reference's order: the EXACT
-        # kernel reproduces the reference BIT FOR BIT, every field of every particle -- the
-        # 1e-12 bar of the north star met literally, with room to spare
+    if exact:
+        # the RF phases and the focusing terms of the thick quadrupoles are evaluated with the C
+        # library's own sin / cos / sinh / cosh (csrc/xtb_libm.cuh) and everything else in these
+        # rings is +, *, /, sqrt in the reference's order: the EXACT kernel reproduces the
+        # reference BIT FOR BIT, every field of every particle, on all four rings -- the 1e-12
+        # bar of the north star met literally, with room to spare
         for ff in common.ALL_F64:
             assert np.array_equal(got[ff], ref[ff]), (name, ff)
     np.testing.assert_allclose(got['s'], ref['s'], rtol=1e-13, atol=1e-9)
@@ -86,7 +87,7 @@ def test_single_elements_bit_exact():
         ('cavity_harmonic', [xb.Drift(length=3.), xb.Cavity(voltage=3e6, harmonic=35640, lag=170.)], True),
         ('rfmultipole', [xb.RFMultipole(voltage=1e4, frequency=4e8, lag=10., knl=[1e-3, 1e-2],
                                         ksl=[0, 2e-2], pn=[10., 20.], ps=[0., 30.])], True),
-        ('quad_focusing', [xb.Quadrupole(length=0.5, k1=0.3)], False),
+        ('quad', [xb.Quadrupole(length=0.5, k1=0.3), xb.Quadrupole(length=0.7, k1=-2.0)], True),
     ]
     for label, els, bitwise in cases:
         line = xb.Line(elements=els)
@@ -293,9 +294,9 @@ def test_full_size_properties():
         assert np.array_equal(one[ff], three[ff], equal_nan=True), ff
 
 
-def test_device_sin_cos_give_glibc_bits():
-    """csrc/xtb_libm.cuh on the device against the C library of this host (`math.sin`: numpy's
-    own SIMD sine is another implementation), every branch of the algorithm."""
+def test_device_libm_gives_glibc_bits():
+    """csrc/xtb_libm.cuh on the device against the C library of this host (`math.*`: numpy's own
+    SIMD routines are other implementations), every branch of the algorithms."""
     import math
     from xtrack_b200 import _cabi
     rng = np.random.default_rng(5)
@@ -306,14 +307,22 @@ def test_device_sin_cos_give_glibc_bits():
           np.array([0.0, -0.0, 0.126, 0.855469, 2.426265, math.pi, -math.pi, math.pi / 2,
                     105414350., 105414349.9, 1e300, 5e-324])]
     x = np.concatenate(xs)
-    ss, cc = _cabi.eval_libm(x)
+    got = _cabi.eval_libm(x)
     ref_s = np.array([math.sin(v) for v in x])
     ref_c = np.array([math.cos(v) for v in x])
     small = np.abs(x) < 105414350.
-    assert np.array_equal(ss[small], ref_s[small])
-    assert np.array_equal(cc[small], ref_c[small])
+    assert np.array_equal(got['sin'][small], ref_s[small])
+    assert np.array_equal(got['cos'][small], ref_c[small])
     # beyond the range of the restated algorithm: the CUDA library function, a correct sine
-    np.testing.assert_allclose(ss[~small], ref_s[~small], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(got['sin'][~small], ref_s[~small], rtol=0, atol=1e-15)
+    # exp / expm1 / sinh / cosh (quadrupole map: arguments sqrt(|K|) L of order 0.1 ... 2)
+    x = np.concatenate([rng.uniform(-0.3466, 0.3466, 200000), rng.uniform(-1.04, 1.04, 200000),
+                        rng.uniform(-2.5, 2.5, 200000), rng.uniform(-21.9, 21.9, 200000),
+                        rng.uniform(-1e-6, 1e-6, 20000), np.array([0.0, 0.5, 1.0, -1.0, 20.0])])
+    got = _cabi.eval_libm(x)
+    for nn in ('exp', 'expm1', 'sinh', 'cosh'):
+        ref = np.array([getattr(math, nn)(v) for v in x])
+        assert np.array_equal(got[nn], ref), nn
 
 
 def test_guard_free_fp64_sequences_are_ieee():

@@ -106,7 +106,7 @@ def load():
                                       ct.POINTER(ct.c_uint64)]
     lib.xtb_eval_philox.argtypes = [ct.c_int, ct.c_uint32, ct.c_uint32, ct.c_uint32, ct.c_uint32,
                                     ct.c_int64, ct.c_void_p]
-    lib.xtb_eval_libm.argtypes = [ct.c_int, ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p]
+    lib.xtb_eval_libm.argtypes = [ct.c_int, ct.c_void_p, ct.c_int64, ct.c_void_p]
     _lib = lib
     return lib
 
@@ -286,11 +286,12 @@ def eval_philox(k0, k1, c0, c1, n, device=0):
 
 
 def eval_libm(x, device=0):
-    """(sin, cos) of the host array `x` by the device functions of csrc/xtb_libm.cuh."""
+    """dict of sin, cos, exp, expm1, sinh, cosh of the host array `x` by the device functions of
+    csrc/xtb_libm.cuh."""
     x = np.ascontiguousarray(x, dtype=np.float64)
-    ss, cc = np.empty_like(x), np.empty_like(x)
-    _check(load().xtb_eval_libm(int(device), x.ctypes.data, len(x), ss.ctypes.data, cc.ctypes.data))
-    return ss, cc
+    out = np.empty((6, len(x)), dtype=np.float64)
+    _check(load().xtb_eval_libm(int(device), x.ctypes.data, len(x), out.ctypes.data))
+    return dict(zip(('sin', 'cos', 'exp', 'expm1', 'sinh', 'cosh'), out))
 
 
 def launch_count():

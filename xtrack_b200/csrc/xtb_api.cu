@@ -643,29 +643,30 @@ extern "C" int xtb_selftest_math(int device, int64_t n_samples, uint64_t seed, i
 }
 
 // ---- self-test of the glibc-compatible sin / cos (xtb_libm.cuh) -------------------------------
-__global__ void xtb_eval_libm_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ s,
-                                     double* __restrict__ c) {
+__global__ void xtb_eval_libm_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    s[i] = xtb_sin_glibc(x[i]);
-    c[i] = xtb_cos_glibc(x[i]);
+    out[i] = xtb_sin_glibc(x[i]);
+    out[n + i] = xtb_cos_glibc(x[i]);
+    out[2 * n + i] = xtb_exp_glibc(x[i]);
+    out[3 * n + i] = xtb_expm1_glibc(x[i]);
+    out[4 * n + i] = xtb_sinh_glibc(x[i]);
+    out[5 * n + i] = xtb_cosh_glibc(x[i]);
 }
 
-extern "C" int xtb_eval_libm(int device, const double* x_host, int64_t n, double* sin_out_host,
-                             double* cos_out_host) {
-    if (!x_host || !sin_out_host || !cos_out_host || n <= 0) return fail(XTB_E_INVALID, "bad argument");
+extern "C" int xtb_eval_libm(int device, const double* x_host, int64_t n, double* out_host) {
+    if (!x_host || !out_host || n <= 0) return fail(XTB_E_INVALID, "bad argument");
     int prev = 0;
     cudaGetDevice(&prev);
     CUDA_TRY(cudaSetDevice(device));
     double* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, (size_t) n * 3 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d, (size_t) n * 7 * sizeof(double)));
     cudaError_t e = cudaMemcpy(d, x_host, (size_t) n * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        xtb_eval_libm_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(d, n, d + n, d + 2 * n);
+        xtb_eval_libm_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(d, n, d + n);
         e = cudaDeviceSynchronize();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(sin_out_host, d + n, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(cos_out_host, d + 2 * n, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d + n, (size_t) n * 6 * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d);
     cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(XTB_E_CUDA, "libm self-test: %s", cudaGetErrorString(e));

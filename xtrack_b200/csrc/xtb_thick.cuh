@@ -180,8 +180,8 @@ static __device__ __noinline__ void focusing_terms(const double K, const double 
         C = xtb_cos_glibc(sqrt_K * length);
     } else if (K < 0.0) {
         const double sqrt_K = sqrt(-K);
-        S = sinh(sqrt_K * length) / sqrt_K;
-        C = cosh(sqrt_K * length);
+        S = xtb_sinh_glibc(sqrt_K * length) / sqrt_K;
+        C = xtb_cosh_glibc(sqrt_K * length);
     } else {
         S = length;
         C = 1.0;
