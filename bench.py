@@ -238,6 +238,9 @@ def main():
     ap.add_argument('--monitor', action='store_true',
                     help='record every turn of every particle in a ParticlesMonitor (240 B per '
                          'particle-turn; BASELINE.json configs[4]); --quick only')
+    ap.add_argument('--compact-every', type=int, default=0,
+                    help='stream-compact the surviving particles every N turns of a launch '
+                         '(Tracker(compact_every=N)): long dynamic-aperture runs lose particles')
     ap.add_argument('--fma', action='store_true',
                     help='FMA-contracted kernel variant (default: exact, reference rounding)')
     args = ap.parse_args()
@@ -325,7 +328,10 @@ def main():
     ic = initial_conditions(args.workload, line, n, rank)
     p_host = xb.Particles(p0c=float(ref.get('p0c')[0]), mass0=ref.mass0, q0=ref.q0,
                           particle_id=first_id + np.arange(n), **ic)
-    tracker = line.build_tracker(_device=dev, exact_arithmetic=not args.fma)
+    tracker = line.build_tracker(_device=dev, exact_arithmetic=not args.fma,
+                                 compact_every=args.compact_every or None)
+    if args.compact_every:
+        config['compact_every'] = args.compact_every
     flop_per_turn = tracker.program.flops          # algorithmic flop per particle-turn
     config['flop_per_pet'] = flop_per_turn / n_el
 
@@ -400,6 +406,7 @@ def main():
                                 'GB_per_s_of_kernel_time': rec_bytes / (float(np.sum(kernel_ms)) * 1e-3) / 1e9,
                                 'x_last_turn_mean': float(np.mean(mon.x[:, args.turns * (args.warmup + args.steps) - 1]))}
         if rank == 0:
+            extra['beam'] = {'n_alive': n_alive, 'n_lost': n_lost}
             emit(({**extra, 'metric': 'particle-element-turns/s', 'value': value, 'quick': True,
                               'ms_per_step': ms_total / args.steps, 'config': config,
                               'clocks': clocks, 'gpu_launches': int(launches),

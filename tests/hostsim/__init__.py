@@ -119,3 +119,14 @@ def trig_stats(reset=True):
     a, b = ct.c_longlong(0), ct.c_longlong(0)
     lib.xtb_hostsim_trig_stats(ct.byref(a), ct.byref(b), int(reset))
     return a.value, b.value
+
+
+STOP_NAMES = ('end', 'slow', 'global_prefix', 'global_main', 'rect', 'ellipse')
+
+
+def stop_counts(reset=True):
+    """How often the hot loop (xtb_run_fast) came back, by reason, since the last reset."""
+    lib = load()
+    out = (ct.c_ulonglong * 8)()
+    lib.xtb_hostsim_stop_counts(out, int(reset))
+    return dict(zip(STOP_NAMES, list(out)))

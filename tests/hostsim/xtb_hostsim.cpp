@@ -32,6 +32,7 @@ using std::min;
 
 #define XTB_WITH_HEAVY
 #define XTB_COUNT_TRIG_MISS
+#define XTB_COUNT_STOPS
 #include "../../xtrack_b200/csrc/xtb_interp.cuh"
 
 // (test hook) lookups / misses of the host-tabulated element trigonometry (xtb_thick.cuh)
@@ -194,4 +195,9 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
         else run<1, false, false, PHot>(a);
     }
     return 0;
+}
+
+// (test hook) returns of xtb_run_fast by reason (XtbStop) since the last reset
+extern "C" void xtb_hostsim_stop_counts(unsigned long long* out8, int reset) {
+    for (int i = 0; i < 8; ++i) { out8[i] = xtb_dbg_stops[i];  if (reset) xtb_dbg_stops[i] = 0; }
 }

@@ -97,6 +97,24 @@ def test_global_limit_and_partial_turns():
     _assert_identical(common.by_id(p), hp.sorted_by_id())
 
 
+def test_lost_particle_does_not_keep_tripping_the_hot_loop():
+    """A lane whose particle was lost goes on executing ops from the axis; inside a crossing
+    bump that is a large-amplitude orbit which left the global limit within a turn and then
+    made xtb_run_fast return at EVERY drift (27 000 returns for 24 lost particles in this
+    case; on the GPU a 200-turn launch with 37 losses ran 30 % slower).  Such lanes are put
+    back on the axis: about one extra return per excursion."""
+    line = common.load_line('hllhc_14')
+    p_host = common.gaussian_particles(line, 60, 5, common.SIGMAS['hllhc_14'], scale=12.0)
+    ref = common.oracle_track(line, p_host, 6)
+    n_lost = int((ref['state'] <= 0).sum())
+    assert 10 < n_lost < 50
+    hostsim.stop_counts(reset=True)
+    got = common.by_id(_track(line, p_host, 6))
+    stops = hostsim.stop_counts()
+    _assert_identical(got, ref)
+    assert stops['global_prefix'] + stops['global_main'] <= 3 * n_lost, stops
+
+
 def test_turn_by_turn_monitor():
     line = common.load_line('sps')
     p_host = common.gaussian_particles(line, 40, 8, common.SIGMAS['sps'], scale=5.0)

@@ -397,6 +397,13 @@ enum XtbStop {
     XTB_STOP_ELLIPSE         // XTB_OP_ELLIPSE at `off`: some lane is outside the aperture
 };
 
+#ifdef XTB_COUNT_STOPS
+static __device__ unsigned long long xtb_dbg_stops[8];     // returns of xtb_run_fast by reason
+#ifndef __CUDA_ARCH__
+#define atomicAdd(p, v) (*(p) += (v))
+#endif
+#endif
+
 // The hot loop.  Executes fast ops from `lb->off` on until something happens that is
 // not fast-path work (XtbStop) and returns what; the caller (xtb_run_tile) deals with
 // it and calls again.  The function
@@ -857,15 +864,33 @@ __device__ XTB_RUN_TILE_INLINE void xtb_run_tile(const xtb_tile_t tb, XtbLanes<N
         pstate_benign(lanes.P[k]);
         lanes.P[k].s = s_keep;
     };
+    // A lane without a particle keeps executing the ops from the on-axis state it was given;
+    // where the reference orbit is not the axis (crossing bumps) that is a large-amplitude
+    // trajectory, which leaves the limit within a turn and would then trip the pre-filter of
+    // the hot loop at EVERY drift for the rest of the launch (measured: 1.3e6 returns for 37
+    // lost particles in 200 turns of hllhc_14, the blocks with a loss 3.5x slower).  Such a
+    // lane is put back on the axis here: one return per excursion.
+    auto repin = [&](const int k) {
+        const double s_keep = lanes.P[k].s;      // (SUNI: s stays the same on every lane)
+        pstate_benign(lanes.P[k]);
+        lanes.P[k].s = s_keep;
+    };
     auto global_check = [&]() {
-        if (a.ignore_global) return;
-        for (int k = 0; k < NPT; ++k)
-            if (lanes.live[k] && outside_global(lanes.P[k], lim)) retire(k, -1);
+        for (int k = 0; k < NPT; ++k) {
+            const S& Q = lanes.P[k];
+            if (!lanes.live[k]) {
+                // (well inside what any form of the pre-filter lets pass; catches NaN)
+                if (!(fabs(Q.x) < 0.5 * lim && fabs(Q.y) < 0.5 * lim)) repin(k);
+            } else if (!a.ignore_global && outside_global(Q, lim)) retire(k, -1);
+        }
     };
 
     for (;;) {
         const int stop = xtb_run_fast<NPT, FRZ, CHI1, SUNI>(tb, &lanes, lim_hi, skip_prefix);
         skip_prefix = 0;
+#ifdef XTB_COUNT_STOPS
+        atomicAdd(&xtb_dbg_stops[stop], 1ull);          // (per thread)
+#endif
         if (stop == XTB_STOP_END) break;
         const xtb_w128 hw = xtb_ld_w(tb, lanes.off);
         const uint32_t h = (uint32_t) hw.x;

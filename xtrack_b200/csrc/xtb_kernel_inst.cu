@@ -36,12 +36,7 @@
 #ifndef XTB_NPT2_BELOW
 #define XTB_NPT2_BELOW 2900
 #endif
-#ifndef XTB_SMALL_GRID_BLOCKS_PER_SM
-#define XTB_SMALL_GRID_BLOCKS_PER_SM 0      /* 0: always XTB_THREADS */
-#endif
-#ifndef XTB_MIN_THREADS
-#define XTB_MIN_THREADS 64
-#endif
+
 
 // ---- launch shape ------------------------------------------------------------------------
 // One grid of XTB_THREADS-thread blocks, block b carrying slots [b * T * NPT, (b + 1) * T * NPT).
@@ -66,10 +61,8 @@ static int xtb_pick_npt(const int64_t n, const int n_sm) {
     return XTB_NPT_THIN;
 }
 
-// Block size: XTB_THREADS, halved while the beam is so small that whole blocks are a coarse
-// unit of SM load (fewer than XTB_SMALL_GRID_BLOCKS_PER_SM blocks per SM): 326 blocks on 148
-// SMs leave SMs with 2 and SMs with 3 (ncu: SMs active 82 % of the launch), 652 half-size
-// blocks spread as 4 and 5.  XTB_THREADS_FORCE overrides (experiments).
+// Block size: XTB_THREADS, halved only for beams too small to give every SM two blocks.
+// XTB_THREADS_FORCE overrides (experiments).
 static unsigned xtb_pick_threads(const int64_t n, const int npt, const int n_sm) {
     static const int forced = [] {
         const char* e = getenv("XTB_THREADS_FORCE");
@@ -78,9 +71,10 @@ static unsigned xtb_pick_threads(const int64_t n, const int npt, const int n_sm)
     if (forced == 32 || forced == 64 || forced == 128) return (unsigned) forced;
     unsigned t = XTB_THREADS;
     if (n_sm <= 0) return t;
-    while (t > XTB_MIN_THREADS
-           && (double) n / ((double) t * npt) < (double) XTB_SMALL_GRID_BLOCKS_PER_SM * n_sm)
-        t >>= 1;
+    // a beam of fewer blocks than SMs (10^4 particles: 40 - 80 blocks of 128 threads on 148 SMs)
+    // leaves SMs idle: smaller blocks until every SM holds two.  (Above that, smaller blocks
+    // only lose: measured 62 500 ... 500 000 particles, profiles/r02_history.md.)
+    while (t > 32 && (double) n / ((double) t * npt) < 2.0 * n_sm) t >>= 1;
     return t;
 }
 
@@ -135,3 +129,16 @@ extern "C" cudaError_t XTB_LAUNCH_NAME(unsigned variant, const XtbTrackArgs* a, 
     default: return cudaErrorNotSupported;
     }
 }
+
+#ifdef XTB_COUNT_STOPS
+#if XTB_EXACT
+extern "C" int xtb_debug_stops(unsigned long long* out8, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out8, xtb_dbg_stops, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0};
+        e = cudaMemcpyToSymbol(xtb_dbg_stops, z, sizeof(z));
+    }
+    return (int) e;
+}
+#endif
+#endif
