@@ -59,7 +59,6 @@ void xt_ref_track_line(
         ParticlesMonitorData tbt_monitor,
         uint64_t track_flags)
 {
-    (void) num_ele_line;
 #ifdef XO_CONTEXT_CPU_OPENMP
     const int64_t capacity = ParticlesData_get__capacity(particles);
     const int num_threads = omp_get_max_threads();
@@ -97,10 +96,25 @@ void xt_ref_track_line(
             if (!isactive) break;
             int64_t const ele_stop = ele_start + num_ele_track;
 
-            if (flag_monitor == 1){
-                ParticlesMonitor_track_local_particle(tbt_monitor, &lpart);
+            /* XS_FLAG_BACKTRACK (tracker.py:628-646,707-731): the elements in reverse order,
+             * at_element counted down, the turn bookkeeping at the START of the pass */
+            const int backtrack = LocalParticle_check_track_flag(&lpart, XS_FLAG_BACKTRACK);
+            int64_t elem_idx, increm;
+            if (backtrack){
+                elem_idx = ele_stop - 1;
+                increm = -1;
+                if (flag_end_turn_actions > 0){
+                    increment_at_turn_backtrack(&lpart, flag_reset_s_at_end_turn,
+                                                line_length, num_ele_line);
+                }
+            } else {
+                if (flag_monitor == 1){
+                    ParticlesMonitor_track_local_particle(tbt_monitor, &lpart);
+                }
+                elem_idx = ele_start;
+                increm = 1;
             }
-            for (int64_t elem_idx = ele_start; elem_idx < ele_stop; elem_idx++){
+            for (; (elem_idx >= ele_start) && (elem_idx < ele_stop); elem_idx += increm){
                 if (flag_monitor == 2){
                     ParticlesMonitor_track_local_particle(tbt_monitor, &lpart);
                 }
@@ -108,12 +122,16 @@ void xt_ref_track_line(
 
                 isactive = check_is_active(&lpart);
                 if (!isactive) break;
-                increment_at_element(&lpart, 1);
+                increment_at_element(&lpart, backtrack ? -1 : 1);
             }
             if (flag_monitor == 2){
                 ParticlesMonitor_track_local_particle(tbt_monitor, &lpart);
             }
-            if (flag_end_turn_actions > 0){
+            if (backtrack){
+                if (flag_monitor == 1){
+                    ParticlesMonitor_track_local_particle(tbt_monitor, &lpart);
+                }
+            } else if (flag_end_turn_actions > 0){
                 if (isactive){
                     increment_at_turn(&lpart, flag_reset_s_at_end_turn);
                 }

@@ -71,6 +71,25 @@ def main():
             return f
         k = bisect.bisect_right([m[0] for m in mm], l) - 1
         return f + ':' + (mm[k][1] if k >= 0 else '?')
+    def category(sass):
+        ff = sass.split()
+        if ff and ff[0].startswith('@'):
+            ff = ff[1:]
+        m = ff[0].split('.')[0] if ff else '?'
+        if m in ('DADD', 'DMUL', 'DFMA', 'DSETP'):
+            return 'fp64'
+        if m in ('MUFU',):
+            return 'mufu'
+        if m in ('MOV', 'IMAD', 'IADD3', 'LOP3', 'SHF', 'SEL', 'ISETP', 'LEA', 'PRMT', 'IADD', 'PLOP3', 'FSEL',
+                 'UMOV', 'ULOP3', 'UIADD3', 'UISETP', 'USEL', 'USHF', 'ULEA', 'UIMAD', 'R2UR', 'S2R', 'CS2R',
+                 'FSETP', 'FADD', 'FMUL', 'FFMA', 'I2F', 'F2I', 'F2F', 'IABS', 'IMNMX', 'VIADD', 'VIMNMX', 'P2R', 'R2P'):
+            return 'int/mov'
+        if m.startswith(('LD', 'ST', 'ATOM', 'RED', 'UBLKCP', 'SYNCS', 'ULD')):
+            return 'mem'
+        if m in ('BRA', 'BSSY', 'BSYNC', 'CALL', 'RET', 'EXIT', 'WARPSYNC', 'BAR', 'JMP', 'BRX', 'NOP', 'VOTE', 'VOTEU', 'SHFL', 'REDUX'):
+            return 'ctrl'
+        return 'other'
+    mix = collections.defaultdict(collections.Counter)
     samples, execd = collections.Counter(), collections.Counter()
     stalls = collections.defaultdict(collections.Counter)
     scols = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
@@ -78,6 +97,8 @@ def main():
         k = fn(loc)
         samples[k] += int(r[ix['# Samples']])
         execd[k] += int(r[ix['Instructions Executed']])
+        mix[k][category(r[ix['Source']])] += int(r[ix['Instructions Executed']])
+        mix['(kernel)'][category(r[ix['Source']])] += int(r[ix['Instructions Executed']])
         for c in scols:
             stalls[k][c[6:]] += int(r[ix[c]])
     ts, te = sum(samples.values()), sum(execd.values())
@@ -86,6 +107,12 @@ def main():
     for k, v in samples.most_common(24):
         top = ', '.join(f'{n} {100 * c / max(v, 1):.0f} %' for n, c in stalls[k].most_common(3))
         print(f'| {k} | {100 * v / ts:.1f} % | {100 * execd[k] / te:.1f} % | {top} |')
+    print('\nexecuted warp instructions by kind (share of the function\'s own):\n')
+    cats = ['fp64', 'mufu', 'int/mov', 'mem', 'ctrl', 'other']
+    print('| function | ' + ' | '.join(cats) + ' |\n|---|' + '---|' * len(cats))
+    for k in ['(kernel)'] + [k for k, _ in samples.most_common(16)]:
+        tot = max(sum(mix[k].values()), 1)
+        print(f'| {k} | ' + ' | '.join(f'{100 * mix[k][c] / tot:.0f} %' for c in cats) + ' |')
 
 
 if __name__ == '__main__':

@@ -685,7 +685,12 @@ L_STOP:
 // xtb_run_tile: global aperture check after statically thick elements, loss check and
 // at_element + 1 at the end of an element (tracker.py:681-711); a lost particle is stored at
 // once and its lane goes on, benign.
-template <int NPT, bool SYNRAD, bool FRZ>
+// THIN (radiation kernels): the run loop of a thin radiating ring (CLIC-DR: drift, edge, wiggler
+// pole, edge, drift ...) -- the same loop with the kick-only bodies alone (thin_rad_kick_run,
+// the beam constants formed once per run); it returns at the first thick body.  Without the
+// thick maps in the function the lanes stay in registers (the general loop spills ~300 bytes
+// around them, and its thin bodies waited on thread-local memory: profiles/r02_history.md).
+template <int NPT, bool SYNRAD, bool FRZ, bool THIN>
 static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<NPT, PState>& lanes,
                                                   const XtbPass ps, const XtbTrackArgs& a) {
     PState T[NPT];
@@ -707,6 +712,8 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
     const double lim = a.global_xy_limit;
     const bool ignore_global = a.ignore_global != 0;
     const bool ebe_monitor = (a.flag_monitor == 2);
+    ThinRadRun<NPT> rad_run;
+    if (THIN) thin_rad_run_begin<NPT>(rad_run, G, a);
 
     // lane k is lost in the current element (index eidx): write it back, go on benign
     auto retire = [&](const int k) {
@@ -735,6 +742,7 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
         const double L = __longlong_as_double((long long) hw.y);
         if (op == XTB_OP_MAGNET_BODY || op == XTB_OP_DRIFT) {
             const int32_t aux = (int32_t) (hw.x >> 32);
+            if (THIN && op == XTB_OP_MAGNET_BODY && !is_thin_kick_body((uint32_t) aux)) break;
             const double* __restrict__ q = reinterpret_cast<const double*>(xtb_tile_ptr(tb, off + 2));
             if (h & (XTB_F_DRIFT << 8)) {           // the Drift element in front
 #pragma unroll
@@ -750,7 +758,8 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
                     }
             }
             if (op == XTB_OP_MAGNET_BODY) {
-                magnet_body_n<NPT, SYNRAD, FRZ>(T, live, G, a, q, aux);
+                if constexpr (THIN) thin_rad_kick_run<NPT, FRZ>(T, live, G, a, body_par(q, aux), rad_run);
+                else magnet_body_n<NPT, SYNRAD, FRZ>(T, live, G, a, q, aux);
             } else {
                 const double len = q[0];
 #pragma unroll
@@ -938,7 +947,11 @@ __device__ XTB_RUN_TILE_INLINE void xtb_run_tile(const xtb_tile_t tb, XtbLanes<N
 #ifdef XTB_WITH_HEAVY
             if constexpr (HEAVY && std::is_same<S, PState>::value) {
                 if (op == XTB_OP_MAGNET_BODY || op == XTB_OP_DRIFT) {
-                    xtb_run_heavy<NPT, SYNRAD, FRZ>(tb, lanes, ps, a);     // a whole run of them
+                    // a whole run of them
+                    if (SYNRAD && !(op == XTB_OP_MAGNET_BODY && !is_thin_kick_body((uint32_t) (hw.x >> 32))))
+                        xtb_run_heavy<NPT, SYNRAD, FRZ, true>(tb, lanes, ps, a);
+                    else
+                        xtb_run_heavy<NPT, SYNRAD, FRZ, false>(tb, lanes, ps, a);
                     break;
                 }
             }

@@ -333,6 +333,10 @@ __device__ __forceinline__ void magnet_drift_n(PState (&P)[N], const double leng
 #pragma unroll
         for (int k = 0; k < N; ++k) drift_exact<FRZ>(P[k], length);
         break;
+    // (these out-of-line maps take the lane by address, which keeps the lane array of the
+    // caller in thread-local memory.  Measured, r02 session 15: handing them a copy instead --
+    // lanes in registers, 600-900 bytes of spills under the 128-register cap -- is SLOWER:
+    // LEP thick 1.61e10 -> 1.48e10 PET/s, CLIC-DR mean 1.08e11 -> 0.81e11)
     case 3:
         for (int k = 0; k < N; ++k) combined_dipole_quad<FRZ>(P[k], length, k0, k1, h);
         break;
@@ -804,39 +808,66 @@ __device__ __forceinline__ void rad_end(const RadSnapshot& s, PState& P, const P
 // per call, the products with literal-zero coefficient sets (main, relative strengths) are
 // left out as the exact identities they are.  Mean model: all here; quantum model: the field
 // and path length here, the photon loop per particle (synrad_emit_photons).
+// What the thin radiating kick needs of the beam and of each particle's reference, formed once
+// per RUN of ops (xtb_interp.cuh::xtb_run_heavy) instead of once per element: the operations
+// are the reference's, on the same operands -- only not repeated.  The reciprocals serve the
+// divisions by these constants (div_by: same correctly rounded quotients, 3 FP64 instructions
+// instead of ~10).
+template <int N>
+struct ThinRadRun {
+    double brho[N];      // p0c / C_LIGHT / q0
+    double g0[N], g0m[N];   // gamma0, gamma0 * mass0
+    double b0[N], rb0[N];   // beta0, RN(1 / beta0)
+    double K1, K2, rK2, rC, rQ;
+};
+template <int N>
+__device__ __forceinline__ void thin_rad_run_begin(ThinRadRun<N>& r, const PSlot (&G)[N], const XtbTrackArgs& a) {
+    const double q0 = a.part.q0, mass0 = a.part.mass0;
+    double pc[N], cl[N], qq[N], t0[N];
+    XTB_LANES { pc[k] = G[k].ld(F_P0C);  cl[k] = XTB_C_LIGHT;  qq[k] = q0; }
+    xtb_vdiv<N>(t0, pc, cl);
+    xtb_vdiv<N>(r.brho, t0, qq);                          // brho_0 = p0c / C_LIGHT / q0
+    XTB_LANES {
+        r.g0[k] = G[k].ld(F_GAMMA0);
+        r.g0m[k] = r.g0[k] * mass0;
+        r.b0[k] = G[k].ld(F_BETA0);
+    }
+    xtb_vrcp<N>(r.rb0, r.b0);
+    const double Q0_coulomb = fabs(q0) * XTB_QELEM;
+    const double mass0_kg = mass0 / XTB_C_LIGHT / XTB_C_LIGHT * XTB_QELEM;
+    const double r0_m = Q0_coulomb * Q0_coulomb
+                        / (4 * XTB_PI * XTB_EPSILON_0 * mass0_kg * XTB_C_LIGHT * XTB_C_LIGHT);
+    r.K1 = 2 * r0_m * XTB_C_LIGHT * Q0_coulomb * Q0_coulomb;
+    r.K2 = 3 * mass0_kg;
+    r.rK2 = 1. / r.K2;
+    r.rC = 1. / XTB_C_LIGHT;
+    r.rQ = 1. / XTB_QELEM;
+}
+
 template <int N, bool FRZ>
-__device__ __forceinline__ void thin_rad_kick_n(PState (&P)[N], const bool (&live)[N], const PSlot (&G)[N],
-                                                const XtbTrackArgs& a, const BodyPar& b) {
+__device__ __forceinline__ void thin_rad_kick_run(PState (&P)[N], const bool (&live)[N], const PSlot (&G)[N],
+                                                  const XtbTrackArgs& a, const BodyPar& b,
+                                                  const ThinRadRun<N>& r) {
     const double length = b.q[0];
     double old_px[N], old_py[N], old_zeta[N];
     XTB_LANES { old_px[k] = P[k].px;  old_py[k] = P[k].py;  old_zeta[k] = P[k].zeta; }
     magnet_kick_n<N, FRZ>(P, b, 1.0);
     if (!(b.radiation_flag() && length > 0)) return;
 
-    const double q0 = a.part.q0, mass0 = a.part.mass0;
     // field at the mean position (x, y do not move in a thin kick): evaluate_field_from_strengths
     // with the user coefficients; the main and relative sets are all zero here
-    double Bx[N], By[N], brho[N], pc[N], t0[N], t1[N];
+    double Bx[N], By[N], t0[N], t1[N];
     {
-        double cl[N], qq[N];
-        XTB_LANES { pc[k] = G[k].ld(F_P0C);  cl[k] = XTB_C_LIGHT;  qq[k] = q0; }
-        xtb_vdiv<N>(t0, pc, cl);
-        xtb_vdiv<N>(brho, t0, qq);                        // brho_0 = p0c / C_LIGHT / q0
-    }
-    {
-        double len[N];
+        const double rlen = 1. / length;
         XTB_LANES {
             double m = 0., n = 0.;
             if (b.has_user()) horner_kick(0.5 * (P[k].x + P[k].x), 0.5 * (P[k].y + P[k].y), 1., b.cu(),
                                           b.order_user(), m, n);
             const double dpx = (-m + -0.) + 0.;           // dpx_mul + dpx_main + dpx_rel
             const double dpy = (n + 0.) + 0.;
-            t0[k] = dpy * brho[k];
-            t1[k] = -dpx * brho[k];
-            len[k] = length;
+            Bx[k] = div_by(dpy * r.brho[k], length, rlen);        // Bx_T = dpy * brho_0 / length
+            By[k] = div_by(-dpx * r.brho[k], length, rlen);       // By_T = -dpx * brho_0 / length
         }
-        xtb_vdiv<N>(Bx, t0, len);                         // Bx_T = dpy * brho_0 / length
-        xtb_vdiv<N>(By, t1, len);                         // By_T = -dpx * brho_0 / length
     }
     // compute_b_perp_mod (Bz = 0 * brho_0: its terms are exact zeros)
     double opd[N], ropd[N], iix[N], iiy[N], iis[N], bperp[N], lpath[N];
@@ -868,54 +899,58 @@ __device__ __forceinline__ void thin_rad_kick_n(PState (&P)[N], const bool (&liv
         return;
     }
     // synrad_average_kick (mean model)
-    const double Q0_coulomb = fabs(q0) * XTB_QELEM;
-    const double mass0_kg = mass0 / XTB_C_LIGHT / XTB_C_LIGHT * XTB_QELEM;
-    const double r0_m = Q0_coulomb * Q0_coulomb
-                        / (4 * XTB_PI * XTB_EPSILON_0 * mass0_kg * XTB_C_LIGHT * XTB_C_LIGHT);
-    const double K1 = 2 * r0_m * XTB_C_LIGHT * Q0_coulomb * Q0_coulomb;
-    const double K2 = 3 * mass0_kg;
-    double g0[N], den[N], ft[N], nd[N], b0[N];
+    double ft[N], nd[N];
     XTB_LANES {
-        g0[k] = G[k].ld(F_GAMMA0);
-        b0[k] = G[k].ld(F_BETA0);
-        const double gamma = g0[k] * opd[k];
-        t0[k] = K1 * gamma * gamma * bperp[k] * bperp[k];
-        t1[k] = K2;
+        const double gamma = r.g0[k] * opd[k];
+        const double Ps_W = div_by(r.K1 * gamma * gamma * bperp[k] * bperp[k], r.K2, r.rK2);
+        // Delta_E_eV = Ps_W * lpath / C / QELEM
+        t0[k] = div_by(div_by(Ps_W * lpath[k], XTB_C_LIGHT, r.rC), XTB_QELEM, r.rQ);
+        t1[k] = r.g0m[k] * opd[k];
     }
-    xtb_vdiv<N>(t0, t0, t1);                              // Ps_W
-    XTB_LANES { t0[k] = t0[k] * lpath[k];  t1[k] = XTB_C_LIGHT; }
-    xtb_vdiv<N>(t0, t0, t1);
-    XTB_LANES t1[k] = XTB_QELEM;
-    xtb_vdiv<N>(t0, t0, t1);                              // Delta_E_eV = Ps_W * lpath / C / QELEM
-    XTB_LANES den[k] = g0[k] * mass0 * opd[k];
-    xtb_vdiv<N>(t1, t0, den);
+    xtb_vdiv<N>(t1, t0, t1);
     XTB_LANES {
         ft[k] = 1 - t1[k];
         nd[k] = opd[k] * ft[k] - 1;                       // (delta + 1) * f_t - 1
     }
     if (!FRZ) {
         // LocalParticle_update_delta
-        double db0[N], pb0[N], nopd[N], rvv[N], rpp[N], ptau[N], rv0v[N];
+        double db0[N], pb0[N], nopd[N], rvv[N], rpp[N], rv0v[N];
         XTB_LANES {
-            db0[k] = nd[k] * b0[k];
-            t0[k] = db0[k] * db0[k] + 2 * db0[k] * b0[k] + 1;
+            db0[k] = nd[k] * r.b0[k];
+            t0[k] = db0[k] * db0[k] + 2 * db0[k] * r.b0[k] + 1;
         }
         xtb_vsqrt<N>(pb0, t0);
         XTB_LANES { pb0[k] = pb0[k] - 1;  nopd[k] = 1 + nd[k];  t0[k] = 1 + pb0[k]; }
         xtb_vdiv<N>(rvv, nopd, t0);
         xtb_vrcp<N>(rpp, nopd);
-        xtb_vdiv<N>(ptau, pb0, b0);
         xtb_vrcp<N>(rv0v, rvv);
         XTB_LANES {
             if (live[k]) {
                 P[k].delta = nd[k];  P[k].rvv = rvv[k];  P[k].rv0v = rv0v[k];  P[k].rpp = rpp[k];
-                G[k].st(F_PTAU, ptau[k]);
+                G[k].st(F_PTAU, div_by(pb0[k], r.b0[k], r.rb0[k]));
             }
         }
     }
     XTB_LANES {
         if (live[k]) { P[k].px *= ft[k];  P[k].py *= ft[k]; }
     }
+}
+
+// (one element on its own: the generic body dispatch)
+template <int N, bool FRZ>
+__device__ __forceinline__ void thin_rad_kick_n(PState (&P)[N], const bool (&live)[N], const PSlot (&G)[N],
+                                                const XtbTrackArgs& a, const BodyPar& b) {
+    ThinRadRun<N> r;
+    thin_rad_run_begin<N>(r, G, a);
+    thin_rad_kick_run<N, FRZ>(P, live, G, a, b, r);
+}
+
+// is this body op a kick-only element in one uniform step (what thin_rad_kick_* implement)?
+__device__ __forceinline__ bool is_thin_kick_body(const uint32_t aux) {
+    // integrator 3 (uniform), drift model -1, no relative / main strengths, not drift-only,
+    // no merged edges, one kick
+    const uint32_t mask = 3u | (15u << 2) | (1u << 8) | (1u << 9) | (1u << 12) | (1u << 13) | (1u << 14);
+    return ((aux & mask) == 3u) && ((aux >> 15) == 1u);
 }
 
 // track_magnet_body_single_particle, track_magnet.h:26-285, on N particles at once.
@@ -937,8 +972,7 @@ __device__ __forceinline__ void magnet_body_n(PState (&P)[N], const bool (&live)
     const int dm = b.drift_model();
     const int nk = b.num_kicks();
     const int integ = b.drift_only() ? 0 : b.integrator();
-    if (SYNRAD && dm == -1 && integ == 3 && nk == 1 && !b.has_rel() && !b.has_main()
-        && !b.edge_in() && !b.edge_out()) {
+    if (SYNRAD && is_thin_kick_body(b.a)) {
         thin_rad_kick_n<N, FRZ>(P, live, G, a, b);       // kick-only element, one step
         return;
     }
