@@ -255,6 +255,11 @@ class Line:
     def _needs_rng(self):
         return self._extra_config['_needs_rng']
 
+    @property
+    def _is_backtrackable(self):
+        """tracker_data.py: every element of the line states an inverse map"""
+        return all(getattr(ee, 'has_backtrack', False) for ee in self.elements)
+
     def get_flags_register(self):
         """track_flags.py:5-12,42-50"""
         bits = {'XS_FLAG_BACKTRACK': 0, 'XS_FLAG_KILL_CAVITY_KICK': 2,
@@ -391,8 +396,9 @@ class Line:
         if multi_element_monitor_at is not None:
             raise NotImplementedError('MultiElementMonitor is CPU-only in the reference '
                                       'and outside the hot-path contract')
-        if kwargs.get('backtrack', False):
-            raise NotImplementedError('backtracking is not part of the contract')
+        backtrack = kwargs.get('backtrack', False)
+        if backtrack is not False and with_progress:
+            raise NotImplementedError('with_progress while backtracking')
         if self.tracker is None or self.tracker.device != particles.device:
             self.build_tracker(_device=particles.device, **self._tracker_kwargs)
         if with_progress:
@@ -406,4 +412,5 @@ class Line:
             num_elements=num_elements, num_turns=num_turns,
             turn_by_turn_monitor=turn_by_turn_monitor,
             freeze_longitudinal=freeze_longitudinal, time=time,
-            _force_no_end_turn_actions=kwargs.get('_force_no_end_turn_actions', False))
+            _force_no_end_turn_actions=kwargs.get('_force_no_end_turn_actions', False),
+            backtrack=backtrack)

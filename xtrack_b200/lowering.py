@@ -415,33 +415,46 @@ def _emit_s_shift(prog, ds):
         prog.op(OP_SSHIFT, [ds])
 
 
+def _emit_misalign_steps(prog, steps, backtrack):
+    """The elementary transformations of one misalignment function in order; when
+    backtracking, the inverse ones in reverse order (track_misalignments.h:59-74, 97-112,
+    225-240, 362-377)."""
+    if backtrack:
+        steps = [(kind, *[-v for v in args]) for kind, *args in reversed(steps)]
+    for kind, *args in steps:
+        if kind == 'xy':
+            prog.op(OP_XYSHIFT, list(args))
+        elif kind == 's':
+            _emit_s_shift(prog, *args)
+        elif kind == 'yrot':
+            _emit_y_rotate(prog, *args)
+        elif kind == 'xrot':
+            _emit_x_rotate(prog, *args)
+        else:
+            _emit_s_rotate(prog, *args)
+
+
 def _misalign_entry_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
-                             psi_with_frame):
-    """track_misalignments.h:38-75 (forward tracking)"""
+                             psi_with_frame, backtrack=False):
+    """track_misalignments.h:38-75"""
     mis_x = dx - anchor * math.cos(phi) * math.sin(theta)
     mis_y = dy - anchor * math.sin(phi)
     mis_s = ds - anchor * (math.cos(phi) * math.cos(theta) - 1)
-    prog.op(OP_XYSHIFT, [mis_x, mis_y])
-    _emit_s_shift(prog, mis_s)
-    _emit_y_rotate(prog, theta)
-    _emit_x_rotate(prog, phi)
-    _emit_s_rotate(prog, psi_no_frame)
-    _emit_s_rotate(prog, psi_with_frame)
+    _emit_misalign_steps(prog, [('xy', mis_x, mis_y), ('s', mis_s), ('yrot', theta),
+                                ('xrot', phi), ('srot', psi_no_frame),
+                                ('srot', psi_with_frame)], backtrack)
 
 
 def _misalign_exit_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
-                            psi_with_frame):
+                            psi_with_frame, backtrack=False):
     """track_misalignments.h:78-113"""
     neg_part_length = anchor - length
     mis_x = neg_part_length * math.cos(phi) * math.sin(theta) - dx
     mis_y = neg_part_length * math.sin(phi) - dy
     mis_s = neg_part_length * (math.cos(phi) * math.cos(theta) - 1) - ds
-    _emit_s_rotate(prog, -psi_with_frame)
-    _emit_s_rotate(prog, -psi_no_frame)
-    _emit_x_rotate(prog, -phi)
-    _emit_y_rotate(prog, -theta)
-    _emit_s_shift(prog, mis_s)
-    prog.op(OP_XYSHIFT, [mis_x, mis_y])
+    _emit_misalign_steps(prog, [('srot', -psi_with_frame), ('srot', -psi_no_frame),
+                                ('xrot', -phi), ('yrot', -theta), ('s', mis_s),
+                                ('xy', mis_x, mis_y)], backtrack)
 
 
 def _mat_mul(a, b):
@@ -480,11 +493,11 @@ def _misalignment_matrix(dx, dy, ds, theta, phi, psi):
 
 
 def _misalign_entry_curved(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
-                           angle, h, psi_with_frame):
+                           angle, h, psi_with_frame, backtrack=False):
     """track_misalignments.h:116-241"""
     if angle == 0.0 and (length != 0.0 or h == 0.0):
         return _misalign_entry_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor,
-                                        length, psi_with_frame)
+                                        length, psi_with_frame, backtrack)
     mm = _misalignment_matrix(dx, dy, ds, theta, phi, psi_no_frame)
     if length != 0.0:
         h = angle / length
@@ -502,20 +515,17 @@ def _misalign_entry_curved(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, l
     rot_theta = math.atan2(me[0][2], me[2][2])
     rot_phi = math.atan2(me[1][2], math.sqrt(me[1][0] * me[1][0] + me[1][1] * me[1][1]))
     rot_psi = math.atan2(me[1][0], me[1][1])
-    prog.op(OP_XYSHIFT, [mis_x, mis_y])
-    _emit_s_shift(prog, mis_s)
-    _emit_y_rotate(prog, rot_theta)
-    _emit_x_rotate(prog, rot_phi)
-    _emit_s_rotate(prog, rot_psi)
-    _emit_s_rotate(prog, psi_with_frame)
+    _emit_misalign_steps(prog, [('xy', mis_x, mis_y), ('s', mis_s), ('yrot', rot_theta),
+                                ('xrot', rot_phi), ('srot', rot_psi),
+                                ('srot', psi_with_frame)], backtrack)
 
 
 def _misalign_exit_curved(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, length,
-                          angle, h, psi_with_frame):
+                          angle, h, psi_with_frame, backtrack=False):
     """track_misalignments.h:244-378"""
     if angle == 0.0 and (length != 0.0 or h == 0.0):
         return _misalign_exit_straight(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor,
-                                       length, psi_with_frame)
+                                       length, psi_with_frame, backtrack)
     mm = _misalignment_matrix(dx, dy, ds, theta, phi, psi_no_frame)
     inv_mm = _rigid_inverse(mm)
     if length != 0.0:
@@ -534,31 +544,34 @@ def _misalign_exit_curved(prog, dx, dy, ds, theta, phi, psi_no_frame, anchor, le
     rot_theta = math.atan2(re[0][2], re[2][2])
     rot_phi = math.atan2(re[1][2], math.sqrt(re[1][0] * re[1][0] + re[1][1] * re[1][1]))
     rot_psi = math.atan2(re[1][0], re[1][1])
-    _emit_s_rotate(prog, -psi_with_frame)
-    prog.op(OP_XYSHIFT, [mis_x, mis_y])
-    _emit_s_shift(prog, mis_s)
-    _emit_y_rotate(prog, rot_theta)
-    _emit_x_rotate(prog, rot_phi)
-    _emit_s_rotate(prog, rot_psi)
+    _emit_misalign_steps(prog, [('srot', -psi_with_frame), ('xy', mis_x, mis_y), ('s', mis_s),
+                                ('yrot', rot_theta), ('xrot', rot_phi), ('srot', rot_psi)],
+                         backtrack)
 
 
-def _with_transformations(prog, el, body, *, length=0.0, curved=False, weight=1.0):
-    """headers/track_local_particle_with_transformations.h:174-204 (+ :99-162)"""
+def _with_transformations(prog, el, body, *, length=0.0, curved=False, weight=1.0,
+                          backtrack=False):
+    """headers/track_local_particle_with_transformations.h:174-204 (+ :99-162); when
+    backtracking the exit transformation comes first, each one inverted (:141-161)"""
     if not el.allow_rot_and_shift or not el.has_misalignment:
         body()
         return
     args = [el.shift_x, el.shift_y, el.shift_s, el.rot_y_rad, el.rot_x_rad,
             el.rot_s_rad_no_frame, el.rot_shift_anchor, length * weight]
     if curved:
-        cargs = args + [el.angle * weight, el.h, el.rot_s_rad]
-        _misalign_entry_curved(prog, *cargs)
-        body()
-        _misalign_exit_curved(prog, *cargs)
+        args = args + [el.angle * weight, el.h, el.rot_s_rad]
+        entry, exit_ = _misalign_entry_curved, _misalign_exit_curved
     else:
-        sargs = args + [el.rot_s_rad]
-        _misalign_entry_straight(prog, *sargs)
+        args = args + [el.rot_s_rad]
+        entry, exit_ = _misalign_entry_straight, _misalign_exit_straight
+    if backtrack:
+        exit_(prog, *args, backtrack=True)
         body()
-        _misalign_exit_straight(prog, *sargs)
+        entry(prog, *args, backtrack=True)
+    else:
+        entry(prog, *args)
+        body()
+        exit_(prog, *args)
 
 
 # ---------------------------------------------------------------------------
@@ -579,8 +592,9 @@ def _emit_thin_multipole(prog, coeffs, hl, b0, b1):
 
 def _lower_edge(prog, synrad, *, model, is_exit, half_gap, knorm, kskew, knl, ksl,
                 factor_knl_ksl, kl_order, knl_rel, ksl_rel, factor_knl_ksl_rel, order_rel,
-                length, face_angle, face_angle_feed_down, fringe_integral):
-    """track_magnet_edge.h:17-167 (forward tracking, no solenoid)"""
+                length, face_angle, face_angle_feed_down, fringe_integral,
+                factor_for_backtrack=1.0):
+    """track_magnet_edge.h:17-167 (no solenoid)"""
     k0 = 0.0
     k0 += knorm[0]
     if abs(length) > 1e-10 and kl_order > -1:
@@ -590,10 +604,12 @@ def _lower_edge(prog, synrad, *, model, is_exit, half_gap, knorm, kskew, knl, ks
     if model == 0:
         r21, r43 = _linear_edge_coefficients(k0, face_angle, face_angle_feed_down, half_gap,
                                              fringe_integral)
-        r21 = r21 * 1.0
-        r43 = r43 * 1.0
+        r21 = r21 * factor_for_backtrack
+        r43 = r43 * factor_for_backtrack
         prog.op(OP_EDGE_LIN, [r21, r43])
     elif model in (1, 2):
+        if factor_for_backtrack < 0:
+            prog.op(OP_SET_STATE, aux=-32)       # the full edge model cannot be backtracked
         should_rotate = 0
         sin_, cos_, tan_ = 0.0, 1.0, 0.0
         if abs(face_angle) > 10e-10:
@@ -662,10 +678,29 @@ def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl,
         edge_entry_angle_fdown += theta_in
         edge_exit_angle_fdown += theta_out
 
-    core_length = length * weight
-    core_length_curved = length_curved * weight
-    factor_knl_ksl_body = factor_knl_ksl * weight
-    factor_knl_ksl_edge = factor_knl_ksl
+    if cfg.get('backtrack'):          # track_magnet.h:413-433
+        core_length = -length * weight
+        core_length_curved = -length_curved * weight
+        factor_knl_ksl_body = -factor_knl_ksl * weight
+        factor_knl_ksl_edge = factor_knl_ksl
+        factor_backtrack_edge = -1.
+        hxl = -hxl
+        edge_entry_active, edge_exit_active = edge_exit_active, edge_entry_active
+        edge_entry_model, edge_exit_model = edge_exit_model, edge_entry_model
+        edge_entry_angle, edge_exit_angle = edge_exit_angle, edge_entry_angle
+        edge_entry_angle_fdown, edge_exit_angle_fdown = edge_exit_angle_fdown, edge_entry_angle_fdown
+        edge_entry_fint, edge_exit_fint = edge_exit_fint, edge_entry_fint
+        edge_entry_hgap, edge_exit_hgap = edge_exit_hgap, edge_entry_hgap
+        theta_in, theta_out = -theta_out, -theta_in
+        cos_theta_in, cos_theta_out = cos_theta_out, cos_theta_in
+        sin_theta_in, sin_theta_out = -sin_theta_out, -sin_theta_in
+        x0_in, x0_out = x0_out, x0_in
+    else:
+        core_length = length * weight
+        core_length_curved = length_curved * weight
+        factor_knl_ksl_body = factor_knl_ksl * weight
+        factor_knl_ksl_edge = factor_knl_ksl
+        factor_backtrack_edge = 1.
 
     if synrad:
         if radiation_flag == 10:
@@ -686,7 +721,8 @@ def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl,
                        factor_knl_ksl=factor_knl_ksl_edge, kl_order=order,
                        knl_rel=knl_rel, ksl_rel=ksl_rel,
                        factor_knl_ksl_rel=factor_knl_ksl_edge * rel_ref_strength,
-                       order_rel=order_rel, length=length)
+                       order_rel=order_rel, length=length,
+                       factor_for_backtrack=factor_backtrack_edge)
 
     if edge_entry_active:
         if rbend_model == 2:
@@ -907,8 +943,14 @@ def _lower_rf(prog, cfg, *, weight, length, voltage, frequency, harmonic, lag, p
     if cfg['synrad']:
         lag += lag_taper
         phase += phase_taper
-    body_length = length
-    factor_knl_ksl_body = 1.0
+    if cfg.get('backtrack'):          # track_rf.h:364-373 (the RF elements have no edges here)
+        body_length = -length
+        factor_knl_ksl_body = -1.0
+        voltage = -voltage
+        transverse_voltage = -transverse_voltage
+    else:
+        body_length = length
+        factor_knl_ksl_body = 1.0
     if integrator == 0:
         integrator = default_integrator
     if model == 0:
@@ -1102,13 +1144,19 @@ def _lower_slice(prog, el, cfg):
     par = el.parent
     pname = type(par).__name__
     kind = el._slice_kind
+    back = bool(cfg.get('backtrack'))
     if kind == 'drift':
         ll = el.weight * par.length
+        if back:                        # drift_slice_*.h: the lengths with the other sign
+            ll = -ll
         if pname == 'DriftExact':
             prog.op(OP_DRIFT_EXACT, [ll])
         elif pname == 'RBend' and par.rbend_model == 2:
             ls = par.length_straight * el.weight
             ds_corr = (par.length - par.length_straight) * el.weight
+            if back:
+                ls *= -1
+                ds_corr *= -1
             prog.op(OP_DRIFT_EXACT, [ls])
             prog.op(OP_ADD_S_ZETA, [ds_corr])
         else:
@@ -1161,15 +1209,19 @@ def _lower_slice(prog, el, cfg):
     args = [par.shift_x, par.shift_y, par.shift_s, par.rot_y_rad, par.rot_x_rad,
             par.rot_s_rad_no_frame, par.rot_shift_anchor - el.slice_offset, length * el.weight]
     if curved:
-        cargs = args + [par.angle * el.weight, par.h, par.rot_s_rad]
-        _misalign_entry_curved(prog, *cargs)
-        body()
-        _misalign_exit_curved(prog, *cargs)
+        args = args + [par.angle * el.weight, par.h, par.rot_s_rad]
+        entry, exit_ = _misalign_entry_curved, _misalign_exit_curved
     else:
-        sargs = args + [par.rot_s_rad]
-        _misalign_entry_straight(prog, *sargs)
+        args = args + [par.rot_s_rad]
+        entry, exit_ = _misalign_entry_straight, _misalign_exit_straight
+    if back:
+        exit_(prog, *args, backtrack=True)
         body()
-        _misalign_exit_straight(prog, *sargs)
+        entry(prog, *args, backtrack=True)
+    else:
+        entry(prog, *args)
+        body()
+        exit_(prog, *args)
     return bool(el.isthick)
 
 
@@ -1177,33 +1229,36 @@ def lower_element(prog, el, cfg):
     """Appends the ops of one element; returns True if the class is statically
     thick (global aperture check after it, tracker.py:681-689)."""
     name = type(el).__name__
+    back = bool(cfg.get('backtrack'))      # XS_FLAG_BACKTRACK: every class states its inverse
+    sign = -1.0 if back else 1.0
 
     if name in ('Marker', '_Placeholder'):
         return False
 
-    if name == 'Drift':
+    if name == 'Drift':                 # elements_src/drift.h:16-19
         model = 2 if cfg.get('exact_drifts') else (el.model or 1)
+        length = -el.length if back else el.length
         if model == 1:
-            prog.op(OP_DRIFT, [el.length])
+            prog.op(OP_DRIFT, [length])
         elif model == 2:
-            prog.op(OP_DRIFT_EXACT, [el.length])
+            prog.op(OP_DRIFT_EXACT, [length])
         return True
 
-    if name == 'DriftExact':
-        prog.op(OP_DRIFT_EXACT, [el.length])
+    if name == 'DriftExact':            # elements_src/drift_exact.h:16-19
+        prog.op(OP_DRIFT_EXACT, [-el.length if back else el.length])
         return True
 
     if name in _MAGNET_CLASSES:
         kw = _magnet_call(el)
         thick_len = el.length if (name != 'Multipole' or el._isthick_field > 0) else 0.0
         _with_transformations(prog, el, lambda: _lower_magnet(prog, cfg, weight=1., **kw),
-                              length=thick_len, curved=name in ('Bend', 'RBend'))
+                              length=thick_len, curved=name in ('Bend', 'RBend'), backtrack=back)
         return name != 'Multipole'
 
     if name == 'Cavity':
         kw = _cavity_call(el)
         _with_transformations(prog, el, lambda: _lower_rf(prog, cfg, weight=1., **kw),
-                              length=el.length)
+                              length=el.length, backtrack=back)
         return True
 
     if getattr(el, '_slice_kind', None) is not None:
@@ -1212,7 +1267,7 @@ def lower_element(prog, el, cfg):
     if name == 'CrabCavity':
         kw = _crab_call(el)
         _with_transformations(prog, el, lambda: _lower_rf(prog, dict(cfg, _crab=True), weight=1., **kw),
-                              length=el.length)
+                              length=el.length, backtrack=back)
         return True
 
     if name == 'RFMultipole':
@@ -1223,16 +1278,20 @@ def lower_element(prog, el, cfg):
                       ps=el.ps, phase_n=el.phase_n, phase_s=el.phase_s, num_kicks=1, model=-1,
                       default_model=0, integrator=0, default_integrator=0, lag_taper=0.,
                       phase_taper=0.)
-        _with_transformations(prog, el, body, length=0.0)
+        _with_transformations(prog, el, body, length=0.0, backtrack=back)
         return False
 
-    if name == 'DipoleEdge':
+    if name == 'DipoleEdge':            # elements_src/dipoleedge.h:27-75
         def body():
             delta_taper = el.delta_taper if cfg['synrad'] else 0.0
             if el.model == 0:
                 r21 = el.r21 * (1 + delta_taper)
                 r43 = el.r43 * (1 + delta_taper)
+                if back:
+                    r21, r43 = -r21, -r43
                 prog.op(OP_EDGE_LIN, [r21, r43])
+            elif el.model == 1 and back:
+                prog.op(OP_SET_STATE, aux=-32)
             elif el.model == 1:
                 if abs(el.e1) < 10e-10:
                     sct = [-999.0, -999.0, -999.0]
@@ -1240,48 +1299,51 @@ def lower_element(prog, el, cfg):
                     sct = [math.sin(el.e1), math.cos(el.e1), math.tan(el.e1)]
                 prog.op(OP_DIPEDGE_NL, [el.k, el.e1, el.fint, el.hgap, *sct], aux=el.side,
                         flops=300, transc=6)
-        _with_transformations(prog, el, body)
+        _with_transformations(prog, el, body, backtrack=back)
         return False
 
-    if name == 'SRotation':
-        prog.op(OP_SROT, [el.sin_z, el.cos_z])
+    if name == 'SRotation':             # elements_src/srotation.h:14-27
+        prog.op(OP_SROT, [-el.sin_z if back else el.sin_z, el.cos_z])
         return False
 
-    if name == 'XYShift':
-        prog.op(OP_XYSHIFT, [el.dx, el.dy])
+    if name == 'XYShift':               # elements_src/xyshift.h:13-28
+        prog.op(OP_XYSHIFT, [-el.dx, -el.dy] if back else [el.dx, el.dy])
         return False
 
     if name == 'Translation':           # elements_src/translation.h:13-26
-        prog.op(OP_XYSHIFT, [el.shift_x, el.shift_y])
+        prog.op(OP_XYSHIFT, [-el.shift_x, -el.shift_y] if back else [el.shift_x, el.shift_y])
         return False
 
     if name == 'Rotation':              # elements_src/rotation.h:13-60
-        for axis in (el._first_rot, el._second_rot, el._third_rot):
+        order = (el._first_rot, el._second_rot, el._third_rot)
+        if back:                        # opposite angles, opposite order (:25-33)
+            order = order[::-1]
+        for axis in order:
             if axis == 0 and el.rot_x_rad != 0.0:
-                aa = el.rot_x_rad
+                aa = sign * el.rot_x_rad
                 prog.op(OP_XROT, [math.sin(aa), math.cos(aa), math.tan(aa)])
             elif axis == 1 and el.rot_y_rad != 0.0:
-                aa = el.rot_y_rad
+                aa = sign * el.rot_y_rad
                 prog.op(OP_YROT, [math.sin(aa), math.cos(aa), math.tan(aa)])
             elif axis == 2 and el.rot_s_rad != 0.0:
-                aa = el.rot_s_rad
+                aa = sign * el.rot_s_rad
                 prog.op(OP_SROT, [math.sin(aa), math.cos(aa)])
         return False
 
     if name == 'LimitRect':
         _with_transformations(prog, el, lambda: prog.op(
-            OP_LIMIT_RECT, [el.min_x, el.max_x, el.min_y, el.max_y]))
+            OP_LIMIT_RECT, [el.min_x, el.max_x, el.min_y, el.max_y]), backtrack=back)
         return False
 
     if name == 'LimitEllipse':
         _with_transformations(prog, el, lambda: prog.op(
-            OP_LIMIT_ELLIPSE, [el.a_squ, el.b_squ, el.a_b_squ]))
+            OP_LIMIT_ELLIPSE, [el.a_squ, el.b_squ, el.a_b_squ]), backtrack=back)
         return False
 
     if name == 'LimitPolygon':
         nv = len(el.x_vertices)
         _with_transformations(prog, el, lambda: prog.op(
-            OP_LIMIT_POLYGON, [*el.x_vertices, *el.y_vertices], aux=nv, flops=7 * nv))
+            OP_LIMIT_POLYGON, [*el.x_vertices, *el.y_vertices], aux=nv, flops=7 * nv), backtrack=back)
         return False
 
     if name == 'ParticlesMonitor':
@@ -1321,10 +1383,13 @@ def lower_element(prog, el, cfg):
     raise NotImplementedError(f'element class {name} is outside the hot-path contract')
 
 
-def lower_line(elements, *, synrad=False, exact_drifts=False, device=None):
+def lower_line(elements, *, synrad=False, exact_drifts=False, device=None, backtrack=False):
     """Lowers a sequence of host elements.  Returns the `Program`.  `device`: where the
-    records of in-line beam monitors live (their address goes into the program)."""
-    cfg = dict(synrad=bool(synrad), exact_drifts=bool(exact_drifts), device=device)
+    records of in-line beam monitors live (their address goes into the program).
+    `backtrack`: every element as its inverse map (what the reference's classes do under
+    XS_FLAG_BACKTRACK); the caller passes the elements in REVERSE order (tracker.py:628-646)."""
+    cfg = dict(synrad=bool(synrad), exact_drifts=bool(exact_drifts), device=device,
+               backtrack=bool(backtrack))
     prog = Program()
     cache = {}
     for el in elements:

@@ -102,6 +102,8 @@ class Tracker:
         self.num_elements = len(line.element_names)
         self._config_key = None
         self._lattice = None
+        self._back_lattice = None       # the inverse maps in reverse order, built on first use
+        self._back_key = None
         self.program = None
         self._ensure_lattice()
 
@@ -142,6 +144,26 @@ class Tracker:
         # the C-ABI handle; raises unless `self.device` is a CUDA device (no CPU fallback)
         return _cabi.Lattice(fused, plain, self.line_length, self.device)
 
+    def _ensure_back_lattice(self):
+        """The lattice XS_FLAG_BACKTRACK stands for: every element lowered as its inverse map
+        (lowering.lower_line(backtrack=True)), in reverse order -- the kernel then runs it
+        forwards like any other program."""
+        key = self._current_config_key()
+        if self._back_lattice is not None and key == self._back_key:
+            return
+        prog = lowering.lower_line(list(reversed(self.line.elements)), synrad=key[0],
+                                   exact_drifts=key[1], device=self.device, backtrack=True)
+        fused = prog.finish(fused=True) if self.fuse else (None, None)
+        plain = prog.finish(fused=False)
+        if self._back_lattice is not None:
+            self._back_lattice.close()
+        self._back_lattice = self._make_lattice(fused, plain)
+        if prog.monitors or prog.last_turns_monitors:
+            for mm in prog.monitors + prog.last_turns_monitors:
+                mm.allocate(self.device)
+            self._back_lattice.set_inline_monitors(prog.monitors, prog.last_turns_monitors)
+        self._back_key = key[:3] + (mutation_count(),)
+
     # -- monitor ------------------------------------------------------------
     def _get_monitor(self, particles, turn_by_turn_monitor, num_turns):
         if turn_by_turn_monitor is None or turn_by_turn_monitor is False:
@@ -163,11 +185,19 @@ class Tracker:
     # -- tracking -----------------------------------------------------------
     def track(self, particles, ele_start=0, ele_stop=None, num_elements=None, num_turns=None,
               turn_by_turn_monitor=None, freeze_longitudinal=False, time=False,
-              _force_no_end_turn_actions=False):
+              _force_no_end_turn_actions=False, backtrack=False):
         line = self.line
         if particles.device != self.device:
             raise ValueError(f'particles are on {particles.device}, tracker on {self.device}')
         self._ensure_lattice()
+        if backtrack is not False:      # tracker.py:1222-1235
+            if isinstance(backtrack, str):
+                assert backtrack == 'force'
+            elif not line._is_backtrackable:
+                raise ValueError('This line is not backtrackable.')
+            if turn_by_turn_monitor not in (None, False):
+                raise NotImplementedError('turn-by-turn monitor while backtracking')
+            self._ensure_back_lattice()
 
         # start position (tracker.py:1252-1266)
         if particles.start_tracking_at_element >= 0:
@@ -219,14 +249,22 @@ class Tracker:
             ev0.record(torch.cuda.current_stream(self.device))
 
         # at most three launches, as the reference issues them (tracker.py:1372-1436)
-        self._lattice.track(particles, num_turns=1, ele_start=ele_start,
-                            num_ele_track=plan.head, flag_end_turn_actions=plan.head_ends_turn,
-                            **common)
-        if plan.full_turns > 0:
-            self._track_middle(particles, plan.full_turns, plan.full_turns_end_turn, common)
-        if plan.tail > 0:
-            self._lattice.track(particles, num_turns=1, ele_start=0, num_ele_track=plan.tail,
-                                flag_end_turn_actions=False, **common)
+        if backtrack is not False:
+            self._backtrack_pass(particles, ele_start, plan.head, plan.head_ends_turn, common)
+            for _ in range(plan.full_turns):
+                self._backtrack_pass(particles, 0, self.num_elements, plan.full_turns_end_turn,
+                                     common)
+            if plan.tail > 0:
+                self._backtrack_pass(particles, 0, plan.tail, False, common)
+        else:
+            self._lattice.track(particles, num_turns=1, ele_start=ele_start,
+                                num_ele_track=plan.head,
+                                flag_end_turn_actions=plan.head_ends_turn, **common)
+            if plan.full_turns > 0:
+                self._track_middle(particles, plan.full_turns, plan.full_turns_end_turn, common)
+            if plan.tail > 0:
+                self._lattice.track(particles, num_turns=1, ele_start=0, num_ele_track=plan.tail,
+                                    flag_end_turn_actions=False, **common)
 
         if time:
             ev1.record(torch.cuda.current_stream(self.device))
@@ -236,6 +274,29 @@ class Tracker:
             line.time_last_track = None
         line.record_last_track = monitor
         self.record_last_track = monitor
+
+    def _backtrack_pass(self, particles, ele_start, num_ele_track, end_turn_actions, common):
+        """One pass of `track_line` under XS_FLAG_BACKTRACK (tracker.py:626-646, 702-731):
+        the turn bookkeeping FIRST (increment_at_turn_backtrack,
+        local_particle_custom_api.h:88-101: at_turn - 1, at_element = len(line), s = line
+        length), then the elements ele_start .. ele_start + num_ele_track - 1 from the last
+        to the first, each as its inverse, at_element counted DOWN.  The kernel runs the
+        reversed inverse lattice forwards; it counts at_element up, mirrored here."""
+        ff = particles._fields
+        if end_turn_actions:
+            act = ff['state'] > 0
+            ff['at_turn'][act] -= 1
+            ff['at_element'][act] = self.num_elements
+            if self.line.reset_s_at_end_turn:
+                ff['s'][act] = self.line_length
+        if num_ele_track <= 0:
+            return
+        at0 = ff['at_element'].clone()
+        self._back_lattice.track(
+            particles, num_turns=1,
+            ele_start=self.num_elements - (ele_start + num_ele_track),
+            num_ele_track=num_ele_track, flag_end_turn_actions=False, **common)
+        ff['at_element'].copy_(2 * at0 - ff['at_element'])
 
     def _track_middle(self, particles, num_turns, flag_end_turn_actions, common):
         """Full turns.  With `compact_every=N` the turns are issued in chunks of N
