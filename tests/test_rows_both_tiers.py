@@ -372,7 +372,7 @@ def test_unsupported_flags_are_rejected(on_gpu):
     dev = _build(line, on_gpu)
     p = common.gaussian_particles(line, 4, 1, common.SIGMAS['toy'], device=dev)
     with pytest.raises(NotImplementedError):
-        line.track(p, backtrack=True)
+        line.track(p, backtrack=True, turn_by_turn_monitor=True)
     if on_gpu:
         line.track_flags['XS_FLAG_SR_TAPER'] = True
         with pytest.raises(Exception):

@@ -223,7 +223,9 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
                          uint32_t variant_flags, void* cuda_stream) {
     if (!L || !particles) return fail(XTB_E_INVALID, "null argument");
     if (track_flags & (1ull << XTB_FLAG_BACKTRACK))
-        return fail(XTB_E_UNSUPPORTED, "backtracking is not part of the contract");
+        return fail(XTB_E_UNSUPPORTED, "XS_FLAG_BACKTRACK: backtracking is lowered on the host (create the lattice from "
+                                       "the inverse maps in reverse order, lowering.lower_line(backtrack=True)); "
+                                       "the kernel takes no such flag");
     if (track_flags & ((1ull << XTB_FLAG_SR_TAPER) | (1ull << XTB_FLAG_SR_KICK_SAME_AS_FIRST)))
         return fail(XTB_E_UNSUPPORTED, "single-particle twiss flags (SR_TAPER / SR_KICK_SAME_AS_FIRST)");
     if (ele_start < 0 || num_ele_track < 0

@@ -190,6 +190,8 @@ class Tracker:
         if particles.device != self.device:
             raise ValueError(f'particles are on {particles.device}, tracker on {self.device}')
         self._ensure_lattice()
+        if backtrack is False and line.track_flags.get('XS_FLAG_BACKTRACK', False):
+            backtrack = 'force'         # the flag set by hand: what the reference's kernel reads
         if backtrack is not False:      # tracker.py:1222-1235
             if isinstance(backtrack, str):
                 assert backtrack == 'force'
@@ -239,7 +241,8 @@ class Tracker:
             variant |= _cabi.VARIANT_PHILOX
         common = dict(flag_reset_s_at_end_turn=line.reset_s_at_end_turn,
                       flag_monitor=flag_monitor, monitor=monitor,
-                      track_flags=line.get_flags_register(),
+                      # (backtracking is resolved here, in the lowering: the kernel never sees it)
+                      track_flags=line.get_flags_register() & ~1,
                       global_xy_limit=float(line.config.get('XTRACK_GLOBAL_XY_LIMIT', 1.0)),
                       variant_flags=variant)
 
