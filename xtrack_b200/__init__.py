@@ -13,5 +13,6 @@ from .elements import (Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupo
 from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
                        BeamSizeMonitor, BeamProfileMonitor)
 from .line import Line
+from .loss_location_refinement import LossLocationRefinement
 
 __version__ = '0.1.0'

@@ -137,6 +137,7 @@ class BeamElement:
     allow_rot_and_shift = True
     behaves_like_drift = False
     has_backtrack = False
+    allow_loss_refinement = False      # backtracking through it while refining a loss location
     needs_rng = False
     iscollective = False
 
@@ -246,6 +247,7 @@ class BeamElement:
 
 
 class Marker(BeamElement):
+    allow_loss_refinement = True
     allow_rot_and_shift = False
     behaves_like_drift = True
     has_backtrack = True
@@ -256,6 +258,7 @@ class Marker(BeamElement):
 
 
 class Drift(BeamElement):
+    allow_loss_refinement = True
     _dict_fields = ('length', 'model')
     _model_table = MODEL_DRIFT
     isthick = True
@@ -270,6 +273,7 @@ class Drift(BeamElement):
 
 
 class DriftExact(BeamElement):
+    allow_loss_refinement = True
     _dict_fields = ('length',)
     isthick = True
     allow_rot_and_shift = False
@@ -342,6 +346,7 @@ class Multipole(_Magnet):
 
 
 class _StraightMagnet(_Magnet):
+    allow_loss_refinement = True
     isthick = True
     _main = None     # ('k1', 'k1s') ...
 
@@ -375,6 +380,7 @@ class Octupole(_StraightMagnet):
 
 
 class _BendCommon(_Magnet):
+    allow_loss_refinement = True
     isthick = True
     _model_table = MODEL_CURVED
 
@@ -571,6 +577,7 @@ class RBend(_BendCommon):
 
 
 class Cavity(BeamElement):
+    allow_loss_refinement = True
     _model_table = MODEL_RF
     _dict_fields = ('length', 'voltage', 'frequency', 'lag', 'phase', 'harmonic', 'lag_taper', 'phase_taper', 'absolute_time', 'num_kicks', 'model', 'integrator')
     isthick = True
@@ -592,6 +599,7 @@ class CrabCavity(BeamElement):
     """beam_elements/crab_cavity.py:51-63, elements_src/crab_cavity.h: an RF dipole kick
     (track_rf.h:116-156, `transverse_voltage`); `lag` in degrees (deprecated there), `phase` in
     radians, both added."""
+    allow_loss_refinement = True
     isthick = True
     has_backtrack = True
     _model_table = MODEL_RF
@@ -611,6 +619,7 @@ class CrabCavity(BeamElement):
 
 
 class RFMultipole(BeamElement):
+    allow_loss_refinement = True
     _dict_fields = ('order', 'knl', 'ksl', 'pn', 'ps', 'phase_n', 'phase_s', 'voltage', 'frequency', 'lag', 'phase', 'absolute_time')
     """rf_multipole.py:51-65; constructor `_HasKnlKsl.__init__` with the phase
     arrays (pn/ps in degrees, phase_n/phase_s in radians)."""
@@ -677,6 +686,7 @@ class DipoleEdge(BeamElement):
 
 
 class SRotation(BeamElement):
+    allow_loss_refinement = True
     _dict_fields = ('cos_z', 'sin_z')
     allow_rot_and_shift = False
     has_backtrack = True
@@ -697,6 +707,7 @@ class SRotation(BeamElement):
 
 
 class XYShift(BeamElement):
+    allow_loss_refinement = True
     _dict_fields = ('dx', 'dy')
     allow_rot_and_shift = False
     has_backtrack = True
@@ -708,6 +719,7 @@ class XYShift(BeamElement):
 
 
 class Translation(BeamElement):
+    allow_loss_refinement = True
     _dict_fields = ('shift_x', 'shift_y')
     """beam_elements/translation.py:15-40, elements_src/translation.h:13-26 (supersedes the
     deprecated XYShift)."""
@@ -721,6 +733,7 @@ class Translation(BeamElement):
 
 
 class Rotation(BeamElement):
+    allow_loss_refinement = True
     _dict_fields = ('rot_s_rad', 'rot_x_rad', 'rot_y_rad', 'seq')
     """beam_elements/rotation.py:14-100, elements_src/rotation.h:13-60: up to three frame
     rotations about x, y, s in the order `seq` (default 'yxs'); zero angles are skipped."""
@@ -903,13 +916,15 @@ def _make_slice_classes():
                 isthick=thick, _slice_kind=kind, _parent_class=pcls,
                 rot_and_shift_from_parent=from_parent,
                 behaves_like_drift=(kind == 'drift'),
+                allow_loss_refinement=kind in ('thick', 'drift'),
                 __doc__=f'{kind} slice of a {pname} (generated wrapper '
                         f'elements_src/{kind if kind in ("thin", "thick", "drift") else "thin"}'
                         f'_slice_*.h of the reference)'))
     for cname, pcls in (('DriftSlice', Drift), ('DriftExactSlice', DriftExact)):
         out[cname] = type(cname, (_Slice,), dict(
             isthick=True, _slice_kind='drift', _parent_class=pcls,
-            rot_and_shift_from_parent=False, behaves_like_drift=True))
+            rot_and_shift_from_parent=False, behaves_like_drift=True,
+            allow_loss_refinement=True))
     return out
 
 

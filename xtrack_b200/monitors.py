@@ -24,6 +24,7 @@ class ParticlesMonitor(BeamElement):
     allow_rot_and_shift = False
     behaves_like_drift = True
     has_backtrack = True
+    allow_loss_refinement = True
 
     def __init__(self, start_at_turn=None, stop_at_turn=None, n_repetitions=None,
                  repetition_period=None, num_particles=None, particle_id_range=None,
@@ -121,6 +122,7 @@ class LastTurnsMonitor(BeamElement):
     _mutation_tracked = False
     allow_rot_and_shift = False
     behaves_like_drift = True
+    allow_loss_refinement = True
 
     properties = ('particle_id', 'at_turn', 'x', 'px', 'y', 'py', 'delta', 'zeta')
 
