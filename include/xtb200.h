@@ -110,6 +110,14 @@ int xtb_lattice_set_inline_monitors(xtb_lattice_handle h,
                                     const xtb_monitor_t* mons, size_t n_mons,
                                     const xtb_last_turns_monitor_t* ltms, size_t n_ltms);
 
+/* Inverse-CDF tables of the `quantum-kick` radiation model (magnet bodies with radiation_flag
+ * 3; xtrack/headers/synrad_spectrum.h:257-406, data of the reference's generated header
+ * synrad_total_energy_tables.h).  `blob` is HOST memory, copied to the lattice's device;
+ * layout in doubles: [0] n_left [1] n_center [2] n_right [3] tail probability max [4] direct
+ * table max (32) [5..7] 0, the left u / centre u / right v probability grids, then the tables
+ * log(X_N) for N = 1..32, 64, 128, 256, each n_left + n_center + n_right long. */
+int xtb_lattice_set_synrad_tables(xtb_lattice_handle h, const double* blob, size_t n_doubles);
+
 /* One `track_line` launch; argument meaning of xtrack/tracker.py:546-564.
  * Asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream). */
 int xtb_track(xtb_lattice_handle h, const xtb_particles_t* particles,

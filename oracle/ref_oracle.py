@@ -127,6 +127,7 @@ def load(variant='serial'):
                                              ct.POINTER(ct.c_uint32), ct.c_int]
         lib.xt_ref_num_threads.restype = ct.c_int
         lib.xt_ref_set_num_threads.argtypes = [ct.c_int]
+        lib.xt_ref_set_synrad_tables.argtypes = [ct.c_void_p]
         _LIBS[variant] = lib
     return _LIBS[variant]
 
@@ -341,6 +342,21 @@ def track_line(hp, ref_elements, *, num_turns, ele_start, num_ele_track,
         int(bool(flag_end_turn_actions)), int(bool(flag_reset_s_at_end_turn)),
         int(flag_monitor), int(num_ele_line or len(ref_elements.ptrs)),
         float(line_length), mon_ptr, int(track_flags))
+
+
+_synrad_tables_keep = {}
+
+
+def set_synrad_tables(blob, variant='synrad'):
+    """Hands the quantum-kick tables (xtrack_b200.synrad_tables blob) to the reference code."""
+    lib = load(variant)
+    if blob is None:
+        _synrad_tables_keep.pop(variant, None)
+        lib.xt_ref_set_synrad_tables(None)
+        return
+    arr = np.ascontiguousarray(blob, dtype=np.float64)
+    _synrad_tables_keep[variant] = arr
+    lib.xt_ref_set_synrad_tables(arr.ctypes.data_as(ct.c_void_p))
 
 
 def init_rand_gen(hp, seeds, variant='serial'):

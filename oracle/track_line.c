@@ -27,6 +27,16 @@ double xtb_oracle_global_xy_limit = 1.0;       /* line.config XTRACK_GLOBAL_XY_L
 
 void xt_ref_set_global_xy_limit(double v){ xtb_oracle_global_xy_limit = v; }
 
+/* inverse-CDF tables of the quantum-kick radiation model: the blob the product uploads to the
+ * GPU (shim/xtrack/headers/synrad_total_energy_tables.h); the caller keeps it alive */
+void xt_ref_set_synrad_tables(const double* blob){
+#ifdef XTB_ORACLE_SYNRAD_TABLES_SHIM_H
+    xtb_qk_blob = blob;
+#else
+    (void) blob;
+#endif
+}
+
 /* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline wants every core */
 void xt_ref_set_num_threads(int n){
 #ifdef XO_CONTEXT_CPU_OPENMP

@@ -72,9 +72,14 @@ class HostSimLattice:
         self._ltms = (_cabi.XtbLastTurnsMonitor * max(1, len(last_turns)))(
             *[_cabi.last_turns_struct(m) for m in last_turns])
 
+    def set_synrad_tables(self, blob):
+        self._synrad_tables = np.ascontiguousarray(blob, dtype=np.float64)
+
     def track(self, particles, *, num_turns, ele_start, num_ele_track, flag_end_turn_actions,
               flag_reset_s_at_end_turn, flag_monitor=0, monitor=None, track_flags=0,
               global_xy_limit=1.0, variant_flags=0, stream=None):
+        tt = getattr(self, '_synrad_tables', None)
+        load().xtb_hostsim_set_synrad_tables(ct.c_void_p(tt.ctypes.data if tt is not None else None))
         pst = _cabi.particles_struct(particles)
         mst = ct.byref(_cabi.monitor_struct(monitor)) if monitor is not None else None
         na = 0xffffffff

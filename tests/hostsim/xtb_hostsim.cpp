@@ -121,6 +121,10 @@ extern "C" void xtb_hostsim_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32
     for (int j = 0; j < 4; ++j) out[j] = b[j];
 }
 
+// (test hook) inverse-CDF tables of the quantum-kick model for the following track calls
+static const double* g_synrad_tables = nullptr;
+extern "C" void xtb_hostsim_set_synrad_tables(const double* blob) { g_synrad_tables = blob; }
+
 extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_offset,
                                   const xtb_particles_t* p, int64_t num_turns, int32_t ele_start,
                                   int32_t num_ele_track, int32_t flag_end_turn_actions,
@@ -134,7 +138,7 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
         const uint64_t* w0 = words + elem_offset[ele_start];
         const uint64_t* w1 = words + elem_offset[ele_start + num_ele_track];
         for (const uint64_t* pw = w0; pw < w1; pw += (*pw >> 16) & 0xffffu)
-            if ((*pw & 0xffu) == XTB_OP_MAGNET_BODY && (((uint32_t) (*pw >> 32) >> 10) & 3u) == 2u) npt_heavy = 1;
+            if ((*pw & 0xffu) == XTB_OP_MAGNET_BODY && (((uint32_t) (*pw >> 32) >> 10) & 3u) >= 2u) npt_heavy = 1;
     }
     npt &= 0xff;
     XtbTrackArgs a;
@@ -160,6 +164,7 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
     a.ignore_local = (int32_t) ((track_flags >> XTB_FLAG_IGNORE_LOCAL_APERTURE) & 1);
     a.kill_cavity_kick = (int32_t) ((track_flags >> XTB_FLAG_KILL_CAVITY_KICK) & 1);
     a.rng_philox = (variant & XTB_VARIANT_PHILOX) ? 1 : 0;
+    a.synrad_tables = g_synrad_tables;
     a.line_length = line_length;
     a.global_xy_limit = global_xy_limit;
     const bool synrad = variant & XTB_VARIANT_SYNRAD, frz = variant & XTB_VARIANT_FREEZE_LONG;

@@ -87,6 +87,7 @@ def load():
     lib.xtb_lattice_destroy.argtypes = [ct.c_void_p]
     lib.xtb_lattice_set_inline_monitors.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_size_t,
                                                     ct.c_void_p, ct.c_size_t]
+    lib.xtb_lattice_set_synrad_tables.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_size_t]
     lib.xtb_track.argtypes = [ct.c_void_p, ct.POINTER(XtbParticles), ct.c_int64, ct.c_int32,
                               ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32,
                               ct.POINTER(XtbMonitor), ct.c_uint64, ct.c_double, ct.c_uint32,
@@ -184,6 +185,11 @@ class Lattice:
             *[last_turns_struct(m) for m in last_turns])
         _check(lib.xtb_lattice_set_inline_monitors(self.handle, mm, len(monitors), ll,
                                                    len(last_turns)))
+
+    def set_synrad_tables(self, blob):
+        """Inverse-CDF tables of the quantum-kick radiation model (synrad_tables.make_blob)."""
+        blob = np.ascontiguousarray(blob, dtype=np.float64)
+        _check(load().xtb_lattice_set_synrad_tables(self.handle, blob.ctypes.data, len(blob)))
 
     def track(self, particles, *, num_turns, ele_start, num_ele_track, flag_end_turn_actions,
               flag_reset_s_at_end_turn, flag_monitor=0, monitor=None, track_flags=0,

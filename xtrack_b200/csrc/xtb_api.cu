@@ -42,7 +42,8 @@ struct xtb_program {
     size_t n_words = 0, n_tiles = 0;
     bool has_heavy = false;
     bool has_beam_mon = false;     // XTB_OP_BEAM_MON / XTB_OP_BEAM_PROFILE present
-    bool has_quantum = false;      // a magnet body with radiation_flag 2 (photon emission)
+    bool has_quantum = false;      // a magnet body with radiation_flag 2 / 3 (random emission)
+    bool has_qk = false;           // radiation_flag 3: needs the inverse-CDF tables
     uint64_t* d_prog = nullptr;          // IMAGE: tile k = its ops + one XTB_OP_END op (2 words)
     uint32_t* d_tile_off = nullptr;      // image offsets [n_tiles + 1]
     std::vector<uint32_t> elem_offset;   // host copy [n_elements + 1], XTB_NOT_ADDRESSABLE allowed
@@ -63,6 +64,7 @@ struct xtb_lattice {
     xtb_program fused, plain;
     xtb_monitor_t* d_mon;
     xtb_last_turns_monitor_t* d_ltm;
+    double* d_synrad_tables;      // quantum-kick model (xtb_lattice_set_synrad_tables)
 };
 
 extern "C" const char* xtb_last_error_string(void) { return g_err; }
@@ -92,7 +94,8 @@ static int program_prepare(xtb_program& G, const uint64_t* words, size_t n_words
             if (nw < 2 || (nw & 1u) || pc + nw > w1) return fail(XTB_E_INVALID, "malformed op in program");
             if (op >= XTB_HEAVY_FIRST) G.has_heavy = true;
             if (op == XTB_OP_BEAM_MON || op == XTB_OP_BEAM_PROFILE) G.has_beam_mon = true;
-            if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) == 2u) G.has_quantum = true;
+            if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) >= 2u) G.has_quantum = true;
+            if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) == 3u) G.has_qk = true;
             pc += nw;
         }
         if (w1 - G.tile_off.back() > XTB_TILE_WORDS) G.tile_off.push_back(w0);
@@ -149,6 +152,7 @@ extern "C" int xtb_lattice_create(const uint64_t* fused_words, size_t n_fused_wo
     L->line_length = line_length;
     L->d_mon = nullptr;
     L->d_ltm = nullptr;
+    L->d_synrad_tables = nullptr;
     int rc = program_prepare(L->plain, plain_words, n_plain_words, plain_elem_offset, n_elements);
     if (rc == XTB_OK) {
         for (size_t e = 0; e <= n_elements; ++e)
@@ -188,6 +192,7 @@ extern "C" int xtb_lattice_destroy(xtb_lattice_handle L) {
     program_free(L->fused);
     if (L->d_mon) cudaFree(L->d_mon);
     if (L->d_ltm) cudaFree(L->d_ltm);
+    if (L->d_synrad_tables) cudaFree(L->d_synrad_tables);
     cudaSetDevice(prev);
     delete L;
     return XTB_OK;
@@ -211,6 +216,22 @@ extern "C" int xtb_lattice_set_inline_monitors(xtb_lattice_handle L, const xtb_m
         CUDA_TRY(cudaMemcpy(L->d_ltm, ltms, n_ltms * sizeof(xtb_last_turns_monitor_t),
                             cudaMemcpyHostToDevice));
     }
+    cudaSetDevice(prev);
+    return XTB_OK;
+}
+
+extern "C" int xtb_lattice_set_synrad_tables(xtb_lattice_handle L, const double* blob, size_t n_doubles) {
+    if (!L || !blob || n_doubles < 8) return fail(XTB_E_INVALID, "null / short table blob");
+    const size_t per_table = (size_t) blob[0] + (size_t) blob[1] + (size_t) blob[2];
+    const size_t n_tables = (size_t) blob[4] + 3;      // N = 1 .. direct max, 64, 128, 256
+    if (n_doubles != 8 + per_table * (1 + n_tables))
+        return fail(XTB_E_INVALID, "table blob does not have the stated layout");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(L->device));
+    if (L->d_synrad_tables) { cudaFree(L->d_synrad_tables);  L->d_synrad_tables = nullptr; }
+    CUDA_TRY(cudaMalloc(&L->d_synrad_tables, n_doubles * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(L->d_synrad_tables, blob, n_doubles * sizeof(double), cudaMemcpyHostToDevice));
     cudaSetDevice(prev);
     return XTB_OK;
 }
@@ -276,6 +297,9 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     a.rng_philox = (variant_flags & XTB_VARIANT_PHILOX) ? 1 : 0;
     a.line_length = L->line_length;
     a.global_xy_limit = global_xy_limit;
+    a.synrad_tables = L->d_synrad_tables;
+    if (G->has_qk && (variant_flags & XTB_VARIANT_SYNRAD) && !L->d_synrad_tables)
+        return fail(XTB_E_INVALID, "quantum-kick radiation needs xtb_lattice_set_synrad_tables first");
 
     unsigned variant = 0;
     if (G->has_heavy || (variant_flags & XTB_VARIANT_SYNRAD)) variant |= 1u;

@@ -38,6 +38,7 @@ struct XtbTrackArgs {
     int32_t rng_philox;          // the particles' generator state is (key, counter) of Philox4x32-10
     double line_length;
     double global_xy_limit;
+    const double* synrad_tables; // quantum-kick model: inverse-CDF tables (xtb_thick.cuh::QkTables)
     // particle slots [slot_begin, slot_end) of the caller's SoA handled by this grid (a
     // track call may be split into several grids, see xtb_kernel_inst.cu::launch)
     int64_t slot_begin, slot_end;

@@ -709,6 +709,181 @@ __device__ __noinline__ void synrad_emit_photons(PState& P, const PSlot& G, cons
     }
 }
 
+// ---- quantum-kick model (radiation_flag 3): the TOTAL energy radiated in a slice ----------
+// synrad_spectrum.h:220-459.  The number of photons is drawn (Poisson), the sum of their
+// energies comes from tabulated inverse CDFs of the sum of N photon energies (N = 1..32 and
+// 64, 128, 256; headers/_generate_synrad_total_energy_tables.py) -- a few table look-ups
+// instead of hundreds of rejection-sampled photons.  The tables are data, uploaded with the
+// lattice (xtb_lattice_set_synrad_tables); layout of the blob, in doubles:
+//   [0] n_left  [1] n_center  [2] n_right  [3] tail probability max  [4] direct table max (32)
+//   [5..7] reserved, then the left u grid, the centre u grid, the right v grid, then the
+//   tables log(X_N) for N = 1..32, 64, 128, 256, each n_left + n_center + n_right long.
+struct QkTables {
+    const double* grid_l;
+    const double* grid_c;
+    const double* grid_r;
+    const double* tables;
+    int n_l, n_c, n_r, direct_max;
+    double tail_max;
+};
+__device__ __forceinline__ QkTables qk_tables(const double* __restrict__ blob) {
+    QkTables t;
+    t.n_l = (int) blob[0];  t.n_c = (int) blob[1];  t.n_r = (int) blob[2];
+    t.tail_max = blob[3];
+    t.direct_max = (int) blob[4];
+    t.grid_l = blob + 8;
+    t.grid_c = t.grid_l + t.n_l;
+    t.grid_r = t.grid_c + t.n_c;
+    t.tables = t.grid_r + t.n_r;
+    return t;
+}
+// table of the sum of n photons (n <= direct_max, or 64 / 128 / 256)
+__device__ __forceinline__ const double* qk_table_of(const QkTables& t, const int64_t n) {
+    const int64_t size = (int64_t) t.n_l + t.n_c + t.n_r;
+    int64_t idx;
+    if (n <= t.direct_max) idx = n - 1;
+    else if (n == 64) idx = t.direct_max;
+    else if (n == 128) idx = t.direct_max + 1;
+    else idx = t.direct_max + 2;
+    return t.tables + idx * size;
+}
+
+// synrad_gen_photon_count, synrad_spectrum.h:220-245
+static __device__ __noinline__ int64_t synrad_gen_photon_count(RadCtx& c, const double average_nphotons) {
+    if (average_nphotons <= 0.0) return 0;
+    if (average_nphotons < 700.0) {
+        const double threshold = exp(-average_nphotons);
+        double product = 1.0;
+        int64_t nphot = -1;
+        do {
+            nphot++;
+            product *= rand_uniform(c);
+        } while (product > threshold && !c.rng_error);
+        return nphot;
+    }
+    double n = rand_exponential(c);
+    int64_t nphot = 0;
+    while (n < average_nphotons && !c.rng_error) {
+        nphot++;
+        n += rand_exponential(c);
+    }
+    return nphot;
+}
+
+// synrad_total_energy_find_grid_index_direct_segment, synrad_spectrum.h:257-288
+__device__ __forceinline__ int64_t qk_find_index(const double value, const double* __restrict__ grid,
+                                                 const int64_t size, const bool is_log_spaced) {
+    if (value <= grid[0]) return 0;
+    if (value >= grid[size - 1]) return size - 2;
+    if (is_log_spaced) {
+        if (value < grid[1]) return 0;
+        const double position = ((log(value) - log(grid[1])) / (log(grid[size - 1]) - log(grid[1]))
+                                 * (size - 2));
+        int64_t i_low = 1 + (int64_t) floor(position);
+        if (i_low < 0) i_low = 0;
+        if (i_low > size - 2) i_low = size - 2;
+        return i_low;
+    }
+    const double du = (grid[size - 1] - grid[0]) / (size - 1);
+    int64_t i_low = (int64_t) floor((value - grid[0]) / du);
+    if (i_low < 0) i_low = 0;
+    if (i_low > size - 2) i_low = size - 2;
+    return i_low;
+}
+// synrad_total_energy_interpolate_segment, synrad_spectrum.h:291-325
+__device__ __forceinline__ double qk_interp_segment(const double value, const double* __restrict__ grid,
+                                                    const double* __restrict__ table, const int64_t offset,
+                                                    const int64_t size, const bool is_log_spaced) {
+    if (value <= grid[0]) return table[offset];
+    if (value >= grid[size - 1]) return table[offset + size - 1];
+    int64_t i_low = qk_find_index(value, grid, size, is_log_spaced);
+    if (i_low < 0) i_low = 0;
+    if (i_low >= size - 1) i_low = size - 2;
+    const int64_t i_high = i_low + 1;
+    const double u_low = grid[i_low], u_high = grid[i_high];
+    double w;
+    if (is_log_spaced && u_low > 0.0 && value > 0.0) w = (log(value) - log(u_low)) / (log(u_high) - log(u_low));
+    else w = (value - u_low) / (u_high - u_low);
+    return (1.0 - w) * table[offset + i_low] + w * table[offset + i_high];
+}
+// synrad_gen_total_energy_normalized_from_log_table, synrad_spectrum.h:327-380
+__device__ __forceinline__ double qk_sample(RadCtx& c, const QkTables& t, const double* __restrict__ table) {
+    const double u = rand_uniform(c);
+    double log_value;
+    if (u < t.tail_max) {
+        log_value = qk_interp_segment(u, t.grid_l, table, 0, t.n_l, true);
+    } else if (u <= 1.0 - t.tail_max) {
+        log_value = qk_interp_segment(u, t.grid_c, table, t.n_l, t.n_c, false);
+    } else {
+        const double v = 1.0 - u;
+        log_value = qk_interp_segment(v, t.grid_r, table, (int64_t) t.n_l + t.n_c, t.n_r, true);
+    }
+    return exp(log_value);
+}
+
+// synrad_emit_total_energy_loss, synrad_spectrum.h:408-459
+template <bool FRZ>
+__device__ __noinline__ void synrad_emit_total_energy_loss(PState& P, const PSlot& G, const XtbTrackArgs& a,
+                                                           const double B_T, const double lpath) {
+    if (fabs(B_T) < 1e-4) return;
+    const double mass0 = a.part.mass0;
+    const double q0 = a.part.q0;
+    const double gamma0 = G.ld(F_GAMMA0);
+    const double beta0 = G.ld(F_BETA0);
+
+    RadCtx c;
+    c.r.s1 = G.ldu(F_RNG_S1);  c.r.s2 = G.ldu(F_RNG_S2);
+    c.r.s3 = G.ldu(F_RNG_S3);  c.r.s4 = G.ldu(F_RNG_S4);
+    c.seeded = !(c.r.s1 == 0 && c.r.s2 == 0 && c.r.s3 == 0 && c.r.s4 == 0);
+    c.rng_error = false;
+    c.philox = a.rng_philox != 0;
+    c.ph.have = false;
+
+    const double n_avg = synrad_average_number_of_photons(mass0, q0, beta0 * gamma0, B_T, lpath);
+    const int64_t nphot = synrad_gen_photon_count(c, n_avg);
+    double total = 0.0;
+    if (nphot > 0 && !c.rng_error) {
+        const QkTables t = qk_tables(a.synrad_tables);
+        int64_t left = nphot;
+        while (left > t.direct_max && !c.rng_error) {
+            int64_t chunk = 1;                      // synrad_largest_power_of_two_leq
+            while (chunk <= left / 2) chunk *= 2;
+            if (chunk > 256) chunk = 256;
+            total += qk_sample(c, t, qk_table_of(t, chunk));
+            left -= chunk;
+        }
+        if (left > 0) total += qk_sample(c, t, qk_table_of(t, left));
+    }
+    G.stu(F_RNG_S1, c.r.s1);  G.stu(F_RNG_S2, c.r.s2);
+    G.stu(F_RNG_S3, c.r.s3);  G.stu(F_RNG_S4, c.r.s4);
+    if (c.rng_error) {       // RNG_ERR_SEEDS_NOT_SET, uniform.h:40-43
+        kill_particle<FRZ>(P, G, -20);
+        return;
+    }
+    if (nphot == 0) return;
+
+    const double Q0_coulomb = fabs(q0) * XTB_QELEM;
+    const double mass0_kg = mass0 * XTB_QELEM / XTB_C_LIGHT / XTB_C_LIGHT;
+    const double P0_J = mass0_kg * beta0 * gamma0 * XTB_C_LIGHT;
+    const double curv = B_T / P0_J * Q0_coulomb;
+    const double gamma = gamma0 * (1 + P.delta);
+    const double p0c = G.ld(F_P0C);
+    const double initial_energy = sqrt(p0c * p0c + mass0 * mass0) + G.ld(F_PTAU) * p0c;
+    const double c1 = 1.5 * 1.973269804593025e-07;
+    const double energy_critical = c1 * (gamma * gamma * gamma0) * curv;
+    double energy_loss_total = total * energy_critical;
+    if (energy_loss_total >= initial_energy) energy_loss_total = initial_energy;
+    if (energy_loss_total >= initial_energy) {
+        P.state = -10;       // XT_LOST_ALL_E_IN_SYNRAD
+    } else {
+        const double energy = initial_energy - energy_loss_total;
+        const double f_t = energy / initial_energy;
+        update_delta<FRZ>(P, G, beta0, (P.delta + 1) * f_t - 1);
+        P.px *= f_t;
+        P.py *= f_t;
+    }
+}
+
 // evaluate_field_from_strengths, track_magnet_kick.h:265-370 (no solenoid terms)
 __device__ __forceinline__ void field_from_strengths(const BodyPar& b, const double p0c, const double q0,
                                                      const double x, const double y, double& Bx_T,
@@ -790,6 +965,8 @@ __device__ __forceinline__ void rad_end(const RadSnapshot& s, PState& P, const P
         synrad_average_kick<FRZ>(P, G, a, B_perp_T, l_path);
     } else if (b.radiation_flag() == 2) {
         synrad_emit_photons<FRZ>(P, G, a, B_perp_T, l_path);
+    } else if (b.radiation_flag() == 3) {
+        synrad_emit_total_energy_loss<FRZ>(P, G, a, B_perp_T, l_path);
     }
 }
 
@@ -892,10 +1069,13 @@ __device__ __forceinline__ void thin_rad_kick_run(PState (&P)[N], const bool (&l
     XTB_LANES { if (!(t0[k] > 1e-280)) bperp[k] = sqrt(t0[k]); }
     XTB_LANES lpath[k] = P[k].rvv * (length - (P[k].zeta - old_zeta[k]));
 
-    if (b.radiation_flag() == 2) {
+    if (b.radiation_flag() >= 2) {
 #pragma unroll 1
-        for (int k = 0; k < N; ++k)
-            if (live[k]) synrad_emit_photons<FRZ>(P[k], G[k], a, bperp[k], lpath[k]);
+        for (int k = 0; k < N; ++k) {
+            if (!live[k]) continue;
+            if (b.radiation_flag() == 2) synrad_emit_photons<FRZ>(P[k], G[k], a, bperp[k], lpath[k]);
+            else synrad_emit_total_energy_loss<FRZ>(P[k], G[k], a, bperp[k], lpath[k]);
+        }
         return;
     }
     // synrad_average_kick (mean model)

@@ -136,6 +136,8 @@ class Tracker:
             mm.allocate(self.device)
         if prog.monitors or prog.last_turns_monitors:
             self._lattice.set_inline_monitors(prog.monitors, prog.last_turns_monitors)
+        if synrad and self.line._extra_config.get('_radiation_model') == 'quantum-kick':
+            self._lattice.set_synrad_tables(self._synrad_tables())
         self.program = prog
         # (allocating the in-line monitors above may have written element fields)
         self._config_key = key[:3] + (mutation_count(),)
@@ -143,6 +145,14 @@ class Tracker:
     def _make_lattice(self, fused, plain):
         # the C-ABI handle; raises unless `self.device` is a CUDA device (no CPU fallback)
         return _cabi.Lattice(fused, plain, self.line_length, self.device)
+
+    def _synrad_tables(self):
+        # (a line may carry its own tables: `line.synrad_tables = synrad_tables.make_blob(...)`)
+        blob = getattr(self.line, 'synrad_tables', None)
+        if blob is None:
+            from . import synrad_tables
+            blob = synrad_tables.load_blob()
+        return blob
 
     def _ensure_back_lattice(self):
         """The lattice XS_FLAG_BACKTRACK stands for: every element lowered as its inverse map
