@@ -244,6 +244,65 @@ GPUFUN int64_t BeamProfileMonitorRecord_len_counts_x(BeamProfileMonitorRecord r)
 GPUFUN int64_t BeamProfileMonitorRecord_len_counts_y(BeamProfileMonitorRecord r){ return r->n_y; }
 GPUFUN double* BeamProfileMonitorRecord_getp1_counts_x(BeamProfileMonitorRecord r, int64_t i){ return r->counts_x + i; }
 GPUFUN double* BeamProfileMonitorRecord_getp1_counts_y(BeamProfileMonitorRecord r, int64_t i){ return r->counts_y + i; }
+
+/* ---- BeamStatsMonitorData (monitors/beam_stats_monitor/beam_stats_monitor.py:60-118, 240-256):
+ *      the scalars, the slot tables, the record of 38 moment arrays (length 0: not kept), the
+ *      touched-record flags and the profile record, as one flat struct; the nested xobjects
+ *      the reference's header asks for are views of it ---- */
+typedef struct BeamStatsMonitorData_s {
+    int64_t start_at_turn, stop_at_turn, every_n_turns, _mode, _num_records, _num_selected_slots,
+            _num_slices, _particle_id_start, _particle_id_stop;
+    double _z_min_edge, _dzeta, _bunch_spacing_zeta;
+    int64_t n_slot_to_selected;
+    int64_t *_slot_to_selected, *_selected_slots;
+    double* field[38];
+    int64_t len_field[38];
+    int64_t* touched;
+    int64_t n_profiles, len_counts;
+    double* counts;
+    int64_t *offsets, *num_bins, *coord_id;
+    double *pmin, *bin_width;
+} *BeamStatsMonitorData;
+typedef BeamStatsMonitorData BeamStatsMonitorRecordData;
+typedef BeamStatsMonitorData BeamStatsMonitorTouchedRecordsData;
+typedef BeamStatsMonitorData BeamStatsMonitorProfileRecordData;
+#define XTB_BSM_I(f) GPUFUN int64_t BeamStatsMonitorData_get_##f(BeamStatsMonitorData el){ return el->f; }
+#define XTB_BSM_D(f) GPUFUN double BeamStatsMonitorData_get_##f(BeamStatsMonitorData el){ return el->f; }
+XTB_BSM_I(start_at_turn) XTB_BSM_I(stop_at_turn) XTB_BSM_I(every_n_turns) XTB_BSM_I(_mode)
+XTB_BSM_I(_num_records) XTB_BSM_I(_num_selected_slots) XTB_BSM_I(_num_slices)
+XTB_BSM_I(_particle_id_start) XTB_BSM_I(_particle_id_stop)
+XTB_BSM_D(_z_min_edge) XTB_BSM_D(_dzeta) XTB_BSM_D(_bunch_spacing_zeta)
+GPUFUN int64_t BeamStatsMonitorData_len__slot_to_selected(BeamStatsMonitorData el){ return el->n_slot_to_selected; }
+GPUFUN int64_t BeamStatsMonitorData_get__slot_to_selected(BeamStatsMonitorData el, int64_t i){ return el->_slot_to_selected[i]; }
+GPUFUN int64_t BeamStatsMonitorData_get__selected_slots(BeamStatsMonitorData el, int64_t i){ return el->_selected_slots[i]; }
+GPUFUN BeamStatsMonitorRecordData BeamStatsMonitorData_getp_data(BeamStatsMonitorData el){ return el; }
+GPUFUN BeamStatsMonitorTouchedRecordsData BeamStatsMonitorData_getp_touched_records(BeamStatsMonitorData el){ return el; }
+GPUFUN BeamStatsMonitorProfileRecordData BeamStatsMonitorData_getp__profile_data(BeamStatsMonitorData el){ return el; }
+#define XTB_BSM_FIELD(f, i) \
+GPUFUN int64_t BeamStatsMonitorRecordData_len_##f(BeamStatsMonitorRecordData r){ return r->len_field[i]; } \
+GPUFUN double* BeamStatsMonitorRecordData_getp1_##f(BeamStatsMonitorRecordData r, int64_t k){ return r->field[i] + k; }
+XTB_BSM_FIELD(num_particles, 0) XTB_BSM_FIELD(sum_beta0_gamma0, 1) XTB_BSM_FIELD(sum_x, 2) 
+XTB_BSM_FIELD(sum_px, 3) XTB_BSM_FIELD(sum_y, 4) XTB_BSM_FIELD(sum_py, 5) 
+XTB_BSM_FIELD(sum_zeta, 6) XTB_BSM_FIELD(sum_delta, 7) XTB_BSM_FIELD(sum_pzeta, 8) 
+XTB_BSM_FIELD(sum_charge_ratio, 9) XTB_BSM_FIELD(sum_mass_ratio, 10) XTB_BSM_FIELD(sum_x_x, 11) 
+XTB_BSM_FIELD(sum_x_px, 12) XTB_BSM_FIELD(sum_x_y, 13) XTB_BSM_FIELD(sum_x_py, 14) 
+XTB_BSM_FIELD(sum_x_zeta, 15) XTB_BSM_FIELD(sum_x_delta, 16) XTB_BSM_FIELD(sum_x_pzeta, 17) 
+XTB_BSM_FIELD(sum_px_px, 18) XTB_BSM_FIELD(sum_px_y, 19) XTB_BSM_FIELD(sum_px_py, 20) 
+XTB_BSM_FIELD(sum_px_zeta, 21) XTB_BSM_FIELD(sum_px_delta, 22) XTB_BSM_FIELD(sum_px_pzeta, 23) 
+XTB_BSM_FIELD(sum_y_y, 24) XTB_BSM_FIELD(sum_y_py, 25) XTB_BSM_FIELD(sum_y_zeta, 26) 
+XTB_BSM_FIELD(sum_y_delta, 27) XTB_BSM_FIELD(sum_y_pzeta, 28) XTB_BSM_FIELD(sum_py_py, 29) 
+XTB_BSM_FIELD(sum_py_zeta, 30) XTB_BSM_FIELD(sum_py_delta, 31) XTB_BSM_FIELD(sum_py_pzeta, 32) 
+XTB_BSM_FIELD(sum_zeta_zeta, 33) XTB_BSM_FIELD(sum_zeta_delta, 34) XTB_BSM_FIELD(sum_zeta_pzeta, 35) 
+XTB_BSM_FIELD(sum_delta_delta, 36) XTB_BSM_FIELD(sum_pzeta_pzeta, 37) 
+GPUFUN int64_t* BeamStatsMonitorTouchedRecordsData_getp1_value(BeamStatsMonitorTouchedRecordsData r, int64_t k){ return r->touched + k; }
+GPUFUN int64_t BeamStatsMonitorProfileRecordData_len_counts(BeamStatsMonitorProfileRecordData r){ return r->len_counts; }
+GPUFUN int64_t BeamStatsMonitorProfileRecordData_len_num_bins(BeamStatsMonitorProfileRecordData r){ return r->n_profiles; }
+GPUFUN double* BeamStatsMonitorProfileRecordData_getp1_counts(BeamStatsMonitorProfileRecordData r, int64_t k){ return r->counts + k; }
+GPUFUN int64_t* BeamStatsMonitorProfileRecordData_getp1_offsets(BeamStatsMonitorProfileRecordData r, int64_t k){ return r->offsets + k; }
+GPUFUN int64_t* BeamStatsMonitorProfileRecordData_getp1_num_bins(BeamStatsMonitorProfileRecordData r, int64_t k){ return r->num_bins + k; }
+GPUFUN int64_t* BeamStatsMonitorProfileRecordData_getp1_coord_id(BeamStatsMonitorProfileRecordData r, int64_t k){ return r->coord_id + k; }
+GPUFUN double* BeamStatsMonitorProfileRecordData_getp1_min(BeamStatsMonitorProfileRecordData r, int64_t k){ return r->pmin + k; }
+GPUFUN double* BeamStatsMonitorProfileRecordData_getp1_bin_width(BeamStatsMonitorProfileRecordData r, int64_t k){ return r->bin_width + k; }
 '''
 
 
@@ -293,6 +352,7 @@ def generate():
     out.append('#include "xtrack/monitors/beam_position_monitor.h"')
     out.append('#include "xtrack/monitors/beam_size_monitor.h"')
     out.append('#include "xtrack/monitors/beam_profile_monitor.h"')
+    out.append('#include "xtrack/monitors/beam_stats_monitor.h"')
     for name in CLASS_ORDER:
         out.append(gen_element_struct(name))
         out.append(f'#include "xtrack/beam_elements/elements_src/{SPECS[name]["header"]}"')
@@ -314,6 +374,7 @@ def generate():
     out.append('        case 1002: BeamPositionMonitor_track_local_particle((BeamPositionMonitorData) el, lpart); break;')
     out.append('        case 1003: BeamSizeMonitor_track_local_particle((BeamSizeMonitorData) el, lpart); break;')
     out.append('        case 1004: BeamProfileMonitor_track_local_particle((BeamProfileMonitorData) el, lpart); break;')
+    out.append('        case 1005: BeamStatsMonitor_track_local_particle((BeamStatsMonitorData) el, lpart); break;')
     out.append('    }\n}')
     out.append('#endif')
     return '\n'.join(out) + '\n'

@@ -87,6 +87,23 @@ class BeamProfileMonitorC(ct.Structure):
                 + [('data', ct.POINTER(BeamProfileRecordC))])
 
 
+class BeamStatsMonitorC(ct.Structure):
+    _fields_ = ([(n, ct.c_int64) for n in ('start_at_turn', 'stop_at_turn', 'every_n_turns', '_mode',
+                                           '_num_records', '_num_selected_slots', '_num_slices',
+                                           '_particle_id_start', '_particle_id_stop')]
+                + [(n, ct.c_double) for n in ('_z_min_edge', '_dzeta', '_bunch_spacing_zeta')]
+                + [('n_slot_to_selected', ct.c_int64),
+                   ('_slot_to_selected', ct.POINTER(ct.c_int64)),
+                   ('_selected_slots', ct.POINTER(ct.c_int64)),
+                   ('field', ct.POINTER(ct.c_double) * 38), ('len_field', ct.c_int64 * 38),
+                   ('touched', ct.POINTER(ct.c_int64)),
+                   ('n_profiles', ct.c_int64), ('len_counts', ct.c_int64),
+                   ('counts', ct.POINTER(ct.c_double)),
+                   ('offsets', ct.POINTER(ct.c_int64)), ('num_bins', ct.POINTER(ct.c_int64)),
+                   ('coord_id', ct.POINTER(ct.c_int64)),
+                   ('pmin', ct.POINTER(ct.c_double)), ('bin_width', ct.POINTER(ct.c_double))])
+
+
 _STRUCTS = {}
 
 
@@ -221,6 +238,8 @@ class RefElements:
             return self._make_beam_monitor(el), 1002 if name == 'BeamPositionMonitor' else 1003
         if name == 'BeamProfileMonitor':
             return self._make_beam_profile(el), 1004
+        if name == 'BeamStatsMonitor':
+            return self._make_beam_stats(el), 1005
         if name not in SPECS:
             raise NotImplementedError(f'oracle: element class {name} not supported')
         st = _struct_for(name)()
@@ -245,6 +264,47 @@ class RefElements:
     def _make_monitor(self, mon):
         cm, keep = make_monitor_struct(mon)
         self._keep += [cm, keep]
+        return ct.addressof(cm)
+
+    def _make_beam_stats(self, mon):
+        """The oracle accumulates into `mon._host`: dict with 'moments' float64 [38, flat]
+        (rows in the reference's field order; rows the monitor does not keep have length 0
+        for the reference's code), 'touched' int64 [n_records], 'profile_counts' float64."""
+        from xtrack_b200.monitors import BSM_RAW_FIELDS, _BSM_COORDS
+        hh = mon._host
+        cm = BeamStatsMonitorC()
+        for nn in ('start_at_turn', 'stop_at_turn', 'every_n_turns', '_mode', '_num_records',
+                   '_num_selected_slots', '_num_slices', '_particle_id_start', '_particle_id_stop',
+                   '_z_min_edge', '_dzeta', '_bunch_spacing_zeta'):
+            setattr(cm, nn, getattr(mon, nn))
+        i64 = lambda arr: np.ascontiguousarray(arr, dtype=np.int64)
+        s2s, sel = i64(mon._slot_to_selected), i64(mon._selected_slots if len(mon._selected_slots) else [0])
+        cm.n_slot_to_selected = len(mon._slot_to_selected)
+        cm._slot_to_selected = s2s.ctypes.data_as(ct.POINTER(ct.c_int64))
+        cm._selected_slots = sel.ctypes.data_as(ct.POINTER(ct.c_int64))
+        for ii, ff in enumerate(BSM_RAW_FIELDS):
+            cm.field[ii] = hh['moments'][ii].ctypes.data_as(ct.POINTER(ct.c_double))
+            cm.len_field[ii] = hh['moments'].shape[1] if ff in mon._needed_fields else 0
+        cm.touched = hh['touched'].ctypes.data_as(ct.POINTER(ct.c_int64))
+        cfgs = list(mon._profile_config.items())
+        offs, total = [], 0
+        for _, cfg in cfgs:
+            offs.append(total)
+            total += mon._flat_size * cfg['num_bins']
+        offsets, nbins = i64(offs or [0]), i64([c['num_bins'] for _, c in cfgs] or [0])
+        cid = i64([_BSM_COORDS.index(cc) for cc, _ in cfgs] or [0])
+        pmin = np.ascontiguousarray([c['range'][0] for _, c in cfgs] or [0.], dtype=np.float64)
+        bw = np.ascontiguousarray([(c['range'][1] - c['range'][0]) / c['num_bins'] for _, c in cfgs]
+                                  or [1.], dtype=np.float64)
+        cm.n_profiles = len(cfgs)
+        cm.len_counts = total
+        cm.counts = hh['profile_counts'].ctypes.data_as(ct.POINTER(ct.c_double))
+        cm.offsets = offsets.ctypes.data_as(ct.POINTER(ct.c_int64))
+        cm.num_bins = nbins.ctypes.data_as(ct.POINTER(ct.c_int64))
+        cm.coord_id = cid.ctypes.data_as(ct.POINTER(ct.c_int64))
+        cm.pmin = pmin.ctypes.data_as(ct.POINTER(ct.c_double))
+        cm.bin_width = bw.ctypes.data_as(ct.POINTER(ct.c_double))
+        self._keep += [cm, s2s, sel, offsets, nbins, cid, pmin, bw]
         return ct.addressof(cm)
 
     def _make_beam_monitor(self, mon):

@@ -11,7 +11,7 @@ from .elements import (Marker, Drift, DriftExact, Multipole, Quadrupole, Sextupo
                        Octupole, Bend, RBend, Cavity, CrabCavity, RFMultipole, DipoleEdge, SRotation, XYShift, Rotation, Translation,
                        LimitRect, LimitEllipse, LimitPolygon)
 from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
-                       BeamSizeMonitor, BeamProfileMonitor)
+                       BeamSizeMonitor, BeamProfileMonitor, BeamStatsMonitor)
 from .line import Line
 from .loss_location_refinement import LossLocationRefinement
 

@@ -93,7 +93,7 @@ static int program_prepare(xtb_program& G, const uint64_t* words, size_t n_words
             const uint32_t op = (uint32_t) (h & 0xffu);
             if (nw < 2 || (nw & 1u) || pc + nw > w1) return fail(XTB_E_INVALID, "malformed op in program");
             if (op >= XTB_HEAVY_FIRST) G.has_heavy = true;
-            if (op == XTB_OP_BEAM_MON || op == XTB_OP_BEAM_PROFILE) G.has_beam_mon = true;
+            if (op == XTB_OP_BEAM_MON || op == XTB_OP_BEAM_PROFILE || op == XTB_OP_BEAM_STATS) G.has_beam_mon = true;
             if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) >= 2u) G.has_quantum = true;
             if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) == 3u) G.has_qk = true;
             pc += nw;

@@ -139,6 +139,167 @@ static __device__ __noinline__ void beam_monitor_record(const double* __restrict
 #endif
 }
 
+// BeamStatsMonitor, monitors/beam_stats_monitor.h:11-419: weighted primitive moments (sum of
+// weights, weighted sums of the 9 first and 27 second moments, optional profiles) per logged
+// turn -- of the whole beam, per bunch slot, per slice of a bunch, or per slice of a full turn
+// (coasting beam).  q[0] is the DEVICE address of the monitor's descriptor, 8-byte words
+// (xtrack_b200/monitors.py:BeamStatsMonitor.allocate):
+//   0 start_at_turn  1 stop_at_turn  2 every_n_turns  3 mode  4 n_records  5 n_selected
+//   6 n_slices  7 z_min_edge (f64)  8 dzeta (f64)  9 bunch_spacing_zeta (f64)  10, 11 particle
+//   id range (start < 0: all)  12 len(slot_to_selected)  13 selected_slots[0]
+//   14 &touched_records  15 n_profiles  16 &profile_counts
+//   17 .. 54 addresses of the 38 record arrays in the reference's field order (0: not kept)
+//   then slot_to_selected[], then per profile {offset, num_bins, coord_id, min, bin_width}.
+// The reference adds with one atomicAdd per particle and quantity; here the lanes of a warp
+// that fall into the same bin (a bunch: all of them) are summed in the warp and ONE lane adds.
+#define XTB_BSM_HEADER 17
+#define XTB_BSM_NFIELDS 38
+static __device__ __noinline__ void beam_stats_record(const double* __restrict__ q, const PState& P,
+                                                      const PSlot& G, const XtbTrackArgs& a) {
+    const int64_t* __restrict__ d = reinterpret_cast<const int64_t*>(__double_as_longlong(q[0]));
+    const double* __restrict__ df = reinterpret_cast<const double*>(d);
+    const int64_t start_at_turn = d[0], stop_at_turn = d[1], every_n_turns = d[2], mode = d[3];
+    const int64_t n_records = d[4], n_selected = d[5], n_slices = d[6];
+    const double z_min_edge = df[7], dzeta = df[8], bunch_spacing_zeta = df[9];
+    const int64_t pid_start = d[10], pid_stop = d[11], n_s2s = d[12];
+    const bool coasting = (mode == 3);
+    const int64_t* __restrict__ s2s = d + XTB_BSM_HEADER + XTB_BSM_NFIELDS;
+
+    int64_t effective_turn = P.at_turn;
+    double zeta = P.zeta;
+    int64_t coasting_slice = 0;
+    bool accepted = true;
+    if (pid_start >= 0) {
+        const int64_t particle_id = G.ldgi(F_PARTICLE_ID);
+        if (particle_id < pid_start || particle_id >= pid_stop) accepted = false;
+    }
+    if (accepted && coasting) {
+        const double line_length = a.line_length;
+        if (line_length <= 0.0) {
+            accepted = false;
+        } else {
+            const double u = ((double) effective_turn - zeta / line_length);
+            effective_turn = (int64_t) floor(u + 0.5);
+            const double relative_turn_fraction = u - (double) effective_turn;
+            const double slice_position = (relative_turn_fraction + 0.5) * (double) n_slices;
+            coasting_slice = (int64_t) floor(slice_position);
+            if (coasting_slice < 0 || coasting_slice >= n_slices) accepted = false;
+            zeta = -relative_turn_fraction * line_length;
+        }
+    }
+    const int64_t turn_offset = effective_turn - start_at_turn;
+    int64_t index = -1, i_record = -1;
+    if (accepted && effective_turn >= start_at_turn && effective_turn < stop_at_turn
+        && turn_offset % every_n_turns == 0) {
+        i_record = turn_offset / every_n_turns;
+        if (i_record >= 0 && i_record < n_records) {
+            index = i_record;
+            if (coasting) {
+                index = (i_record * n_selected) * n_slices + coasting_slice;
+            } else if (mode > 0) {
+                int64_t slot = 0, i_selected = 0;
+                if (bunch_spacing_zeta != 0.0) {
+                    slot = (int64_t) -floor((zeta - z_min_edge) / bunch_spacing_zeta);
+                    i_selected = (slot >= 0 && slot < n_s2s) ? s2s[slot] : -1;
+                } else if (n_selected == 1) {
+                    slot = d[13];
+                    i_selected = 0;
+                } else {
+                    i_selected = -1;
+                }
+                if (i_selected < 0) {
+                    index = -1;
+                } else if (mode == 1) {
+                    index = i_record * n_selected + i_selected;
+                } else {
+                    const double z_min_edge_bunch = z_min_edge - slot * bunch_spacing_zeta;
+                    const int64_t i_slice = (int64_t) floor((zeta - z_min_edge_bunch) / dzeta);
+                    if (i_slice < 0 || i_slice >= n_slices) index = -1;
+                    else index = (i_record * n_selected + i_selected) * n_slices + i_slice;
+                }
+            }
+        }
+    }
+    // the weighted quantities, in the order of the record arrays
+    double v[XTB_BSM_NFIELDS];
+    double coords[7];
+    double weight = 0.;
+    if (index >= 0) {
+        weight = G.ldg(F_WEIGHT);
+        const double beta0 = G.ld(F_BETA0);
+        const double charge_ratio = G.ld(F_CHARGE_RATIO);
+        coords[0] = P.x;  coords[1] = P.px;  coords[2] = P.y;  coords[3] = P.py;  coords[4] = zeta;
+        coords[5] = P.delta;  coords[6] = G.ld(F_PTAU) / beta0;
+        v[0] = weight;
+        v[1] = weight * (beta0 * G.ld(F_GAMMA0));
+        for (int j = 0; j < 7; ++j) v[2 + j] = weight * coords[j];
+        v[9] = weight * charge_ratio;
+        v[10] = weight * (charge_ratio / P.chi);
+        int k = 11;
+        for (int i = 0; i < 7; ++i)
+            for (int j = i; j < 7; ++j) {
+                if (i == 5 && j == 6) continue;              // (no delta_pzeta moment)
+                v[k++] = weight * coords[i] * coords[j];
+            }
+    } else {
+        for (int j = 0; j < XTB_BSM_NFIELDS; ++j) v[j] = 0.;
+    }
+    int64_t* touched = reinterpret_cast<int64_t*>(d[14]);
+#ifdef __CUDA_ARCH__
+    const unsigned active = __activemask();
+    int same = 0;
+    __match_all_sync(active, (long long) index, &same);
+    if (same) {
+        if (index >= 0) {
+            const int leader = __ffs(active) - 1;
+            const bool lead = ((int) (threadIdx.x & 31) == leader);
+            if (lead) touched[i_record] = 1;
+            for (int j = 0; j < XTB_BSM_NFIELDS; ++j) {
+                double* dst = reinterpret_cast<double*>(d[XTB_BSM_HEADER + j]);
+                if (!dst) continue;                          // (uniform: the descriptor's)
+                double sum = 0.;
+                for (unsigned m = active; m; m &= m - 1) sum += __shfl_sync(active, v[j], __ffs(m) - 1);
+                if (lead) atomicAdd(dst + index, sum);
+            }
+        }
+    } else if (index >= 0) {
+        touched[i_record] = 1;
+        for (int j = 0; j < XTB_BSM_NFIELDS; ++j) {
+            double* dst = reinterpret_cast<double*>(d[XTB_BSM_HEADER + j]);
+            if (dst) atomicAdd(dst + index, v[j]);
+        }
+    }
+#else
+    if (index >= 0) {
+        touched[i_record] = 1;
+        for (int j = 0; j < XTB_BSM_NFIELDS; ++j) {
+            double* dst = reinterpret_cast<double*>(d[XTB_BSM_HEADER + j]);
+            if (dst) dst[index] += v[j];
+        }
+    }
+#endif
+    // weighted profiles (bins are spread over the beam: plain per-particle adds)
+    const int64_t n_profiles = d[15];
+    if (index >= 0 && n_profiles > 0) {
+        double* counts = reinterpret_cast<double*>(d[16]);
+        const int64_t* pw = s2s + n_s2s;
+        for (int64_t ip = 0; ip < n_profiles; ++ip, pw += 5) {
+            const int64_t off = pw[0], nb = pw[1], cid = pw[2];
+            const double vmin = reinterpret_cast<const double*>(pw)[3];
+            const double width = reinterpret_cast<const double*>(pw)[4];
+            const double value = (cid >= 0 && cid < 7) ? coords[cid] : 0.0;
+            const int64_t ib = (int64_t) floor((value - vmin) / width);
+            if (ib >= 0 && ib < nb) {
+#ifdef __CUDA_ARCH__
+                atomicAdd(counts + off + index * nb + ib, weight);
+#else
+                counts[off + index * nb + ib] += weight;
+#endif
+            }
+        }
+    }
+}
+
 // BeamProfileMonitor, monitors/beam_profile_monitor.h:15-80: per time sample a histogram of
 // x and one of y (particle counts per bin; the bins are spread over the beam, so the plain
 // per-particle atomic add of the reference is kept).
@@ -253,6 +414,9 @@ static __device__ __noinline__ void generic_op(const uint32_t op, const int32_t 
         break;
     case XTB_OP_BEAM_PROFILE:
         if constexpr (BMON) { if (live) beam_profile_record(q, P, G); }
+        break;
+    case XTB_OP_BEAM_STATS:
+        if constexpr (BMON) { if (live) beam_stats_record(q, P, G, a); }
         break;
     case XTB_OP_KILL:
         kill_particle<FRZ>(P, G, aux);

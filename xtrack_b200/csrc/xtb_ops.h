@@ -50,7 +50,7 @@
  * layout changes; xtrack_b200/lowering.py carries the same number (OPS_ABI_VERSION) and
  * _cabi.load() refuses a library whose xtb_ops_abi_version() differs: a stale libxtb200.so
  * cannot silently interpret a newer program. */
-#define XTB_OPS_ABI_VERSION 4
+#define XTB_OPS_ABI_VERSION 5
 
 #define XTB_F_START   0x01u
 #define XTB_F_END     0x02u
@@ -103,6 +103,7 @@
 #define XTB_OP_ADD_X         53   /* [dx]  x += dx              (rbend straight body)       */
 #define XTB_OP_BEAM_MON      54   /* aux=#sums (3 position, 5 size); see beam_monitor_record */
 #define XTB_OP_BEAM_PROFILE  55   /* BeamProfileMonitor; see beam_profile_record              */
+#define XTB_OP_BEAM_STATS    57   /* [(ptr) descriptor, 0]  BeamStatsMonitor; see beam_stats_record */
 #define XTB_OP_CRAB          56   /* aux=absolute_time; [V_t, f, lag, phase]  track_rf.h:116-156 */
 
 /* -- heavy set (thick magnets; compiled in the HEAVY kernel variants) ------ */

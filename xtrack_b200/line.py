@@ -19,14 +19,15 @@ import numpy as np
 
 from . import elements as _el
 from .monitors import (ParticlesMonitor, LastTurnsMonitor, BeamPositionMonitor,
-                       BeamSizeMonitor, BeamProfileMonitor)
+                       BeamSizeMonitor, BeamProfileMonitor, BeamStatsMonitor)
 from .particles import Particles
 
 _MONITOR_CLASSES = {'ParticlesMonitor': ParticlesMonitor,
                     'LastTurnsMonitor': LastTurnsMonitor,
                     'BeamPositionMonitor': BeamPositionMonitor,
                     'BeamSizeMonitor': BeamSizeMonitor,
-                    'BeamProfileMonitor': BeamProfileMonitor}
+                    'BeamProfileMonitor': BeamProfileMonitor,
+                    'BeamStatsMonitor': BeamStatsMonitor}
 
 
 class Line:

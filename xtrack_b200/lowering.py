@@ -27,7 +27,7 @@ import math
 import numpy as np
 
 # ---- opcodes / flags: mirror of csrc/xtb_ops.h ----------------------------
-OPS_ABI_VERSION = 4          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
+OPS_ABI_VERSION = 5          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
 F_START, F_END, F_GLOBAL, F_DRIFT = 0x01, 0x02, 0x04, 0x08
 
 # fast set (fused program only): one whole element per op
@@ -74,6 +74,7 @@ OP_ADD_X = 53
 OP_BEAM_MON = 54
 OP_BEAM_PROFILE = 55
 OP_CRAB = 56
+OP_BEAM_STATS = 57
 # heavy set
 OP_MAGNET_BODY = 64
 OP_MAGNET_EDGE = 65
@@ -117,7 +118,7 @@ FLOPS = {
     OP_NOP: 0, OP_DRIFT: 17, OP_DRIFT_EXACT: 21, OP_CAVITY: 25, OP_EDGE_LIN: 6,
     OP_SROT: 12, OP_XYSHIFT: 2, OP_SSHIFT: 23, OP_YROT: 30, OP_XROT: 30,
     OP_LIMIT_RECT: 0, OP_LIMIT_ELLIPSE: 5, OP_MONITOR: 0, OP_LAST_TURNS: 0,
-    OP_KILL: 0, OP_SET_STATE: 0, OP_ADD_S_ZETA: 2, OP_ADD_X: 1,
+    OP_BEAM_STATS: 80, OP_KILL: 0, OP_SET_STATE: 0, OP_ADD_S_ZETA: 2, OP_ADD_X: 1,
 }
 
 
@@ -1377,6 +1378,13 @@ def lower_element(prog, el, cfg):
                  _RawWord(el.nx), el.x_min, el.dx, _RawWord(el.ny), el.y_min, el.dy,
                  _RawWord(dd['counts_x'].data_ptr()), _RawWord(dd['counts_y'].data_ptr())],
                 flops=10)
+        prog.beam_monitors.append(el)
+        return False
+
+    if name == 'BeamStatsMonitor':
+        # the op carries the device address of the monitor's descriptor (monitors.py)
+        desc = el.allocate(cfg.get('device'))
+        prog.op(OP_BEAM_STATS, [_RawWord(desc.data_ptr()), 0.0])
         prog.beam_monitors.append(el)
         return False
 
