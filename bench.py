@@ -59,9 +59,14 @@ WORKLOADS = {
     # ... and with the deterministic mean energy loss (configure_radiation('mean'))
     'clic_dr_mean': ('clic_dr', 'CLIC-DR thin lattice, mean synchrotron radiation, Gaussian beam'),
     'lep_mean': ('lep', 'LEP thick lattice, mean synchrotron radiation, Gaussian beam'),
+    # ... and with the tabulated total energy loss per slice (configure_radiation('quantum-kick'))
+    'clic_dr_qkick': ('clic_dr', 'CLIC-DR thin lattice, quantum-kick synchrotron radiation, '
+                                 'Gaussian beam'),
+    'lep_qkick': ('lep', 'LEP thick lattice, quantum-kick synchrotron radiation, Gaussian beam'),
 }
 RADIATION = {'clic_dr_quantum': 'quantum', 'lep_quantum': 'quantum',
-             'clic_dr_mean': 'mean', 'lep_mean': 'mean'}
+             'clic_dr_mean': 'mean', 'lep_mean': 'mean',
+             'clic_dr_qkick': 'quantum-kick', 'lep_qkick': 'quantum-kick'}
 
 
 def toy_ring(xb, thin=False):
@@ -123,7 +128,7 @@ def initial_conditions(workload, line, n, rank):
         sig = dict(x=4e-3, px=1e-4, y=2e-3, py=1e-4, zeta=0.2, delta=1e-3)
     elif workload.startswith('toy_ring'):
         sig = dict(x=1e-3, px=1e-4, y=1e-3, py=1e-4, zeta=5e-2, delta=1e-4)
-    elif workload == 'clic_dr_quantum':
+    elif workload in ('clic_dr_quantum', 'clic_dr_qkick'):
         sig = dict(x=1e-4, px=2e-5, y=2e-5, py=4e-6, zeta=2e-3, delta=1e-3)
     else:
         sig = dict(x=2e-4, px=2e-6, y=5e-5, py=1e-6, zeta=5e-3, delta=3e-4)
@@ -196,6 +201,9 @@ def cpu_reference_run(workload, line, n_particles, target_seconds, warm=True):
     kw = dict(ele_start=0, num_ele_track=len(line), flag_end_turn_actions=1,
               flag_reset_s_at_end_turn=1, line_length=line.get_length(), variant=variant)
     hp = ro.HostParticles.from_particles(p)
+    if RADIATION.get(workload) == 'quantum-kick':
+        from xtrack_b200 import synrad_tables
+        ro.set_synrad_tables(synrad_tables.load_blob(), variant)
     if workload in RADIATION:
         ro.init_rand_gen(hp, np.arange(1, n_particles + 1, dtype=np.uint32), variant=variant)
         p = None
@@ -506,11 +514,13 @@ def main():
     # DRAM traffic of one tracking launch from the committed ncu --set full capture (this is
     # an FP64-bound kernel: the figure only shows that HBM is idle, 5e-7 B per element-turn)
     traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_summary.json')) as fid:
-            traffic = json.load(fid).get('dram_bytes_per_launch')
-    except Exception:
-        pass
+    for summary in ('r02_ncu_summary.json', 'r01_ncu_summary.json'):     # (latest round first)
+        try:
+            with open(os.path.join(ROOT, 'profiles', summary)) as fid:
+                traffic = json.load(fid).get('dram_bytes_per_launch')
+            break
+        except Exception:
+            pass
     roofline = {
         'bound': 'fp64', 'achieved': achieved / 1e12, 'peak': peak_sustained / 1e12,
         'unit': 'TFLOP/s', 'frac': achieved / peak_sustained, 'traffic': traffic,

@@ -23,6 +23,8 @@ run cfg2_hllhc_125k --workload hllhc_da --particles 125000 --turns 1000 --steps 
 run cfg3_sps_4M --workload sps_apertures --particles 4000000 --turns 100 --steps 2 --warmup 3
 run cfg4_clic_quantum_1M --workload clic_dr_quantum --particles 1000000 --turns 3 --steps 1 --warmup 3
 run cfg4_clic_mean_1M --workload clic_dr_mean --particles 1000000 --turns 5 --steps 1 --warmup 3
+run cfg4_clic_qkick_1M --workload clic_dr_qkick --particles 1000000 --turns 5 --steps 1 --warmup 3
+run cfg4_lep_qkick_1M --workload lep_qkick --particles 1000000 --turns 2 --steps 1 --warmup 3
 run cfg4_lep_quantum_1M --workload lep_quantum --particles 1000000 --turns 1 --steps 1 --warmup 3
 run cfg4_lep_mean_1M --workload lep_mean --particles 1000000 --turns 2 --steps 1 --warmup 3
 run cfg5_lep_thick_1M --workload lep_thick --particles 1000000 --turns 5 --steps 2 --warmup 3

@@ -5,7 +5,7 @@
 The reference generates them offline with xtrack/headers/_generate_synrad_total_energy_tables.py
 into a C header that is not part of the reference checkout (.MISSING_LARGE_BLOBS).  This script
 RUNS THAT GENERATOR where it lies (nothing of it is copied; it is executed with its output path
-pointed at a scratch directory -- about two hours on one core), reads the numbers out of the
+pointed at a scratch directory -- about half an hour on one core), reads the numbers out of the
 header it writes and stores them as float64 arrays.  Needs /root/reference (or
 XTB_REFERENCE_ROOT) and scipy.
 

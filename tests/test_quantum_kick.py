@@ -83,3 +83,52 @@ def test_missing_tables_fail_loudly(monkeypatch):
     monkeypatch.setattr(synrad_tables, '_blob', None)
     with pytest.raises(FileNotFoundError, match='quantum-kick'):
         line.build_tracker(_device='cpu', _tracker_class=hostsim.HostSimTracker)
+
+
+def test_shipped_tables_are_the_sum_of_n_photon_energies():
+    """xtrack_b200/data/synrad_total_energy_tables.npz (made by the reference's generator,
+    scripts/make_synrad_tables.py): quantile functions of X_N = x_1 + ... + x_N, x = E / E_c
+    distributed as the synchrotron-radiation photon spectrum, for which <x> = 8 / (15 sqrt 3)
+    and <x^2> = 11 / 27."""
+    blob = synrad_tables.load_blob()
+    n_l, n_c, n_r = (int(v) for v in blob[:3])
+    assert (n_l, n_c, n_r) == (2296, 1601, 2296) and blob[4] == 32
+    assert len(blob) == 8 + (n_l + n_c + n_r) * (1 + len(synrad_tables.TABLE_COUNTS))
+    left_u, center_u, right_v = blob[8:8 + n_l], blob[8 + n_l:8 + n_l + n_c], blob[8 + n_l + n_c:8 + n_l + n_c + n_r]
+    assert left_u[0] == 0 and np.all(np.diff(left_u) > 0) and np.all(np.diff(center_u) > 0)
+    assert abs(left_u[-1] - blob[3]) < 1e-15 and abs(center_u[0] - blob[3]) < 1e-15
+    size = n_l + n_c + n_r
+    mean1, var1 = 8 / (15 * np.sqrt(3)), 11 / 27 - (8 / (15 * np.sqrt(3))) ** 2
+    for kk, nn in enumerate(synrad_tables.TABLE_COUNTS):
+        tt = blob[8 + size * (1 + kk):8 + size * (2 + kk)]
+        ql, qc, qr = np.exp(tt[:n_l]), np.exp(tt[n_l:n_l + n_c]), np.exp(tt[n_l + n_c:])
+        assert np.all(np.diff(ql) >= 0) and np.all(np.diff(qc) > 0) and np.all(np.diff(qr) <= 0), nn
+        assert ql[-1] <= qc[0] * (1 + 1e-9) and qc[-1] <= qr[-1] * (1 + 1e-9), nn
+        m1 = np.trapezoid(ql, left_u) + np.trapezoid(qc, center_u) + np.trapezoid(qr, right_v)
+        m2 = (np.trapezoid(ql ** 2, left_u) + np.trapezoid(qc ** 2, center_u)
+              + np.trapezoid(qr ** 2, right_v))
+        assert abs(m1 / (nn * mean1) - 1) < 2e-3, (nn, m1)
+        assert abs((m2 - m1 ** 2) / (nn * var1) - 1) < 2e-2, (nn, m2 - m1 ** 2)
+
+
+def test_quantum_kick_energy_loss_statistics_vs_photon_by_photon():
+    """The same ring under `quantum` (photon by photon) and `quantum-kick` (shipped tables):
+    mean and spread of the energy lost in two turns agree within the statistics of the sample."""
+    import hostsim
+    n = 500
+    out = {}
+    for model in ('quantum', 'quantum-kick'):
+        line = common.load_line('clic_dr')
+        line.configure_radiation(model=model)
+        p = common.gaussian_particles(line, n, 5, common.SIGMAS['clic_dr'], scale=0.1)
+        common.seed_rng_host(p, np.arange(1, n + 1, dtype=np.uint32) * 104729)
+        e0 = p.get('ptau').copy()
+        line.build_tracker(_device='cpu', _tracker_class=hostsim.HostSimTracker)
+        line.track(p, num_turns=2)
+        assert np.all(p.get('state') > 0)
+        out[model] = (p.get('ptau') - e0) * p.get('p0c')          # eV
+    mq, mk = out['quantum'].mean(), out['quantum-kick'].mean()
+    sq, sk = out['quantum'].std(), out['quantum-kick'].std()
+    assert mq < -5e6                                   # ~ 4 MeV per turn
+    assert abs(mk / mq - 1) < 4 * sq / abs(mq) / np.sqrt(n) + 5e-3, (mk, mq)
+    assert abs(sk / sq - 1) < 0.15, (sk, sq)
