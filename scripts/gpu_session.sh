@@ -15,7 +15,7 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 for wl in sps_apertures lep_thick; do
   timeout 400 python bench.py --workload $wl --quick --steps 3 --warmup 1 --turns 5 --particles 500000 > $OUT/bench_$wl.json 2>> $OUT/bench.err
 done
-for wl in lep_quantum clic_dr_quantum; do
+for wl in lep_quantum clic_dr_quantum lep_mean clic_dr_mean lep_qkick clic_dr_qkick; do
   timeout 400 python bench.py --workload $wl --quick --steps 2 --warmup 1 --turns 2 --particles 300000 > $OUT/bench_$wl.json 2>> $OUT/bench.err
 done
 kill $SMI
@@ -27,4 +27,13 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:xtb_
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xtb_track_kernel -s 1 -c 1 \
     -o $OUT/prof_lep -f python bench.py --workload lep_thick --particles 300000 --quick --steps 1 --warmup 1 --turns 1 --no-cpu-baseline > $OUT/ncu_lep.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xtb_track_kernel -s 1 -c 1 \
+    -o $OUT/prof_clic_mean -f python bench.py --workload clic_dr_mean --particles 300000 --quick --steps 1 --warmup 1 --turns 1 --no-cpu-baseline > $OUT/ncu_clic_mean.log 2>&1
 tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; cat $OUT/bench.json
+for f in $OUT/bench_*.json; do python - <<PY
+import json
+try:
+    d=json.load(open('$f')); print('$f'.split('/')[-1], '%.4e'%d['value'], d.get('roofline',{}).get('frac'))
+except Exception as e: print('$f', 'FAILED', e)
+PY
+done

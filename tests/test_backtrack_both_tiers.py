@@ -153,3 +153,32 @@ def test_backtrack_refused_for_lines_without_inverse():
         line.track(p, backtrack=True)
     line.track(p, ele_start=0, ele_stop=1, backtrack='force')      # the caller insists
     assert np.allclose(p.get('s'), -1.0)
+
+
+@pytest.mark.gpu
+def test_full_size_round_trip_on_gpu():
+    """BASELINE.json configs[1] at its full per-GPU size, through a size-independent property:
+    10^6 particles two turns forwards then two turns backwards through hllhc_14 are where they
+    started (the inverse lattice undoes the lattice: every lowered inverse map, the reversed
+    order and the turn bookkeeping at once)."""
+    line = common.load_line('hllhc_14')
+    n, nr = 1_000_000, 1000
+    r = np.linspace(0, 2e-3, nr + 1)[1:]
+    th = np.linspace(0, np.pi / 2, n // nr)
+    rr, tt = np.meshgrid(r, th, indexing='ij')
+    ref_p = line.particle_ref
+    p_host = xb.Particles(x=(rr * np.cos(tt)).ravel(), y=(rr * np.sin(tt)).ravel(),
+                          delta=np.full(n, 2.7e-4), p0c=float(ref_p.get('p0c')[0]),
+                          mass0=ref_p.mass0, q0=ref_p.q0)
+    line.build_tracker(_device='cuda:0', exact_arithmetic=True)
+    p = p_host.copy(_device='cuda:0')
+    line.track(p, num_turns=2)
+    mid = common.by_id(p)
+    assert np.all(mid['state'] > 0) and np.all(mid['at_turn'] == 2)
+    assert np.max(np.abs(mid['x'] - p_host.get('x'))) > 1e-4          # it did move
+    line.track(p, num_turns=2, backtrack=True)
+    end = common.by_id(p)
+    assert np.all(end['state'] > 0) and np.all(end['at_turn'] == 0) and np.all(end['at_element'] == 0)
+    for ff, tol in (('x', 1e-12), ('px', 1e-14), ('y', 1e-12), ('py', 1e-14), ('zeta', 1e-11),
+                    ('delta', 1e-15)):
+        assert np.max(np.abs(end[ff] - p_host.get(ff))) < tol, (ff, np.max(np.abs(end[ff] - p_host.get(ff))))
