@@ -870,6 +870,15 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
         if (live[k])
             ae_base[k] = (ps.el_reset ? 0 : (int32_t) G[k].ldi(F_AT_ELEMENT)) + (int32_t) ps.el_off;
     }
+#ifdef __CUDA_ARCH__
+    // The lane array stays ADDRESSABLE, i.e. in thread-local memory that the L1 serves, and the
+    // registers go to the temporaries of the maps.  Measured (profiles/r02_history.md, section 7):
+    // with the lanes promoted to registers ptxas spills 0.6 - 9 KB per thread under the
+    // 128-register cap and every workload of these loops gets slower (LEP thick 1.61 -> 1.48e10
+    // PET/s, CLIC-DR mean 1.08 -> 0.81e11).  Whether the array is promoted used to hinge on
+    // which out-of-line map happened to take a lane by address; this pins it.
+    asm volatile("" ::"l"(&T[0]) : "memory");
+#endif
     uint32_t off = lanes.off, eidx = lanes.eidx;
     // launch constants read once (through `a` they are loads the compiler will not hoist over
     // the stores of the loop: ncu showed long-scoreboard stalls on them per op)

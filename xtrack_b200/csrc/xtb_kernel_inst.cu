@@ -27,6 +27,7 @@
 #ifndef XTB_NPT_SYNRAD
 #define XTB_NPT_SYNRAD 1
 #endif
+static_assert(XTB_NPT_SYNRAD == 1, "the photon-emission calls are compiled into the one-lane bodies only");
 // small beams: particles per SM below which the thin kernel runs with 1 / 2 particles per thread
 // (measured on hllhc_14 and SPS, 62 500 ... 500 000 particles on 148 SMs, profiles/r02_history.md:
 // NPT 1 wins up to ~310 000 particles per GPU, NPT 2 around 375 000, NPT 3 from 500 000 on)

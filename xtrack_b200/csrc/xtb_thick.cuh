@@ -1069,14 +1069,17 @@ __device__ __forceinline__ void thin_rad_kick_run(PState (&P)[N], const bool (&l
     XTB_LANES { if (!(t0[k] > 1e-280)) bperp[k] = sqrt(t0[k]); }
     XTB_LANES lpath[k] = P[k].rvv * (length - (P[k].zeta - old_zeta[k]));
 
-    if (b.radiation_flag() >= 2) {
-#pragma unroll 1
-        for (int k = 0; k < N; ++k) {
-            if (!live[k]) continue;
-            if (b.radiation_flag() == 2) synrad_emit_photons<FRZ>(P[k], G[k], a, bperp[k], lpath[k]);
-            else synrad_emit_total_energy_loss<FRZ>(P[k], G[k], a, bperp[k], lpath[k]);
+    // (programs with random emission run on the one-lane kernels, xtb_kernel_inst.cu: the
+    // calls are not even compiled into the two-lane run loop of the mean model, whose register
+    // allocation they cost 100 bytes of spills)
+    if constexpr (N == 1) {
+        if (b.radiation_flag() >= 2) {
+            if (live[0]) {
+                if (b.radiation_flag() == 2) synrad_emit_photons<FRZ>(P[0], G[0], a, bperp[0], lpath[0]);
+                else synrad_emit_total_energy_loss<FRZ>(P[0], G[0], a, bperp[0], lpath[0]);
+            }
+            return;
         }
-        return;
     }
     // synrad_average_kick (mean model)
     double ft[N], nd[N];
