@@ -775,7 +775,13 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
     })
     XTB_HANDLER(MULTPN, {
         const uint32_t order = (uint32_t) (hw.x >> 32);
-        _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn<CHI1>(P[k], c0.x, order);
+        if (order == 2) {
+            _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn_c<2, CHI1>(P[k], c0.x);
+        } else if (order == 3) {
+            _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn_c<3, CHI1>(P[k], c0.x);
+        } else {
+            _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn<CHI1>(P[k], c0.x, order);
+        }
     })
     XTB_HANDLER_X2(EDGE, {
         _Pragma("unroll") for (int k = 0; k < NPT; ++k) edge_linear_c<CHI1>(P[k], c0.x, c0.y);
