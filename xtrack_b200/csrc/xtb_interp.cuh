@@ -775,10 +775,16 @@ static __device__ __noinline__ int xtb_run_fast(const xtb_tile_t tb, XtbLanes<NP
     })
     XTB_HANDLER(MULTPN, {
         const uint32_t order = (uint32_t) (hw.x >> 32);
+#ifdef XTB_NO_PN_SPECIAL      /* (A/B switch of the tuning sessions) */
+        if (false) {
+#else
         if (order == 2) {
+#endif
             _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn_c<2, CHI1>(P[k], c0.x);
+#ifndef XTB_NO_PN_SPECIAL
         } else if (order == 3) {
             _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn_c<3, CHI1>(P[k], c0.x);
+#endif
         } else {
             _Pragma("unroll") for (int k = 0; k < NPT; ++k) mult_kick_pn<CHI1>(P[k], c0.x, order);
         }
@@ -903,13 +909,29 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
         lanes.live[k] = false;
         pstate_benign(T[k]);
     };
-    // end of a statically thick element: global aperture check, loss check, at_element + 1
+    // end of a Drift element: global aperture check, loss check, at_element + 1.  As in the
+    // thin kernels an integer test on the high words of x, y comes first (|x| >= lim / 2 implies
+    // hi32(|x|) >= hi32(lim / 2); NaN passes it too): the exact test of the reference, the
+    // write-back of a lost particle and the re-pinning of a lane without particle that
+    // wandered off (see xtb_run_tile) only run when some lane is beyond half the limit.
+    const uint32_t half_lim_hi = (lim > 0.) ? (uint32_t) __double2hiint(0.5 * lim) : 0u;
     auto end_thick = [&]() {
+        uint32_t m_ = 0;
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
-            if (!live[k]) { pstate_benign(T[k]);  continue; }
-            if (!ignore_global) global_aperture_check(T[k], lim);
-            if (T[k].state <= 0) retire(k);
+            m_ = max(m_, (uint32_t) __double2hiint(T[k].x) & 0x7fffffffu);
+            m_ = max(m_, (uint32_t) __double2hiint(T[k].y) & 0x7fffffffu);
+        }
+        if (m_ >= half_lim_hi) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                if (!live[k]) {
+                    if (!(fabs(T[k].x) < 0.5 * lim && fabs(T[k].y) < 0.5 * lim)) pstate_benign(T[k]);
+                    continue;
+                }
+                if (!ignore_global) global_aperture_check(T[k], lim);
+                if (T[k].state <= 0) retire(k);
+            }
         }
         eidx += 1;
     };
@@ -947,7 +969,12 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
             if (h & (XTB_F_END << 8)) {
 #pragma unroll
                 for (int k = 0; k < NPT; ++k) {
-                    if (!live[k]) { pstate_benign(T[k]);  continue; }
+                    if (!live[k]) {
+                        // (a lane without particle: back on the axis once it has wandered off)
+                        if (!(fabs(T[k].x) < 0.5 * lim && fabs(T[k].y) < 0.5 * lim)) pstate_benign(T[k]);
+                        T[k].state = 1;
+                        continue;
+                    }
                     if ((h & (XTB_F_GLOBAL << 8)) && !ignore_global) global_aperture_check(T[k], lim);
                     if (T[k].state <= 0) retire(k);
                 }
