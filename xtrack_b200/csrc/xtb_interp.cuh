@@ -922,6 +922,9 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
             m_ = max(m_, (uint32_t) __double2hiint(T[k].x) & 0x7fffffffu);
             m_ = max(m_, (uint32_t) __double2hiint(T[k].y) & 0x7fffffffu);
         }
+#ifdef XTB_NO_HEAVY_PREFILTER      /* (A/B switch of the tuning sessions) */
+        m_ = 0xffffffffu;
+#endif
         if (m_ >= half_lim_hi) {
 #pragma unroll
             for (int k = 0; k < NPT; ++k) {

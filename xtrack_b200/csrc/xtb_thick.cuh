@@ -431,6 +431,9 @@ __device__ __forceinline__ BodyPar body_par(const double* q, const int32_t aux) 
     return b;
 }
 
+template <int N, bool FRZ>
+__device__ __forceinline__ void magnet_kick_curv_n(PState (&P)[N], const BodyPar& b, const double kick_weight);
+
 // track_magnet_kick_single_particle, track_magnet_kick.h:24-144, on N particles
 template <int N, bool FRZ>
 __device__ __forceinline__ void magnet_kick_n(PState (&P)[N], const BodyPar& b, const double kick_weight) {
@@ -464,6 +467,13 @@ __device__ __forceinline__ void magnet_kick_n(PState (&P)[N], const BodyPar& b, 
             P[k].py += kick_weight * n;
         }
     }
+    magnet_kick_curv_n<N, FRZ>(P, b, kick_weight);
+}
+
+// ... its curvature terms (track_magnet_kick.h:98-142)
+template <int N, bool FRZ>
+__device__ __forceinline__ void magnet_kick_curv_n(PState (&P)[N], const BodyPar& b, const double kick_weight) {
+    const double length = b.q[0];
     const double h = b.q[4], hxl = b.q[5];
     const double htot = b.q[8];
 #pragma unroll
@@ -1028,7 +1038,27 @@ __device__ __forceinline__ void thin_rad_kick_run(PState (&P)[N], const bool (&l
     const double length = b.q[0];
     double old_px[N], old_py[N], old_zeta[N];
     XTB_LANES { old_px[k] = P[k].px;  old_py[k] = P[k].py;  old_zeta[k] = P[k].zeta; }
-    magnet_kick_n<N, FRZ>(P, b, 1.0);
+    // the kick (magnet_kick_n with kick_weight 1; only the user coefficients are set here).
+    // The Horner sums are kept: for chi == 1 they ARE the sums of the field evaluation below
+    // (same coefficients, x and y do not move in a thin kick, 0.5 * (x + x) == x).
+    double um[N], un[N];
+    XTB_LANES { um[k] = 0.;  un[k] = 0.; }
+    if (b.has_user()) {
+        const double* __restrict__ cu = b.cu();
+        const int ou = b.order_user();
+        XTB_LANES {
+            const double x = P[k].x, y = P[k].y, chi = P[k].chi;
+            switch (ou) {           // (uniform: the op's)
+            case 0: horner_kick_c<0>(x, y, chi, cu, um[k], un[k]);  break;
+            case 1: horner_kick_c<1>(x, y, chi, cu, um[k], un[k]);  break;
+            case 2: horner_kick_c<2>(x, y, chi, cu, um[k], un[k]);  break;
+            default: horner_kick(x, y, chi, cu, ou, um[k], un[k]);  break;
+            }
+            P[k].px += 1.0 * (-um[k]);
+            P[k].py += 1.0 * un[k];
+        }
+    }
+    magnet_kick_curv_n<N, FRZ>(P, b, 1.0);
     if (!(b.radiation_flag() && length > 0)) return;
 
     // field at the mean position (x, y do not move in a thin kick): evaluate_field_from_strengths
@@ -1037,9 +1067,10 @@ __device__ __forceinline__ void thin_rad_kick_run(PState (&P)[N], const bool (&l
     {
         const double rlen = 1. / length;
         XTB_LANES {
-            double m = 0., n = 0.;
-            if (b.has_user()) horner_kick(0.5 * (P[k].x + P[k].x), 0.5 * (P[k].y + P[k].y), 1., b.cu(),
-                                          b.order_user(), m, n);
+            double m = um[k], n = un[k];
+            if (b.has_user() && P[k].chi != 1.0)
+                horner_kick(0.5 * (P[k].x + P[k].x), 0.5 * (P[k].y + P[k].y), 1., b.cu(),
+                            b.order_user(), m, n);
             const double dpx = (-m + -0.) + 0.;           // dpx_mul + dpx_main + dpx_rel
             const double dpy = (n + 0.) + 0.;
             Bx[k] = div_by(dpy * r.brho[k], length, rlen);        // Bx_T = dpy * brho_0 / length

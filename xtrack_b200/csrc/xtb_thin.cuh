@@ -86,6 +86,22 @@ __device__ __forceinline__ void horner_kick(const double x, const double y, cons
     }
 }
 
+// (the same with the order known at compile time: no loop counter, no address arithmetic)
+template <int ORDER>
+__device__ __forceinline__ void horner_kick_c(const double x, const double y, const double chi,
+                                              const double* __restrict__ c, double& dpx_mul,
+                                              double& dpy_mul) {
+    dpx_mul = chi * c[0];
+    dpy_mul = chi * c[1];
+#pragma unroll
+    for (int i = 1; i <= ORDER; ++i) {
+        const double zre = dpx_mul * x - dpy_mul * y;
+        const double zim = dpx_mul * y + dpy_mul * x;
+        dpx_mul = chi * c[2 * i] + zre;
+        dpy_mul = chi * c[2 * i + 1] + zim;
+    }
+}
+
 // Thin multipole without curvature: Multipole (model -1) of multipole.h:16-75
 // -> track_magnet_kick_single_particle, track_magnet_kick.h:24-144, with
 // hxl == 0 and all-zero knl_rel / main strengths (their kicks are exact zeros).
