@@ -78,7 +78,10 @@ def load():
         got = int(lib.xtb_ops_abi_version())
     except AttributeError:
         got = None
-    if got != lowering.OPS_ABI_VERSION:
+    # (XTB_LIB_ABI_OVERRIDE: A/B sessions that load an OLDER build as a tuning variant beside the
+    # product library, when the format change between the two is known not to matter to it)
+    if got != lowering.OPS_ABI_VERSION and not (
+            _build.SUFFIX and os.environ.get('XTB_LIB_ABI_OVERRIDE') == str(got)):
         raise XtbError(f'{_build.LIB} interprets op-stream format {got}, the host lowering '
                        f'emits {lowering.OPS_ABI_VERSION}: rebuild with `python -m xtrack_b200.build -f`')
     lib.xtb_lattice_create.argtypes = [ct.c_void_p, ct.c_size_t, ct.c_void_p,

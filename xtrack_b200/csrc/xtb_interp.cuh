@@ -1012,21 +1012,20 @@ static __device__ __noinline__ void xtb_run_heavy(const xtb_tile_t tb, XtbLanes<
             const uint32_t fop = op & ~(uint32_t) XTB_OPBIT_DRIFT;
             const double* __restrict__ c = reinterpret_cast<const double*>(xtb_tile_ptr(tb, off + 2));
             const uint32_t order = (uint32_t) (hw.x >> 32);
-#pragma unroll
-            for (int k = 0; k < NPT; ++k) {
-                switch (fop) {
-                case XTB_OP_MULT0: { const double cc[2] = {c[0], c[1]};  mult_kick_c<0, false>(T[k], cc);  break; }
-                case XTB_OP_MULT1: { const double cc[4] = {c[0], c[1], c[2], c[3]};  mult_kick_c<1, false>(T[k], cc);  break; }
-                case XTB_OP_MULTN: mult_kick(T[k], c, (int) order);  break;
-                case XTB_OP_MULTPN: mult_kick_pn<false>(T[k], c[0], order);  break;
-                case XTB_OP_MULTP1: mult_kick_p1<false>(T[k], c[0]);  break;
-                case XTB_OP_MULTH0: mult_kick_h0<FRZ, false>(T[k], c[0], c[1], c[2], c[3]);  break;
-                case XTB_OP_MULTH0N: mult_kick_h0n<FRZ, false>(T[k], c[0], c[1], c[2]);  break;
-                case XTB_OP_MULTH1N: mult_kick_h1n<FRZ, false>(T[k], c[0], c[1], c[2], c[3], c[4]);  break;
-                case XTB_OP_EDGE: edge_linear_c<false>(T[k], c[0], c[1]);  break;
-                default: break;      // XTB_OP_NOP
-                }
+#define XTB_EACH_LANE _Pragma("unroll") for (int k = 0; k < NPT; ++k)
+            switch (fop) {           // (one decode for all lanes)
+            case XTB_OP_MULT0: { const double cc[2] = {c[0], c[1]};  XTB_EACH_LANE mult_kick_c<0, false>(T[k], cc);  break; }
+            case XTB_OP_MULT1: { const double cc[4] = {c[0], c[1], c[2], c[3]};  XTB_EACH_LANE mult_kick_c<1, false>(T[k], cc);  break; }
+            case XTB_OP_MULTN: XTB_EACH_LANE mult_kick(T[k], c, (int) order);  break;
+            case XTB_OP_MULTPN: XTB_EACH_LANE mult_kick_pn<false>(T[k], c[0], order);  break;
+            case XTB_OP_MULTP1: XTB_EACH_LANE mult_kick_p1<false>(T[k], c[0]);  break;
+            case XTB_OP_MULTH0: XTB_EACH_LANE mult_kick_h0<FRZ, false>(T[k], c[0], c[1], c[2], c[3]);  break;
+            case XTB_OP_MULTH0N: XTB_EACH_LANE mult_kick_h0n<FRZ, false>(T[k], c[0], c[1], c[2]);  break;
+            case XTB_OP_MULTH1N: XTB_EACH_LANE mult_kick_h1n<FRZ, false>(T[k], c[0], c[1], c[2], c[3], c[4]);  break;
+            case XTB_OP_EDGE: XTB_EACH_LANE edge_linear_c<false>(T[k], c[0], c[1]);  break;
+            default: break;      // XTB_OP_NOP
             }
+#undef XTB_EACH_LANE
             eidx += 1;               // (these ops cannot lose a particle)
         } else {
             break;

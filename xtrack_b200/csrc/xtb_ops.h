@@ -50,7 +50,7 @@
  * layout changes; xtrack_b200/lowering.py carries the same number (OPS_ABI_VERSION) and
  * _cabi.load() refuses a library whose xtb_ops_abi_version() differs: a stale libxtb200.so
  * cannot silently interpret a newer program. */
-#define XTB_OPS_ABI_VERSION 5
+#define XTB_OPS_ABI_VERSION 6
 
 #define XTB_F_START   0x01u
 #define XTB_F_END     0x02u

@@ -375,7 +375,7 @@ __device__ __forceinline__ void magnet_drift_n(PState (&P)[N], const double leng
 
 // ------------------------------------------------------------ body params ----
 // OP_MAGNET_BODY parameter block (lowering.py::_lower_magnet):
-//  q[0] length  q[1] k0_drift  q[2] k1_drift  q[3] h_drift  q[4] h_kick  q[5] hxl
+//  q[0] length  q[1] k0_drift (kick-only bodies: 1 / length)  q[2] k1_drift  q[3] h_drift  q[4] h_kick  q[5] hxl
 //  q[6] A0 = k0_h_correction*length + k0l   q[7] A1 = k1_h_correction*length + k1l
 //  q[8] htot    q[9] (int) order_user | order_rel << 32
 //  q[10..17] k0_tot k1_tot k2 k3 k0s k1s k2s k3s   (field evaluation for radiation)
@@ -1065,7 +1065,7 @@ __device__ __forceinline__ void thin_rad_kick_run(PState (&P)[N], const bool (&l
     // with the user coefficients; the main and relative sets are all zero here
     double Bx[N], By[N], t0[N], t1[N];
     {
-        const double rlen = 1. / length;
+        const double rlen = b.q[1];          // RN(1 / length), folded by the host lowering
         XTB_LANES {
             double m = um[k], n = un[k];
             if (b.has_user() && P[k].chi != 1.0)

@@ -27,7 +27,7 @@ import math
 import numpy as np
 
 # ---- opcodes / flags: mirror of csrc/xtb_ops.h ----------------------------
-OPS_ABI_VERSION = 5          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
+OPS_ABI_VERSION = 6          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
 F_START, F_END, F_GLOBAL, F_DRIFT = 0x01, 0x02, 0x04, 0x08
 
 # fast set (fused program only): one whole element per op
@@ -822,7 +822,11 @@ def _lower_magnet(prog, cfg, *, weight, length, order, inv_factorial_order, knl,
             orl = len(coeffs_rel) // 2 - 1
             trig, n_inner = _trig_table(c['drift_model'], integrator, num_multipole_kicks,
                                         drift_only, core_length, c['h_drift'])
-            params = [core_length, c['k0_drift'], c['k1_drift'], c['h_drift'], c['h_kick'], hxl,
+            # (a kick-only body has no drift map: the slot of k0_drift carries RN(1 / length),
+            # which the radiating thin kick divides by -- xtb_thick.cuh::thin_rad_kick_run)
+            inv_length = (1.0 / core_length) if (c['drift_model'] == -1 and core_length != 0.0) else None
+            params = [core_length, c['k0_drift'] if inv_length is None else inv_length,
+                      c['k1_drift'], c['h_drift'], c['h_kick'], hxl,
                       a0, a1, htot, _RawWord(ou | (orl << 32)),
                       c['k0_drift'] + c['k0_kick'], c['k1_drift'] + c['k1_kick'], k2, k3,
                       k0s, k1s, k2s, k3s,
