@@ -25,14 +25,15 @@ PY
 }
 NMAX=$(nvidia-smi -L | wc -l)
 if [ $NMAX -ge 8 ]; then
-  for n in 1 2 4 8; do
+  # (N = 1, 2 were measured on smaller allocations: profiles/r02_bench_exact.json, *_n2.json)
+  for n in 4 8; do
     run strong_n$n $n --scaling strong --particles 1000000 --steps 3 --warmup 3 --no-cpu-baseline
   done
-  run weak_n8 8 --steps 3 --warmup 3 --cpu-seconds 6
+  run weak_n8 8 --steps 3 --warmup 3 --no-cpu-baseline
 else
   run strong_n$NMAX $NMAX --scaling strong --particles 1000000 --steps 3 --warmup 3 --no-cpu-baseline
   run weak_n$NMAX $NMAX --steps 3 --warmup 3 --cpu-seconds 6
 fi
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NMAX --master-addr 127.0.0.1 --master-port 29599 \
-    bench.py --impl reference --gpus $NMAX --steps 2 --warmup 1 --cpu-seconds 6 > $OUT/ref_n$NMAX.json 2> $OUT/ref_n$NMAX.err
+    bench.py --impl reference --gpus $NMAX --steps 1 --warmup 1 --cpu-seconds 4 > $OUT/ref_n$NMAX.json 2> $OUT/ref_n$NMAX.err
 cut -c1-400 $OUT/ref_n$NMAX.json
