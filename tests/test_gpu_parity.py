@@ -413,12 +413,20 @@ def test_losses_in_thick_lattice_gpu():
                        & (got['at_element'] == ref['at_element']))
         print('exact' if exact else 'fma', 'lost', n_lost, 'identical loss records', frac)
         assert frac >= 0.9995, frac
+        if exact:
+            # glibc's sin / cos / sinh / cosh on the device (csrc/xtb_libm.cuh), IEEE division
+            # and square root: the reference to the bit, lost particles included
+            assert frac == 1.0
+            for ff in common.COORDS:
+                assert np.array_equal(got[ff], ref[ff]), ff
+            continue
         lost = ref['state'] <= 0
         ok = lost & (got['at_element'] == ref['at_element']) & (got['at_turn'] == ref['at_turn'])
         # a beam this wide (4 x the sigmas of the parity test, up to the aperture) sits in the
         # non-linear fields: the libm sensitivity is larger and scatters from particle to
         # particle, one noise realisation underestimates it (measured: 7e-11 in x against a
-        # yardstick of 1.6e-11) -- floor of 1e-9 here, the loss records above are the point
+        # yardstick of 1.6e-11) -- floor of 1e-9 for the FMA variant (another rounding by
+        # construction), the loss records above are the point
         common.assert_parity(got, ref, yard, exact, mask=ok, label='lep lost', floor=1e-9)
         common.assert_parity(got, ref, yard, exact, mask=~lost & (got['state'] > 0),
                              label='lep alive', floor=1e-9)
