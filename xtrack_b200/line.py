@@ -287,6 +287,14 @@ class Line:
         self.config['XTRACK_MULTIPOLE_NO_SYNRAD'] = (model is None)
         self._invalidate()
 
+    def compensate_radiation_energy_loss(self, delta0='zero_mean', rtol_eneloss=1e-12,
+                                         max_iter=100, verbose=True, **kwargs):
+        """line.py `compensate_radiation_energy_loss` -> tapering.py:9-159 (see tapering.py)."""
+        from . import tapering
+        return tapering.compensate_radiation_energy_loss(
+            self, delta0=delta0, rtol_eneloss=rtol_eneloss, max_iter=max_iter, verbose=verbose,
+            **kwargs)
+
     def _invalidate(self):
         self.tracker = None
 
