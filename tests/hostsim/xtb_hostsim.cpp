@@ -164,6 +164,14 @@ extern "C" int xtb_hostsim_track(const uint64_t* words, const uint32_t* elem_off
     a.ignore_local = (int32_t) ((track_flags >> XTB_FLAG_IGNORE_LOCAL_APERTURE) & 1);
     a.kill_cavity_kick = (int32_t) ((track_flags >> XTB_FLAG_KILL_CAVITY_KICK) & 1);
     a.rng_philox = (variant & XTB_VARIANT_PHILOX) ? 1 : 0;
+    a.aperture_prefilter = 0;
+    for (size_t pc = 0; pc + 2 < image.size();) {            // as xtb_api.cu::program_prepare
+        const uint32_t hx = (uint32_t) image[pc], opx = hx & 0xffu;
+        if (opx == XTB_OP_END) break;
+        if (opx < XTB_GENERIC_FIRST && ((opx & ~(uint32_t) XTB_OPBIT_DRIFT) == XTB_OP_RECT || (opx & ~(uint32_t) XTB_OPBIT_DRIFT) == XTB_OP_ELLIPSE))
+            a.aperture_prefilter = 1;
+        pc += hx >> 16;
+    }
     a.synrad_tables = g_synrad_tables;
     a.line_length = line_length;
     a.global_xy_limit = global_xy_limit;

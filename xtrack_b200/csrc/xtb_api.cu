@@ -44,6 +44,7 @@ struct xtb_program {
     bool has_beam_mon = false;     // XTB_OP_BEAM_MON / XTB_OP_BEAM_PROFILE present
     bool has_quantum = false;      // a magnet body with radiation_flag 2 / 3 (random emission)
     bool has_qk = false;           // radiation_flag 3: needs the inverse-CDF tables
+    bool has_fast_aperture = false;    // XTB_OP_RECT / XTB_OP_ELLIPSE (with or without drift prefix)
     uint64_t* d_prog = nullptr;          // IMAGE: tile k = its ops + one XTB_OP_END op (2 words)
     uint32_t* d_tile_off = nullptr;      // image offsets [n_tiles + 1]
     std::vector<uint32_t> elem_offset;   // host copy [n_elements + 1], XTB_NOT_ADDRESSABLE allowed
@@ -93,6 +94,8 @@ static int program_prepare(xtb_program& G, const uint64_t* words, size_t n_words
             const uint32_t op = (uint32_t) (h & 0xffu);
             if (nw < 2 || (nw & 1u) || pc + nw > w1) return fail(XTB_E_INVALID, "malformed op in program");
             if (op >= XTB_HEAVY_FIRST) G.has_heavy = true;
+            if (op < XTB_GENERIC_FIRST && ((op & ~(uint32_t) XTB_OPBIT_DRIFT) == XTB_OP_RECT || (op & ~(uint32_t) XTB_OPBIT_DRIFT) == XTB_OP_ELLIPSE))
+                G.has_fast_aperture = true;
             if (op == XTB_OP_BEAM_MON || op == XTB_OP_BEAM_PROFILE || op == XTB_OP_BEAM_STATS) G.has_beam_mon = true;
             if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) >= 2u) G.has_quantum = true;
             if (op == XTB_OP_MAGNET_BODY && (((uint32_t) (h >> 32) >> 10) & 3u) == 3u) G.has_qk = true;
@@ -295,6 +298,7 @@ extern "C" int xtb_track(xtb_lattice_handle L, const xtb_particles_t* particles,
     a.ignore_local = (int32_t) ((track_flags >> XTB_FLAG_IGNORE_LOCAL_APERTURE) & 1);
     a.kill_cavity_kick = (int32_t) ((track_flags >> XTB_FLAG_KILL_CAVITY_KICK) & 1);
     a.rng_philox = (variant_flags & XTB_VARIANT_PHILOX) ? 1 : 0;
+    a.aperture_prefilter = G->has_fast_aperture ? 1 : 0;
     a.line_length = L->line_length;
     a.global_xy_limit = global_xy_limit;
     a.synrad_tables = L->d_synrad_tables;

@@ -50,7 +50,7 @@
  * layout changes; xtrack_b200/lowering.py carries the same number (OPS_ABI_VERSION) and
  * _cabi.load() refuses a library whose xtb_ops_abi_version() differs: a stale libxtb200.so
  * cannot silently interpret a newer program. */
-#define XTB_OPS_ABI_VERSION 6
+#define XTB_OPS_ABI_VERSION 7
 
 #define XTB_F_START   0x01u
 #define XTB_F_END     0x02u
@@ -68,6 +68,8 @@
 #define XTB_OP_EDGE           6   /* [r21, r43]            track_dipole_edge_linear.h:30-39  */
 #define XTB_OP_RECT           7   /* [min_x, max_x, min_y, max_y]        limitrect.h:10-38   */
 #define XTB_OP_ELLIPSE        8   /* [a_squ, b_squ, a_b_squ, 0]          limitellipse.h:13   */
+/* RECT, ELLIPSE: aux = (tx16 << 16) | ty16, the high 16 bits of the high words of two lengths
+ * with "|x| < tx and |y| < ty => inside": an integer pre-filter in front of the exact test */
 #define XTB_OP_FDRIFT         9   /* [L, 0]  a Drift element as main op (+ global check)    */
 #define XTB_OP_MULTP1        10   /* [cn_1, 0]  plain normal quadrupole kick (cs_1 = c_0 = 0)  */
 #define XTB_OP_MULTH0N       11   /* [hl, B0, cn_0, 0]     MULTH0 with cs_0 == 0               */

@@ -36,6 +36,7 @@ struct XtbTrackArgs {
     int32_t flag_end_turn_actions, flag_reset_s, flag_monitor;
     int32_t ignore_global, ignore_local, kill_cavity_kick;
     int32_t rng_philox;          // the particles' generator state is (key, counter) of Philox4x32-10
+    int32_t aperture_prefilter;  // the program holds fast aperture ops (RECT / ELLIPSE)
     double line_length;
     double global_xy_limit;
     const double* synrad_tables; // quantum-kick model: inverse-CDF tables (xtb_thick.cuh::QkTables)

@@ -27,7 +27,7 @@ import math
 import numpy as np
 
 # ---- opcodes / flags: mirror of csrc/xtb_ops.h ----------------------------
-OPS_ABI_VERSION = 6          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
+OPS_ABI_VERSION = 7          # XTB_OPS_ABI_VERSION: _cabi.load() checks the library against it
 F_START, F_END, F_GLOBAL, F_DRIFT = 0x01, 0x02, 0x04, 0x08
 
 # fast set (fused program only): one whole element per op
@@ -228,9 +228,14 @@ class Program:
         if opcode == OP_EDGE_LIN:
             return FOP_EDGE, params[:2], 0
         if opcode == OP_LIMIT_RECT:
-            return FOP_RECT, params[:4], 0
+            min_x, max_x, min_y, max_y = params[:4]
+            tx = min(-min_x, max_x) if (min_x < 0 < max_x) else 0.0
+            ty = min(-min_y, max_y) if (min_y < 0 < max_y) else 0.0
+            return FOP_RECT, params[:4], _inside_for_sure(tx, ty)
         if opcode == OP_LIMIT_ELLIPSE:
-            return FOP_ELLIPSE, params[:3], 0
+            a_squ, b_squ = params[:2]
+            # |x| < 0.7 a and |y| < 0.7 b: x^2 / a^2 + y^2 / b^2 < 0.98
+            return FOP_ELLIPSE, params[:3], _inside_for_sure(0.7 * math.sqrt(a_squ), 0.7 * math.sqrt(b_squ))
         return None
 
     def finish(self, fused=False):
@@ -281,6 +286,18 @@ class Program:
                 self._emit(words, FOP_FDRIFT, 0, 0, [pending[0]])
         offsets.append(len(words))
         return (np.array(words, dtype=np.uint64), np.array(offsets, dtype=np.uint32))
+
+
+def _inside_for_sure(tx, ty):
+    """aux word of the fast aperture ops: a particle with |x| < tx and |y| < ty is inside the
+    aperture for sure.  The kernel compares the HIGH 32-bit words of |x|, |y| (integers: no
+    FP64 instruction) with the high 16 bits of those of tx, ty rounded DOWN (packed x: bits
+    31-16, y: bits 15-0); 0 = no such box, every particle takes the exact test."""
+    def hi16(tt):
+        if not (tt > 0.0) or not math.isfinite(tt):
+            return 0
+        return int(np.float64(tt).view(np.uint64) >> np.uint64(48)) & 0x7fff
+    return (hi16(tx) << 16) | hi16(ty)
 
 
 class _RawWord:
