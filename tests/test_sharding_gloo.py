@@ -40,9 +40,14 @@ def _worker(rank, world, port, n_total, turns, out_dir):
     lost = p.get('state') <= 0
     hist = torch.from_numpy(np.bincount(p.get('at_element')[lost], minlength=len(line) + 1))
     sharding.all_reduce_histogram(hist)
+    lost_all = sharding.gather_lost_particles(p, dst=0)
     if rank == 0:
         np.save(os.path.join(out_dir, 'stats.npy'), stats.numpy())
         np.save(os.path.join(out_dir, 'hist.npy'), hist.numpy())
+        np.savez(os.path.join(out_dir, 'lost.npz'), **{nn: lost_all.get(nn) for nn in
+                 ('particle_id', 'state', 'at_element', 'at_turn', 'x', 'y', 's')})
+    else:
+        assert lost_all is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,6 +76,12 @@ def test_two_ranks_equal_one(tmp_path):
     np.testing.assert_allclose(stats[2:], ref[2:], rtol=1e-12, atol=1e-18)
     lost = full.get('state') <= 0
     assert np.array_equal(hist, np.bincount(full.get('at_element')[lost], minlength=len(line) + 1))
+    # the lost-particle records gathered on rank 0 are those of the single run
+    got = np.load(tmp_path / 'lost.npz')
+    one = sharding.lost_particles(full)
+    assert len(got['particle_id']) == int(ref[1]) and np.all(np.diff(got['particle_id']) > 0)
+    for nn in ('particle_id', 'state', 'at_element', 'at_turn', 'x', 'y', 's'):
+        assert np.array_equal(got[nn], one.get(nn)), nn
     bs = sharding.beam_statistics(stats)
     assert bs['n_alive'] + bs['n_lost'] == n_total
     assert 0 < bs['sigma']['x'] < 2e-2

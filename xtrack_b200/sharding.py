@@ -71,3 +71,34 @@ def partial_stats_host(particles):
             out[kk] = (vv[ii] * vv[jj]).sum()
             kk += 1
     return out
+
+
+def lost_particles(particles):
+    """The lost particles of `particles` (state <= 0, allocated slots) as a host `Particles`,
+    ordered by particle_id: where (`at_element`, `s` -- refined or not), when (`at_turn`) and
+    with which coordinates each of them stopped.  `to_dict()` / `to_pandas()` give the record."""
+    from .particles import LAST_INVALID_STATE
+    host = particles.copy(_device='cpu')
+    st = host.get('state')
+    keep = (st <= 0) & (st > LAST_INVALID_STATE)
+    out = host.filter(keep)
+    out.sort(by='particle_id', interleave_lost_particles=True)
+    return out
+
+
+def gather_lost_particles(particles, dst=0):
+    """The lost particles of ALL ranks on rank `dst` (a host `Particles` ordered by particle_id;
+    None on the other ranks): the optional end-of-run gather of SURVEY.md section 8(e).  Only the lost
+    ones travel -- a few KB for a dynamic-aperture run."""
+    from .particles import Particles
+    mine = lost_particles(particles)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return mine
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, mine.to_dict())
+    if dist.get_rank() != dst:
+        return None
+    merged = Particles.merge([Particles.from_dict(dd) for dd in parts if len(dd['state']) > 0]
+                             or [mine])
+    merged.sort(by='particle_id', interleave_lost_particles=True)
+    return merged
