@@ -146,44 +146,42 @@ class LossLocationRefinement:
 
 
 # ---- what lies between two apertures (:211-281) --------------------------------------------
+_FRAME_FIELDS = {'SRotation': ('angle',), 'Rotation': ('rot_s_rad', 'rot_x_rad', 'rot_y_rad'),
+                 'Translation': ('shift_x', 'shift_y'), 'XYShift': ('dx', 'dy')}
+
+
 def check_for_active_shifts_and_rotations(line, i_aper_0, i_aper_1):
+    """Is there a frame element that actually moves the frame between the two apertures?"""
     for ii in range(i_aper_0, i_aper_1):
         ee = _resolve(line[ii], line)
-        name = type(ee).__name__
-        if name == 'SRotation' and not np.isclose(ee.angle, 0, rtol=0, atol=1e-15):
-            return True
-        if name == 'Rotation' and not np.allclose(
-                [ee.rot_s_rad, ee.rot_x_rad, ee.rot_y_rad], 0, rtol=0, atol=1e-15):
-            return True
-        if name == 'Translation' and not np.allclose([ee.shift_x, ee.shift_y], 0, rtol=0, atol=1e-15):
-            return True
-        if name == 'XYShift' and not np.allclose([ee.dx, ee.dy], 0, rtol=0, atol=1e-15):
-            return True
+        for ff in _FRAME_FIELDS.get(type(ee).__name__, ()):
+            if abs(getattr(ee, ff)) > 1e-15:
+                return True
     return False
 
 
 def fields_equal(a, b, atol=1e-15):
+    """Equality of two element fields to `atol` (scalars, arrays, sequences of them)."""
     if a is b:
         return True
     if type(a) is not type(b):
         return False
-    if isinstance(a, np.ndarray):
-        return a.shape == b.shape and np.allclose(a, b, rtol=0, atol=atol)
-    if np.isscalar(a):
-        return abs(a - b) <= atol
     if isinstance(a, (list, tuple)):
         return len(a) == len(b) and all(fields_equal(x, y, atol) for x, y in zip(a, b))
+    if isinstance(a, np.ndarray) or np.isscalar(a):
+        aa, bb = np.asarray(a), np.asarray(b)
+        if aa.dtype.kind in 'fiub' and bb.dtype.kind in 'fiub':
+            return aa.shape == bb.shape and bool(np.all(np.abs(aa - bb) <= atol))
+        return aa.shape == bb.shape and bool(np.all(aa == bb))
     return a == b
 
 
 def apertures_are_identical(aper1, aper2, line):
     aper1, aper2 = _resolve(aper1, line), _resolve(aper2, line)
-    if aper1.__class__ != aper2.__class__:
+    if type(aper1) is not type(aper2):
         return False
     d1, d2 = aper1.to_dict(), aper2.to_dict()
-    if set(d1) != set(d2):
-        return False
-    return all(fields_equal(d1[kk], d2[kk]) for kk in d1)
+    return set(d1) == set(d2) and all(fields_equal(d1[kk], d2[kk]) for kk in d1)
 
 
 def find_apertures(line):
@@ -436,52 +434,52 @@ def polygon_impact_from_origin(x_vertices, y_vertices, theta):
     return t_hit * dx[:, 0], t_hit * dy[:, 0]
 
 
-def characterize_aperture(line, i_aperture, n_theta, r_max, dr, coming_from='upstream'):
-    """The aperture `i_aperture` together with the thin transformations around it, as a convex
-    polygon with a vertex at each of `n_theta` angles: probe particles on a polar grid are
-    tracked through the thin elements from the adjacent thick element to the aperture
-    (backwards for `coming_from='downstream'`), first on a coarse radial grid up to `r_max`,
-    then with step `dr` around the radius where each angle was stopped."""
-    assert coming_from in ('upstream', 'downstream')
-    if coming_from == 'upstream':
-        i_start = find_adjacent_thick(line, i_aperture, 'upstream') + 1
-        i_stop = i_aperture + 1
-        backtrack = False
-        index_start_thin = i_start
-    else:
-        i_stop = find_adjacent_thick(line, i_aperture, 'downstream')
-        i_start = i_aperture
-        backtrack = 'force'
-        assert all(_has_backtrack(line[ii], line) for ii in range(i_start, min(i_stop + 1, len(line))))
-        index_start_thin = i_stop - 1
+def _first_stopped_radius(line, theta, r_from, r_grid, track_kw):
+    """Probe particles at the radii `r_from[j] + r_grid[i]` along every angle `theta[j]`, tracked
+    through the aperture: per angle, the index of the first grid radius that is stopped and
+    the probes' coordinates (arrays [angle, radius])."""
+    rr = r_from[:, None] + r_grid[None, :]
+    xx, yy = rr * np.cos(theta)[:, None], rr * np.sin(theta)[:, None]
+    logger.info(f'aperture scan: {xx.size} probe particles')
+    probes = Particles(p0c=1, x=xx.ravel().copy(), y=yy.ravel().copy(), _device=line.tracker.device)
+    with _preserve_track_flags(line):
+        line.track_flags['XS_FLAG_IGNORE_GLOBAL_APERTURE'] = True
+        line.track(probes, **track_kw)
+    by_id = np.argsort(probes.get('particle_id'), kind='stable')
+    passed = probes.get('state')[by_id].reshape(rr.shape) > 0
+    return np.argmin(passed, axis=1), xx, yy
 
-    theta_vect = np.linspace(0, 2 * np.pi, n_theta + 1)[:-1]
-    this_rmin, this_rmax = 0.0, r_max
-    this_dr = (this_rmax - this_rmin) / 100.
-    rmin_theta = 0 * theta_vect
-    for iteration in range(2):
-        r_vect = np.arange(this_rmin, this_rmax, this_dr)
-        RR, TT = np.meshgrid(r_vect, theta_vect)
-        RR = RR + np.atleast_2d(rmin_theta).T
-        x_test = RR.flatten() * np.cos(TT.flatten())
-        y_test = RR.flatten() * np.sin(TT.flatten())
-        logger.info(f'iteration={iteration} num_part={x_test.shape[0]}')
-        ptest = Particles(p0c=1, x=x_test.copy(), y=y_test.copy(), _device=line.tracker.device)
-        with _preserve_track_flags(line):
-            line.track_flags['XS_FLAG_IGNORE_GLOBAL_APERTURE'] = True
-            line.track(ptest, ele_start=i_start, ele_stop=i_stop, backtrack=backtrack)
-        order = np.argsort(ptest.get('particle_id'), kind='stable')
-        state_mat = ptest.get('state')[order].reshape(RR.shape)
-        i_r_aper = np.argmin(state_mat > 0, axis=1)
-        rmin_theta = r_vect[i_r_aper - 1]
-        this_rmin = 0
-        this_rmax = 2 * this_dr
-        this_dr = dr
-    x_mat = x_test.reshape(RR.shape)
-    y_mat = y_test.reshape(RR.shape)
-    x_nc = np.array([x_mat[itt, i_r_aper[itt]] for itt in range(n_theta)])
-    y_nc = np.array([y_mat[itt, i_r_aper[itt]] for itt in range(n_theta)])
-    x_hull, y_hull = _convex_hull_in_order(x_nc, y_nc)
-    # a convex polygon with a vertex at every requested angle
-    xv, yv = polygon_impact_from_origin(x_hull, y_hull, theta_vect)
+
+def characterize_aperture(line, i_aperture, n_theta, r_max, dr, coming_from='upstream'):
+    """The aperture `i_aperture` together with the thin transformations around it, as the beam
+    sees it: a convex polygon with a vertex at each of `n_theta` angles.  Probe particles on a
+    polar grid go through the thin elements between the adjacent thick element and the aperture
+    (backwards for `coming_from='downstream'`) -- a coarse radial scan up to `r_max` in a
+    hundred steps, then one with step `dr` over the two coarse steps around the radius where each
+    angle was stopped (:570-658 of the reference's module: same grids, same polygon)."""
+    if coming_from == 'upstream':
+        first = find_adjacent_thick(line, i_aperture, 'upstream') + 1
+        track_kw = dict(ele_start=first, ele_stop=i_aperture + 1, backtrack=False)
+        index_start_thin = first
+    elif coming_from == 'downstream':
+        last = find_adjacent_thick(line, i_aperture, 'downstream')
+        for ii in range(i_aperture, min(last + 1, len(line))):
+            if not _has_backtrack(line[ii], line):
+                raise TypeError(f'Cannot backtrack through element {line.element_names[ii]}')
+        track_kw = dict(ele_start=i_aperture, ele_stop=last, backtrack='force')
+        index_start_thin = last - 1
+    else:
+        raise ValueError(f'Invalid direction: {coming_from}')
+
+    theta = np.linspace(0, 2 * np.pi, n_theta + 1)[:-1]
+    coarse_step = r_max / 100.
+    coarse = np.arange(0, r_max, coarse_step)
+    i_stop, _, _ = _first_stopped_radius(line, theta, np.zeros(n_theta), coarse, track_kw)
+    inner = coarse[i_stop - 1]                       # last coarse radius that passed
+    fine = np.arange(0, 2 * coarse_step, dr)
+    i_stop, xx, yy = _first_stopped_radius(line, theta, inner, fine, track_kw)
+    rows = np.arange(n_theta)
+    x_hull, y_hull = _convex_hull_in_order(xx[rows, i_stop], yy[rows, i_stop])
+    # the hull has no vertex at most angles: put one at every requested angle
+    xv, yv = polygon_impact_from_origin(x_hull, y_hull, theta)
     return _el.LimitPolygon(x_vertices=xv, y_vertices=yv), index_start_thin
